@@ -1,0 +1,29 @@
+# Builds libvo_b200.so (the CUDA hot path + its C ABI, sm_100a only) and the CPU oracle.
+# nvcc cross-compiles without a GPU.  The .so is built IN-TREE so it travels to the GPU box.
+NVCC ?= nvcc
+PKG := visual-odometry_b200
+CSRC := $(PKG)/csrc
+LIB := $(PKG)/lib/libvo_b200.so
+NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
+             -Xcompiler -fPIC,-Wall,-ffp-contract=off --expt-relaxed-constexpr
+SRCS := $(CSRC)/lib.cu $(CSRC)/nn.cu $(CSRC)/picp.cu $(CSRC)/triangulate.cu
+OBJS := $(SRCS:$(CSRC)/%.cu=build/%.o)
+HDRS := $(wildcard $(CSRC)/*.cuh) include/vo_b200.h
+
+all: $(LIB) oracle
+
+$(LIB): $(OBJS)
+	@mkdir -p $(dir $@)
+	$(NVCC) -shared -o $@ $(OBJS) -lcudart_static -lpthread -ldl -lrt
+
+build/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVCCFLAGS) -Xptxas -v -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -rf build $(LIB)
+	$(MAKE) -C oracle clean
+.PHONY: all oracle clean

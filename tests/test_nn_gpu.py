@@ -1,0 +1,185 @@
+"""GPU parity: vo_nn_* vs the oracle's bruteForceBestMatch — indices must be BIT-EXACT."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _vec11(app):
+    return np.concatenate([np.arange(len(app), dtype=np.float32)[:, None], app], axis=1)
+
+
+@pytest.fixture(scope="module")
+def bundled():
+    return np.load(os.path.join(HERE, "golden", "bundled_frames.npz"))
+
+
+def test_bundled_frames_match_id_truth_and_oracle(vo, oracle, bundled):
+    frames = list(bundled["frames"])
+    nn = vo.NNIndex(0)
+    for a, b in zip(frames[:-1], frames[1:]):
+        if b != a + 1:
+            continue
+        m, q = _vec11(bundled[f"app_{a}"]), _vec11(bundled[f"app_{b}"])
+        nn.set_map(m)
+        idx, d2 = nn.best_match(q, 0.1, want_d2=True)
+        pos = {int(v): i for i, v in enumerate(bundled[f"ids_{a}"])}
+        truth = np.array([pos.get(int(v), -1) for v in bundled[f"ids_{b}"]], np.int32)
+        oi, od = oracle.nn_best_match(m, q, 0.1)
+        assert np.array_equal(idx, truth)
+        assert np.array_equal(idx, oi)
+        assert np.array_equal(d2[idx >= 0], od[idx >= 0])
+    nn.close()
+
+
+@pytest.mark.parametrize("M,Q", [(1, 1), (127, 124), (128, 129), (1000, 257), (5000, 3000),
+                                 (20000, 9000), (100003, 2048)])
+def test_planted_random_vs_oracle(vo, oracle, synth, M, Q):
+    m = synth.nn_map_rows_np(0, M)
+    q, target = synth.nn_queries_np(Q, M)
+    nn = vo.NNIndex(0)
+    nn.set_map(m)
+    idx, d2 = nn.best_match(q, 0.1, want_d2=True)
+    nn.close()
+    oi, od = oracle.nn_best_match(m, q, 0.1)
+    assert np.array_equal(idx, oi)
+    hit = oi >= 0
+    assert np.array_equal(d2[hit], od[hit])
+    exact = (np.arange(Q) % 4) < 2
+    assert np.array_equal(idx[exact], target[exact])
+
+
+def test_large_radius_true_argmin(vo, oracle):
+    """radius large enough that EVERY row is a candidate: exercises the bound-tightening path."""
+    rng = np.random.RandomState(5)
+    m = rng.uniform(-1, 1, (3000, 11)).astype(np.float32)
+    q = rng.uniform(-1, 1, (700, 11)).astype(np.float32)
+    nn = vo.NNIndex(0)
+    nn.set_map(m)
+    for norm in (0.8, 2.0, 100.0):
+        idx, d2 = nn.best_match(q, norm, want_d2=True)
+        oi, od = oracle.nn_best_match(m, q, norm)
+        assert np.array_equal(idx, oi)
+        assert np.array_equal(d2[oi >= 0], od[oi >= 0])
+    nn.close()
+
+
+def test_ties_lowest_index_and_no_match_and_edge(vo, oracle):
+    rng = np.random.RandomState(3)
+    m = rng.uniform(-1, 1, (4096, 11)).astype(np.float32)
+    dup = rng.choice(2000, 64, replace=False)
+    m[2000 + np.arange(64)] = m[dup]      # 64 duplicate pairs
+    m[4000:4010] = m[dup[0]]              # and a 12-way tie
+    q = np.concatenate([m[dup], m[4000:4001], np.full((3, 11), 7.0, np.float32)])
+    nn = vo.NNIndex(0)
+    nn.set_map(m)
+    idx = nn.best_match(q, 0.1)
+    oi, _ = oracle.nn_best_match(m, q, 0.1)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(idx[:64], dup)
+    assert idx[64] == dup[0]
+    assert idx[-3:].tolist() == [-1, -1, -1]
+    # d2 exactly == norm^2 is NOT a match (strict '<', brute_force_search.h:35)
+    one = np.zeros((1, 11), np.float32)
+    qq = np.zeros((1, 11), np.float32)
+    qq[0, 1] = 0.5
+    nn.set_map(one)
+    assert nn.best_match(qq, 0.5).tolist() == [-1]
+    assert nn.best_match(qq, float(np.nextafter(np.float32(0.5), np.float32(1)))).tolist() == [0]
+    nn.close()
+
+
+def test_near_ties_within_rounding(vo, oracle):
+    """rows a few ulp apart around a query: the winner must follow the reference's summation
+    order, not the FMA filter's."""
+    rng = np.random.RandomState(9)
+    base = rng.uniform(-1, 1, 10).astype(np.float32)
+    rows = np.tile(base, (512, 1))
+    rows += (rng.randint(-3, 4, rows.shape) * np.float32(2.0 ** -24)).astype(np.float32)
+    m = _vec11(rows)
+    q = _vec11(np.tile(base, (64, 1)) + (rng.randint(-3, 4, (64, 10)) * np.float32(2.0 ** -23)).astype(np.float32))
+    nn = vo.NNIndex(0)
+    nn.set_map(m)
+    idx, d2 = nn.best_match(q, 0.1, want_d2=True)
+    nn.close()
+    oi, od = oracle.nn_best_match(m, q, 0.1)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(d2, od)
+
+
+def test_empty_inputs(vo):
+    nn = vo.NNIndex(0)
+    nn.set_map(np.zeros((0, 11), np.float32))
+    assert nn.best_match(np.zeros((5, 11), np.float32), 0.1).tolist() == [-1] * 5
+    nn.set_map(np.zeros((10, 11), np.float32))
+    assert nn.best_match(np.zeros((0, 11), np.float32), 0.1).shape == (0,)
+    nn.close()
+
+
+@pytest.mark.parametrize("dim", [2, 3, 5, 16])
+def test_general_dimension(vo, oracle, dim):
+    rng = np.random.RandomState(dim)
+    m = rng.uniform(-1, 1, (2000, dim + 1)).astype(np.float32)
+    q = np.concatenate([m[rng.choice(2000, 100)], rng.uniform(-1, 1, (100, dim + 1)).astype(np.float32)])
+    nn = vo.NNIndex(0)
+    nn.set_map(m)
+    idx, d2 = nn.best_match(q, 0.3, want_d2=True)
+    nn.close()
+    oi, od = oracle.nn_best_match(m, q, 0.3)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(d2[oi >= 0], od[oi >= 0])
+
+
+def test_radius_search(vo, oracle):
+    rng = np.random.RandomState(4)
+    m = rng.uniform(-0.3, 0.3, (3000, 11)).astype(np.float32)
+    q = rng.uniform(-0.3, 0.3, (37, 11)).astype(np.float32)
+    nn = vo.NNIndex(0)
+    nn.set_map(m)
+    counts, lst = nn.radius_search(q, 0.6, 256)
+    nn.close()
+    oc, ol = oracle.nn_radius_search(m, q, 0.6, 256)
+    assert np.array_equal(counts, oc)
+    for i in range(len(q)):
+        k = min(counts[i], 256)
+        assert np.array_equal(lst[i, :k], ol[i, :k])
+    got = vo.bruteForceSearch(m, q[0], 0.6)
+    assert np.array_equal(got, ol[0, :oc[0]])
+    assert vo.bruteForceBestMatch(m, q[0], 0.6) == oracle.nn_best_match(m, q[:1], 0.6)[0][0]
+
+
+def test_device_resident_path_and_linearity_at_scale(vo, synth):
+    """Full-size property test (oracle-free): 1e5 queries vs a 1e6-row device-generated map;
+    every exact planted copy must come back as its own row (or a lower-index duplicate at d2=0),
+    and answers must not depend on how the query batch is split."""
+    import torch
+
+    M, Q = 1_000_000, 100_000
+    dev = torch.device("cuda:0")
+    m = synth.nn_map_torch(M, dev)
+    qn, target = synth.nn_queries_np(Q, M)
+    q = torch.from_numpy(qn).to(dev)
+    idx = torch.empty(Q, dtype=torch.int32, device=dev)
+    d2 = torch.empty(Q, dtype=torch.float32, device=dev)
+    nn = vo.NNIndex(0)
+    nn.set_stream(torch.cuda.current_stream().cuda_stream)
+    nn.set_map_device(m.data_ptr(), M, 11, 1)
+    nn.best_match_device(q.data_ptr(), Q, 11, 0.1, idx.data_ptr(), d2.data_ptr())
+    torch.cuda.synchronize()
+    got = idx.cpu().numpy()
+    exact = (np.arange(Q) % 4) < 2
+    assert np.array_equal(got[exact], target[exact])
+    noisy = (np.arange(Q) % 4) == 2
+    assert np.array_equal(got[noisy], target[noisy])
+    assert np.all(got[(np.arange(Q) % 4) == 3] == -1)
+    # split invariance
+    idx2 = torch.empty(Q, dtype=torch.int32, device=dev)
+    h = Q // 3
+    nn.best_match_device(q.data_ptr(), h, 11, 0.1, idx2.data_ptr())
+    nn.best_match_device(q[h:].data_ptr(), Q - h, 11, 0.1, idx2[h:].data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(idx, idx2)
+    nn.close()

@@ -1,0 +1,722 @@
+// nn.cu — exact brute-force appearance nearest neighbour for sm_100a.
+//
+// Replaces bruteForceBestMatch / bruteForceSearch (reference include/brute_force_search.h:3-41)
+// and answers TreeNode_::bestMatchFull queries (include/eigen_kdtree.h:90-115) exactly.
+//
+// Design (DESIGN.md §NN has the full derivation):
+//   * set_map re-packs the caller's AoS rows [id | a0..a9] (44 B, the reference's Vector11f) into
+//     48-byte rows  [a0..a3][a4..a7][a8 a9 |a|^2 0]  so that a tile of TM rows is one contiguous,
+//     16-byte aligned block that a single 1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) stages
+//     into shared memory; STAGES tiles are in flight behind mbarriers.
+//   * the filter kernel keeps TQ queries per thread in registers as (-2*q_k) and evaluates, for
+//     every (query,row) pair,   acc = |m|^2 + sum_k (-2 q_k) m_k   = d^2 - |q|^2
+//     with 10 FFMA on the FP32 pipe (K=10 is too shallow for tensor cores) and one FMNMX that
+//     folds the row into a per-query running minimum.  Rows are broadcast LDS.128 reads.
+//   * a pair can only be the reference's answer if its d^2 (in the reference's own rounding
+//     order) is < bound; the FMA form differs from that by at most eps_q (proved in DESIGN.md), so
+//     after every tile a thread whose running minimum dips below (bound - |q|^2 + eps_q) re-scans
+//     that tile for that query, recomputes the candidate rows in the REFERENCE order with
+//     __fsub_rn/__fmul_rn/__fadd_rn (no contraction) and merges (d2_bits<<32 | row) into the
+//     query's 64-bit key with atomicMin — strict minimum, lowest row index on ties, exactly
+//     brute_force_search.h:30-40.  The bound then tightens to the best exact d^2 found, so the
+//     kernel is a correct argmin for any radius, not only small ones.
+//   * no float atomics, no data-dependent result: indices are bit-exact vs the oracle.
+#include <float.h>
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace vo {
+
+constexpr int NN_DIM = 10;            // fast-path dimension (Vector11f minus the id column)
+constexpr int NN_TM = 128;            // map rows per shared-memory tile
+constexpr int NN_STAGES = 4;          // TMA stages in flight
+constexpr int NN_ROW_BYTES = 48;      // packed row: 3 x float4
+constexpr uint32_t NN_TILE_BYTES = NN_TM * NN_ROW_BYTES;
+constexpr unsigned long long NN_KEY_NONE = 0xFFFFFFFFFFFFFFFFull;
+
+// ---- the reference's distance, one rounding per operation ---------------------------------
+// (p-q).tail(n).squaredNorm() under Eigen's SSE2 linear-vectorised redux; see oracle_sqdist.
+template <int DIM>
+__device__ __forceinline__ float ref_sqdist(const float (&m)[DIM], const float (&q)[DIM]) {
+  float s[DIM];
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) {
+    const float d = __fsub_rn(m[i], q[i]);
+    s[i] = __fmul_rn(d, d);
+  }
+  constexpr int n4 = (DIM / 4) * 4, n8 = (DIM / 8) * 8;
+  float r;
+  if (n4 > 0) {
+    float a[4] = {s[0], s[1], s[2], s[3]};
+    if (n4 > 4) {
+      float c[4] = {s[4], s[5], s[6], s[7]};
+#pragma unroll
+      for (int i = 8; i < n8; i += 8)
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          a[l] = __fadd_rn(a[l], s[i + l]);
+          c[l] = __fadd_rn(c[l], s[i + 4 + l]);
+        }
+#pragma unroll
+      for (int l = 0; l < 4; ++l) a[l] = __fadd_rn(a[l], c[l]);
+      if (n4 > n8)
+#pragma unroll
+        for (int l = 0; l < 4; ++l) a[l] = __fadd_rn(a[l], s[n8 + l]);
+    }
+    r = __fadd_rn(__fadd_rn(a[0], a[2]), __fadd_rn(a[1], a[3]));
+#pragma unroll
+    for (int i = n4; i < DIM; ++i) r = __fadd_rn(r, s[i]);
+  } else {
+    r = s[0];
+#pragma unroll
+    for (int i = 1; i < DIM; ++i) r = __fadd_rn(r, s[i]);
+  }
+  return r;
+}
+
+// run-time dimension version (general kernel)
+__device__ __forceinline__ float ref_sqdist_dyn(const float* __restrict__ m,
+                                                const float* __restrict__ q, int dim) {
+  const int n4 = (dim / 4) * 4, n8 = (dim / 8) * 8;
+  auto sq = [&](int i) {
+    const float d = __fsub_rn(m[i], q[i]);
+    return __fmul_rn(d, d);
+  };
+  float r;
+  if (n4 > 0) {
+    float a0 = sq(0), a1 = sq(1), a2 = sq(2), a3 = sq(3);
+    if (n4 > 4) {
+      float c0 = sq(4), c1 = sq(5), c2 = sq(6), c3 = sq(7);
+      for (int i = 8; i < n8; i += 8) {
+        a0 = __fadd_rn(a0, sq(i));
+        a1 = __fadd_rn(a1, sq(i + 1));
+        a2 = __fadd_rn(a2, sq(i + 2));
+        a3 = __fadd_rn(a3, sq(i + 3));
+        c0 = __fadd_rn(c0, sq(i + 4));
+        c1 = __fadd_rn(c1, sq(i + 5));
+        c2 = __fadd_rn(c2, sq(i + 6));
+        c3 = __fadd_rn(c3, sq(i + 7));
+      }
+      a0 = __fadd_rn(a0, c0);
+      a1 = __fadd_rn(a1, c1);
+      a2 = __fadd_rn(a2, c2);
+      a3 = __fadd_rn(a3, c3);
+      if (n4 > n8) {
+        a0 = __fadd_rn(a0, sq(n8));
+        a1 = __fadd_rn(a1, sq(n8 + 1));
+        a2 = __fadd_rn(a2, sq(n8 + 2));
+        a3 = __fadd_rn(a3, sq(n8 + 3));
+      }
+    }
+    r = __fadd_rn(__fadd_rn(a0, a2), __fadd_rn(a1, a3));
+    for (int i = n4; i < dim; ++i) r = __fadd_rn(r, sq(i));
+  } else {
+    r = sq(0);
+    for (int i = 1; i < dim; ++i) r = __fadd_rn(r, sq(i));
+  }
+  return r;
+}
+
+__device__ __forceinline__ unsigned long long nn_pack_key(float d2, uint32_t row) {
+  // d2 >= 0, so its bit pattern is monotone as an unsigned integer
+  return (static_cast<unsigned long long>(__float_as_uint(d2)) << 32) | row;
+}
+
+// ---- map re-pack ------------------------------------------------------------------------------
+// one thread per padded row; rows >= n_rows are neutral ( |m|^2 = +inf never passes the filter )
+__global__ void __launch_bounds__(256)
+nn_repack_kernel(const float* __restrict__ rows, int64_t n_rows, int64_t n_rows_padded,
+                 int row_stride, int skip, float4* __restrict__ packed,
+                 unsigned int* __restrict__ mm_max_bits) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float mm_for_max = 0.f;
+  if (r < n_rows_padded) {
+    float v[NN_DIM];
+    float mm;
+    if (r < n_rows) {
+      const float* src = rows + r * (int64_t)row_stride + skip;
+#pragma unroll
+      for (int k = 0; k < NN_DIM; ++k) v[k] = __ldg(src + k);
+      mm = 0.f;
+#pragma unroll
+      for (int k = 0; k < NN_DIM; ++k) mm = fmaf(v[k], v[k], mm);
+      if (isfinite(mm)) mm_for_max = mm;
+    } else {
+#pragma unroll
+      for (int k = 0; k < NN_DIM; ++k) v[k] = 0.f;
+      mm = INFINITY;
+    }
+    float4* dst = packed + r * 3;
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    dst[2] = make_float4(v[8], v[9], mm, 0.f);
+  }
+  // block max of |m|^2 (non-negative -> uint order == float order)
+  unsigned int bits = __float_as_uint(mm_for_max);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, o));
+  if ((threadIdx.x & 31) == 0 && bits != 0u) atomicMax(mm_max_bits, bits);
+}
+
+// ---- filter + exact re-rank kernel ----------------------------------------------------------
+struct NNParams {
+  const float4* packed;
+  int64_t n_rows;
+  int64_t n_tiles;
+  int64_t tiles_per_split;
+  const float* queries;
+  int64_t n_queries;
+  int query_stride;
+  int skip;
+  float bound;              // norm*norm
+  const float* mm_max;      // device scalar written by the re-pack
+  unsigned long long* keys; // per query, pre-set to NN_KEY_NONE
+};
+
+// filter threshold for one query:  acc < (bound - |q|^2) + eps_q  is implied by  d2_ref < bound.
+// eps_q bounds |acc + |q|^2 - d2_ref| (FMA chain, |m|^2 and |q|^2 roundings); DESIGN.md §NN.
+__device__ __forceinline__ float nn_filter_threshold(const float (&qn)[NN_DIM], float bound,
+                                                     float mm_max) {
+  float qq = 0.f;
+#pragma unroll
+  for (int k = 0; k < NN_DIM; ++k) {
+    const float q = -0.5f * qn[k];
+    qq = fmaf(q, q, qq);
+  }
+  const float u64 = 64.f * 5.9604645e-8f;  // 64 * 2^-24
+  const float eps = u64 * (qq + mm_max) + 0.5f * u64 * fabsf(bound);
+  return (bound - qq) + eps;
+}
+
+// Slow path (rare): re-scan one tile for one query, exact arithmetic for the candidates.
+// Returns the tightened exact bound.
+__device__ __noinline__ float nn_rescan_tile(const float4* __restrict__ tile, int64_t row0,
+                                             int64_t n_rows, float qn0, float qn1, float qn2,
+                                             float qn3, float qn4, float qn5, float qn6, float qn7,
+                                             float qn8, float qn9, float tq, float bound,
+                                             unsigned long long* key) {
+  const float q[NN_DIM] = {-0.5f * qn0, -0.5f * qn1, -0.5f * qn2, -0.5f * qn3, -0.5f * qn4,
+                           -0.5f * qn5, -0.5f * qn6, -0.5f * qn7, -0.5f * qn8, -0.5f * qn9};
+  for (int r = 0; r < NN_TM; ++r) {
+    const float4 a = tile[r * 3 + 0], b = tile[r * 3 + 1], c = tile[r * 3 + 2];
+    float acc = c.z;
+    acc = fmaf(qn0, a.x, acc);
+    acc = fmaf(qn1, a.y, acc);
+    acc = fmaf(qn2, a.z, acc);
+    acc = fmaf(qn3, a.w, acc);
+    acc = fmaf(qn4, b.x, acc);
+    acc = fmaf(qn5, b.y, acc);
+    acc = fmaf(qn6, b.z, acc);
+    acc = fmaf(qn7, b.w, acc);
+    acc = fmaf(qn8, c.x, acc);
+    acc = fmaf(qn9, c.y, acc);
+    if (acc < tq) {
+      const int64_t row = row0 + r;
+      const float m[NN_DIM] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y};
+      const float d2 = ref_sqdist<NN_DIM>(m, q);
+      if (row < n_rows && d2 < bound) {  // strict '<' : brute_force_search.h:35
+        bound = d2;
+        atomicMin(key, nn_pack_key(d2, static_cast<uint32_t>(row)));
+      }
+    }
+  }
+  return bound;
+}
+
+template <int TQ, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+nn_filter_kernel(const NNParams p) {
+  extern __shared__ __align__(128) unsigned char nn_smem[];
+  float4* tiles = reinterpret_cast<float4*>(nn_smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(nn_smem + NN_STAGES * NN_TILE_BYTES);
+
+  const int tid = threadIdx.x;
+  const int64_t tile_begin = (int64_t)blockIdx.x * p.tiles_per_split;
+  const int64_t tile_end = min(tile_begin + p.tiles_per_split, p.n_tiles);
+  if (tile_begin >= tile_end) return;  // uniform for the CTA
+  const int64_t qbase = (int64_t)blockIdx.y * (THREADS * TQ);
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NN_STAGES; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NN_STAGES; ++s)
+      if (tile_begin + s < tile_end) {
+        mbar_arrive_expect_tx(&full[s], NN_TILE_BYTES);
+        tma_load_1d(tiles + s * (NN_TM * 3), p.packed + (tile_begin + s) * (NN_TM * 3),
+                    NN_TILE_BYTES, &full[s]);
+      }
+  }
+
+  // queries of this thread, pre-scaled by -2, plus their filter thresholds and exact bounds
+  const float mm_max = __ldg(p.mm_max);
+  float qn[TQ][NN_DIM];
+  float tq[TQ], bound[TQ], mn[TQ];
+#pragma unroll
+  for (int j = 0; j < TQ; ++j) {
+    const int64_t qi = qbase + (int64_t)j * THREADS + tid;
+    if (qi < p.n_queries) {
+      const float* src = p.queries + qi * (int64_t)p.query_stride + p.skip;
+#pragma unroll
+      for (int k = 0; k < NN_DIM; ++k) qn[j][k] = -2.f * __ldg(src + k);
+      tq[j] = nn_filter_threshold(qn[j], p.bound, mm_max);
+    } else {
+#pragma unroll
+      for (int k = 0; k < NN_DIM; ++k) qn[j][k] = 0.f;
+      tq[j] = -INFINITY;
+    }
+    bound[j] = p.bound;
+    mn[j] = INFINITY;
+  }
+
+  int stage = 0;
+  uint32_t parity = 0;
+  for (int64_t t = tile_begin; t < tile_end; ++t) {
+    mbar_wait(&full[stage], parity);
+    const float4* __restrict__ tile = tiles + stage * (NN_TM * 3);
+
+#pragma unroll 2
+    for (int r = 0; r < NN_TM; ++r) {
+      const float4 a = tile[r * 3 + 0];
+      const float4 b = tile[r * 3 + 1];
+      const float4 c = tile[r * 3 + 2];
+#pragma unroll
+      for (int j = 0; j < TQ; ++j) {
+        float acc = c.z;
+        acc = fmaf(qn[j][0], a.x, acc);
+        acc = fmaf(qn[j][1], a.y, acc);
+        acc = fmaf(qn[j][2], a.z, acc);
+        acc = fmaf(qn[j][3], a.w, acc);
+        acc = fmaf(qn[j][4], b.x, acc);
+        acc = fmaf(qn[j][5], b.y, acc);
+        acc = fmaf(qn[j][6], b.z, acc);
+        acc = fmaf(qn[j][7], b.w, acc);
+        acc = fmaf(qn[j][8], c.x, acc);
+        acc = fmaf(qn[j][9], c.y, acc);
+        mn[j] = fminf(mn[j], acc);
+      }
+    }
+
+    // rare: some row of this tile may be within the bound for some query of this thread
+#pragma unroll
+    for (int j = 0; j < TQ; ++j) {
+      if (mn[j] < tq[j]) {
+        const int64_t qi = qbase + (int64_t)j * THREADS + tid;
+        const float nb = nn_rescan_tile(tile, t * NN_TM, p.n_rows, qn[j][0], qn[j][1], qn[j][2],
+                                        qn[j][3], qn[j][4], qn[j][5], qn[j][6], qn[j][7],
+                                        qn[j][8], qn[j][9], tq[j], bound[j], p.keys + qi);
+        if (nb < bound[j]) {
+          bound[j] = nb;
+          tq[j] = fminf(tq[j], nn_filter_threshold(qn[j], nb, mm_max));
+        }
+      }
+      mn[j] = INFINITY;
+    }
+
+    __syncthreads();  // every warp is done with this stage -> refill it
+    if (tid == 0 && t + NN_STAGES < tile_end) {
+      mbar_arrive_expect_tx(&full[stage], NN_TILE_BYTES);
+      tma_load_1d(tiles + stage * (NN_TM * 3), p.packed + (t + NN_STAGES) * (NN_TM * 3),
+                  NN_TILE_BYTES, &full[stage]);
+    }
+    if (++stage == NN_STAGES) {
+      stage = 0;
+      parity ^= 1u;
+    }
+  }
+}
+
+// keys -> (index, d2)
+__global__ void __launch_bounds__(256)
+nn_finalize_kernel(const unsigned long long* __restrict__ keys, int64_t n, int32_t* best_idx,
+                   float* best_d2, float bound) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long k = keys[i];
+  if (k == NN_KEY_NONE) {
+    best_idx[i] = -1;
+    if (best_d2) best_d2[i] = bound;
+  } else {
+    best_idx[i] = static_cast<int32_t>(k & 0xFFFFFFFFull);
+    if (best_d2) best_d2[i] = __uint_as_float(static_cast<unsigned int>(k >> 32));
+  }
+}
+
+// ---- general kernel: any dimension 1..VO_NN_MAX_DIM, raw AoS rows, reference arithmetic ------
+// thread = query, blockIdx.y = map split; all threads of a warp read the same row (broadcast).
+__global__ void __launch_bounds__(128)
+nn_general_kernel(const float* __restrict__ rows, int64_t n_rows, int row_stride, int skip,
+                  int dim, const float* __restrict__ queries, int64_t n_queries, int query_stride,
+                  int query_skip, float bound, int64_t rows_per_split,
+                  unsigned long long* __restrict__ keys) {
+  const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= n_queries) return;
+  float q[VO_NN_MAX_DIM];
+  for (int k = 0; k < dim; ++k)
+    q[k] = __ldg(queries + qi * (int64_t)query_stride + query_skip + k);
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_split;
+  const int64_t r1 = min(r0 + rows_per_split, n_rows);
+  float best = bound;
+  int64_t best_row = -1;
+  for (int64_t r = r0; r < r1; ++r) {
+    const float d2 = ref_sqdist_dyn(rows + r * (int64_t)row_stride + skip, q, dim);
+    if (d2 < best) {
+      best = d2;
+      best_row = r;
+    }
+  }
+  if (best_row >= 0) atomicMin(keys + qi, nn_pack_key(best, static_cast<uint32_t>(best_row)));
+}
+
+// ---- bruteForceSearch: one warp per query, ascending row order -----------------------------------
+__global__ void __launch_bounds__(128)
+nn_radius_kernel(const float* __restrict__ rows, int64_t n_rows, int row_stride, int skip, int dim,
+                 const float* __restrict__ queries, int64_t n_queries, int query_stride,
+                 int query_skip, float bound, int32_t* __restrict__ counts,
+                 int32_t* __restrict__ idx_out, int32_t max_per_query) {
+  const int lane = threadIdx.x & 31;
+  const int64_t qi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (qi >= n_queries) return;
+  float q[VO_NN_MAX_DIM];
+  for (int k = 0; k < dim; ++k)
+    q[k] = __ldg(queries + qi * (int64_t)query_stride + query_skip + k);
+  int32_t total = 0;
+  for (int64_t base = 0; base < n_rows; base += 32) {
+    const int64_t r = base + lane;
+    bool hit = false;
+    if (r < n_rows)
+      hit = ref_sqdist_dyn(rows + r * (int64_t)row_stride + skip, q, dim) < bound;
+    const unsigned int ballot = __ballot_sync(0xffffffffu, hit);
+    if (hit && idx_out) {
+      const int32_t pos = total + __popc(ballot & ((1u << lane) - 1u));
+      if (pos < max_per_query) idx_out[qi * (int64_t)max_per_query + pos] = static_cast<int32_t>(r);
+    }
+    total += __popc(ballot);
+  }
+  if (lane == 0) counts[qi] = total;
+}
+
+}  // namespace vo
+
+// =================================================================================================
+// host side
+// =================================================================================================
+using namespace vo;
+
+struct vo_nn_s {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int64_t n_rows = 0;
+  int row_stride = 0, skip = 0, dim = 0;
+  bool fast = false;          // packed layout valid (dim == NN_DIM)
+  int64_t n_tiles = 0;
+  DevBuf raw;                 // staging copy of the caller's rows (host variant / general path)
+  // rows as seen by the general + radius kernels: the packed buffer (stride 12, skip 0) on the
+  // fast path, the private raw copy otherwise
+  const float* rows_dev = nullptr;
+  int map_stride = 0, map_skip = 0;
+  DevBuf packed;
+  DevBuf scalars;             // [0] = mm_max
+  DevBuf keys;
+  DevBuf q_stage, idx_stage, d2_stage, cnt_stage, list_stage;
+};
+
+static int nn_launch_filter(vo_nn_s* h, const float* queries_dev, int64_t nq, int qstride,
+                            float bound) {
+  NNParams p;
+  p.packed = h->packed.as<float4>();
+  p.n_rows = h->n_rows;
+  p.n_tiles = h->n_tiles;
+  p.queries = queries_dev;
+  p.n_queries = nq;
+  p.query_stride = qstride;
+  p.skip = h->skip;
+  p.bound = bound;
+  p.mm_max = h->scalars.as<float>();
+  p.keys = h->keys.as<unsigned long long>();
+
+  const int sms = num_sms(h->device);
+  const size_t smem = NN_STAGES * NN_TILE_BYTES + NN_STAGES * sizeof(uint64_t);
+  auto splits_for = [&](int64_t qtiles, int64_t resident) {
+    // Every wave should be full: with one query tile per blockIdx.y and `resident` CTAs alive at
+    // once, `resident` map splits make each query tile exactly one wave.  Small maps get fewer,
+    // fatter splits (>= 8 tiles each) and rely on the query dimension to fill the chip.
+    int64_t s = resident;
+    if (h->n_tiles < 8 * s) s = std::max<int64_t>(1, h->n_tiles / 8);
+    if (qtiles * s < resident) s = std::min<int64_t>(h->n_tiles, (resident + qtiles - 1) / qtiles);
+    return std::max<int64_t>(1, s);
+  };
+  auto launch = [&](auto kernel, int tq, int threads) -> int {
+    const int64_t qtiles = (nq + (int64_t)tq * threads - 1) / ((int64_t)tq * threads);
+    VO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    VO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    const int64_t splits = splits_for(qtiles, (int64_t)sms * std::max(per_sm, 1));
+    p.tiles_per_split = (h->n_tiles + splits - 1) / splits;
+    const int64_t nsplit = (h->n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+    VO_REQUIRE(qtiles <= 65535, VO_ERR_UNSUPPORTED, "too many query tiles for one launch");
+    dim3 grid((unsigned)nsplit, (unsigned)qtiles);
+    kernel<<<grid, threads, smem, h->stream>>>(p);
+    VO_LAUNCH_CHECK();
+    return VO_OK;
+  };
+  if (nq > 8192) return launch(nn_filter_kernel<8, 256>, 8, 256);
+  if (nq > 1024) return launch(nn_filter_kernel<2, 256>, 2, 256);
+  return launch(nn_filter_kernel<1, 128>, 1, 128);
+}
+
+static int nn_set_map_common(vo_nn_s* h, const float* rows_dev, int64_t n_rows, int row_stride,
+                             int skip) {
+  h->n_rows = n_rows;
+  h->row_stride = row_stride;
+  h->skip = skip;
+  h->dim = row_stride - skip;
+  h->rows_dev = rows_dev;
+  h->map_stride = row_stride;
+  h->map_skip = skip;
+  h->fast = (h->dim == NN_DIM);
+  if (!h->fast || n_rows == 0) return VO_OK;
+  h->n_tiles = (n_rows + NN_TM - 1) / NN_TM;
+  const int64_t padded = h->n_tiles * NN_TM;
+  int rc = h->packed.reserve((size_t)padded * NN_ROW_BYTES);
+  if (rc) return rc;
+  rc = h->scalars.reserve(64);
+  if (rc) return rc;
+  VO_CUDA(cudaMemsetAsync(h->scalars.p, 0, 64, h->stream));
+  const int threads = 256;
+  const int64_t blocks = (padded + threads - 1) / threads;
+  nn_repack_kernel<<<(unsigned)blocks, threads, 0, h->stream>>>(
+      rows_dev, n_rows, padded, row_stride, skip, h->packed.as<float4>(),
+      h->scalars.as<unsigned int>());
+  VO_LAUNCH_CHECK();
+  // from here on the caller's rows are not needed: the packed rows are [a0..a9 |a|^2 0]
+  h->rows_dev = h->packed.as<float>();
+  h->map_stride = NN_ROW_BYTES / (int)sizeof(float);
+  h->map_skip = 0;
+  return VO_OK;
+}
+
+static int nn_best_match_common(vo_nn_s* h, const float* queries_dev, int64_t nq, int qstride,
+                                float norm, int32_t* idx_dev, float* d2_dev) {
+  const float bound = norm * norm;  // brute_force_search.h:31
+  if (nq == 0) return VO_OK;
+  int rc = h->keys.reserve((size_t)nq * sizeof(unsigned long long));
+  if (rc) return rc;
+  VO_CUDA(cudaMemsetAsync(h->keys.p, 0xFF, (size_t)nq * sizeof(unsigned long long), h->stream));
+  if (h->n_rows > 0) {
+    if (h->fast) {
+      rc = nn_launch_filter(h, queries_dev, nq, qstride, bound);
+      if (rc) return rc;
+    } else {
+      const int threads = 128;
+      const int64_t qblocks = (nq + threads - 1) / threads;
+      const int sms = num_sms(h->device);
+      int64_t splits = std::max<int64_t>(1, (4LL * sms + qblocks - 1) / qblocks);
+      splits = std::min<int64_t>(splits, std::max<int64_t>(1, h->n_rows / 64));
+      splits = std::min<int64_t>(splits, 65535);
+      const int64_t rps = (h->n_rows + splits - 1) / splits;
+      dim3 grid((unsigned)qblocks, (unsigned)((h->n_rows + rps - 1) / rps));
+      nn_general_kernel<<<grid, threads, 0, h->stream>>>(
+          h->rows_dev, h->n_rows, h->map_stride, h->map_skip, h->dim, queries_dev, nq, qstride,
+          h->skip, bound, rps, h->keys.as<unsigned long long>());
+      VO_LAUNCH_CHECK();
+    }
+  }
+  const int threads = 256;
+  nn_finalize_kernel<<<(unsigned)((nq + threads - 1) / threads), threads, 0, h->stream>>>(
+      h->keys.as<unsigned long long>(), nq, idx_dev, d2_dev, bound);
+  VO_LAUNCH_CHECK();
+  return VO_OK;
+}
+
+extern "C" {
+
+int vo_nn_create(vo_nn_t* out, int device) {
+  VO_REQUIRE(out != nullptr, VO_ERR_ARG, "null handle pointer");
+  int n = 0;
+  VO_CUDA(cudaGetDeviceCount(&n));
+  VO_REQUIRE(device >= 0 && device < n, VO_ERR_ARG, "bad device ordinal");
+  DeviceGuard g(device);
+  vo_nn_s* h = new vo_nn_s();
+  h->device = device;
+  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    set_error("cudaStreamCreate -> %s", cudaGetErrorString(e));
+    delete h;
+    return VO_ERR_CUDA;
+  }
+  h->own_stream = true;
+  *out = h;
+  return VO_OK;
+}
+
+int vo_nn_destroy(vo_nn_t h) {
+  if (!h) return VO_OK;
+  DeviceGuard g(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->raw.release();
+  h->packed.release();
+  h->scalars.release();
+  h->keys.release();
+  h->q_stage.release();
+  h->idx_stage.release();
+  h->d2_stage.release();
+  h->cnt_stage.release();
+  h->list_stage.release();
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return VO_OK;
+}
+
+int vo_nn_set_stream(vo_nn_t h, void* cuda_stream) {
+  VO_REQUIRE(h != nullptr, VO_ERR_ARG, "null handle");
+  DeviceGuard g(h->device);
+  if (h->own_stream) {
+    cudaStreamSynchronize(h->stream);
+    cudaStreamDestroy(h->stream);
+    h->own_stream = false;
+  }
+  h->stream = static_cast<cudaStream_t>(cuda_stream);
+  return VO_OK;
+}
+
+int vo_nn_synchronize(vo_nn_t h) {
+  VO_REQUIRE(h != nullptr, VO_ERR_ARG, "null handle");
+  DeviceGuard g(h->device);
+  VO_CUDA(cudaStreamSynchronize(h->stream));
+  return VO_OK;
+}
+
+static int nn_check_layout(int64_t n, int stride, int skip) {
+  VO_REQUIRE(n >= 0 && n < (1LL << 31), VO_ERR_ARG, "row count out of range");
+  VO_REQUIRE(skip >= 0 && stride > skip, VO_ERR_ARG, "bad stride/skip");
+  VO_REQUIRE(stride - skip <= VO_NN_MAX_DIM, VO_ERR_UNSUPPORTED, "dimension > VO_NN_MAX_DIM");
+  return VO_OK;
+}
+
+int vo_nn_set_map(vo_nn_t h, const float* rows_host, int64_t n_rows, int row_stride,
+                  int skip_cols) {
+  VO_REQUIRE(h != nullptr, VO_ERR_ARG, "null handle");
+  int rc = nn_check_layout(n_rows, row_stride, skip_cols);
+  if (rc) return rc;
+  VO_REQUIRE(rows_host != nullptr || n_rows == 0, VO_ERR_ARG, "null rows");
+  DeviceGuard g(h->device);
+  const size_t bytes = (size_t)n_rows * row_stride * sizeof(float);
+  rc = h->raw.reserve(bytes ? bytes : 16);
+  if (rc) return rc;
+  if (bytes)
+    VO_CUDA(cudaMemcpyAsync(h->raw.p, rows_host, bytes, cudaMemcpyHostToDevice, h->stream));
+  rc = nn_set_map_common(h, h->raw.as<float>(), n_rows, row_stride, skip_cols);
+  if (rc) return rc;
+  // the host buffer may be freed by the caller as soon as we return
+  VO_CUDA(cudaStreamSynchronize(h->stream));
+  return VO_OK;
+}
+
+int vo_nn_set_map_device(vo_nn_t h, const float* rows_dev, int64_t n_rows, int row_stride,
+                         int skip_cols) {
+  VO_REQUIRE(h != nullptr, VO_ERR_ARG, "null handle");
+  int rc = nn_check_layout(n_rows, row_stride, skip_cols);
+  if (rc) return rc;
+  VO_REQUIRE(rows_dev != nullptr || n_rows == 0, VO_ERR_ARG, "null rows");
+  DeviceGuard g(h->device);
+  if (row_stride - skip_cols != NN_DIM && n_rows > 0) {
+    // general path reads the rows at query time: keep a private copy
+    const size_t bytes = (size_t)n_rows * row_stride * sizeof(float);
+    rc = h->raw.reserve(bytes);
+    if (rc) return rc;
+    VO_CUDA(cudaMemcpyAsync(h->raw.p, rows_dev, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    rows_dev = h->raw.as<float>();
+  }
+  return nn_set_map_common(h, rows_dev, n_rows, row_stride, skip_cols);
+}
+
+int vo_nn_best_match_device(vo_nn_t h, const float* queries_dev, int64_t n_queries,
+                            int query_stride, float norm, int32_t* best_idx_dev,
+                            float* best_d2_dev) {
+  VO_REQUIRE(h != nullptr, VO_ERR_ARG, "null handle");
+  VO_REQUIRE(h->row_stride > 0, VO_ERR_STATE, "set_map not called");
+  VO_REQUIRE(n_queries >= 0, VO_ERR_ARG, "negative query count");
+  VO_REQUIRE(query_stride - h->skip >= h->dim, VO_ERR_ARG, "query stride too small");
+  VO_REQUIRE((queries_dev && best_idx_dev) || n_queries == 0, VO_ERR_ARG, "null pointer");
+  DeviceGuard g(h->device);
+  return nn_best_match_common(h, queries_dev, n_queries, query_stride, norm, best_idx_dev,
+                              best_d2_dev);
+}
+
+int vo_nn_best_match(vo_nn_t h, const float* queries_host, int64_t n_queries, int query_stride,
+                     float norm, int32_t* best_idx_host, float* best_d2_host) {
+  VO_REQUIRE(h != nullptr, VO_ERR_ARG, "null handle");
+  VO_REQUIRE(h->row_stride > 0, VO_ERR_STATE, "set_map not called");
+  VO_REQUIRE(n_queries >= 0, VO_ERR_ARG, "negative query count");
+  VO_REQUIRE(query_stride - h->skip >= h->dim, VO_ERR_ARG, "query stride too small");
+  VO_REQUIRE((queries_host && best_idx_host) || n_queries == 0, VO_ERR_ARG, "null pointer");
+  if (n_queries == 0) return VO_OK;
+  DeviceGuard g(h->device);
+  const size_t qbytes = (size_t)n_queries * query_stride * sizeof(float);
+  int rc = h->q_stage.reserve(qbytes);
+  if (rc) return rc;
+  rc = h->idx_stage.reserve((size_t)n_queries * sizeof(int32_t));
+  if (rc) return rc;
+  rc = h->d2_stage.reserve((size_t)n_queries * sizeof(float));
+  if (rc) return rc;
+  VO_CUDA(cudaMemcpyAsync(h->q_stage.p, queries_host, qbytes, cudaMemcpyHostToDevice, h->stream));
+  rc = nn_best_match_common(h, h->q_stage.as<float>(), n_queries, query_stride, norm,
+                            h->idx_stage.as<int32_t>(), h->d2_stage.as<float>());
+  if (rc) return rc;
+  VO_CUDA(cudaMemcpyAsync(best_idx_host, h->idx_stage.p, (size_t)n_queries * sizeof(int32_t),
+                          cudaMemcpyDeviceToHost, h->stream));
+  if (best_d2_host)
+    VO_CUDA(cudaMemcpyAsync(best_d2_host, h->d2_stage.p, (size_t)n_queries * sizeof(float),
+                            cudaMemcpyDeviceToHost, h->stream));
+  VO_CUDA(cudaStreamSynchronize(h->stream));
+  return VO_OK;
+}
+
+int vo_nn_radius_search(vo_nn_t h, const float* queries_host, int64_t n_queries, int query_stride,
+                        float norm, int32_t* counts_host, int32_t* idx_out_host,
+                        int32_t max_per_query) {
+  VO_REQUIRE(h != nullptr, VO_ERR_ARG, "null handle");
+  VO_REQUIRE(h->row_stride > 0, VO_ERR_STATE, "set_map not called");
+  VO_REQUIRE(n_queries >= 0 && max_per_query >= 0, VO_ERR_ARG, "negative size");
+  VO_REQUIRE(query_stride - h->skip >= h->dim, VO_ERR_ARG, "query stride too small");
+  VO_REQUIRE((queries_host && counts_host) || n_queries == 0, VO_ERR_ARG, "null pointer");
+  if (n_queries == 0) return VO_OK;
+  DeviceGuard g(h->device);
+  const size_t qbytes = (size_t)n_queries * query_stride * sizeof(float);
+  int rc = h->q_stage.reserve(qbytes);
+  if (rc) return rc;
+  rc = h->cnt_stage.reserve((size_t)n_queries * sizeof(int32_t));
+  if (rc) return rc;
+  const size_t lbytes = (size_t)n_queries * max_per_query * sizeof(int32_t);
+  if (idx_out_host && lbytes) {
+    rc = h->list_stage.reserve(lbytes);
+    if (rc) return rc;
+    VO_CUDA(cudaMemsetAsync(h->list_stage.p, 0xFF, lbytes, h->stream));
+  }
+  VO_CUDA(cudaMemcpyAsync(h->q_stage.p, queries_host, qbytes, cudaMemcpyHostToDevice, h->stream));
+  const int threads = 128;
+  const int64_t blocks = (n_queries * 32 + threads - 1) / threads;
+  nn_radius_kernel<<<(unsigned)blocks, threads, 0, h->stream>>>(
+      h->rows_dev, h->n_rows, h->map_stride, h->map_skip, h->dim, h->q_stage.as<float>(),
+      n_queries, query_stride, h->skip, norm * norm, h->cnt_stage.as<int32_t>(),
+      (idx_out_host && lbytes) ? h->list_stage.as<int32_t>() : nullptr, max_per_query);
+  VO_LAUNCH_CHECK();
+  VO_CUDA(cudaMemcpyAsync(counts_host, h->cnt_stage.p, (size_t)n_queries * sizeof(int32_t),
+                          cudaMemcpyDeviceToHost, h->stream));
+  if (idx_out_host && lbytes)
+    VO_CUDA(cudaMemcpyAsync(idx_out_host, h->list_stage.p, lbytes, cudaMemcpyDeviceToHost,
+                            h->stream));
+  VO_CUDA(cudaStreamSynchronize(h->stream));
+  return VO_OK;
+}
+
+}  // extern "C"

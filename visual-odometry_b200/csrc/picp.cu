@@ -1,0 +1,601 @@
+// picp.cu — projective-ICP Gauss-Newton rounds, entirely on the device (sm_100a).
+//
+// Replaces PICPSolver::{init,errorAndJacobian,linearize,oneRound}  (reference
+// src/picp_solver.cpp:16-112) with Camera::projectPoint inlined (include/camera.h:25-37) and
+// v2tEuler / Rotation{X,Y,Z} / skew (include/utils.h:16-102).
+//
+// One launch == one oneRound():
+//   * grid = a multiple of the SM count, grid-stride over the correspondences; every thread
+//     batches PICP_UNROLL independent (pair -> world point, image point) gathers before it does
+//     any arithmetic so that enough bytes are in flight to cover HBM latency;
+//   * per correspondence: pc = T*p, z-range / image-bounds rejection, e = proj - meas,
+//     J = Jp*K*[I | skew(-pc)] in the factored form  A = iz*(K_row - uv*K_row2), J = [A | A*S]
+//     (K is treated as a general 3x3), robust weight, and the 21 upper-triangular entries of
+//     lambda*J^T J plus the 6 of lambda*J^T e accumulated in registers;
+//   * warp-shuffle + shared-memory block reduction -> one 32-float partial per block in global
+//     memory -> the LAST block to finish (atomic ticket) sums the partials in a fixed order, adds
+//     the damping, runs the pivoted 6x6 LDL^T solve, builds v2tEuler(dx) and left-multiplies the
+//     pose.  No float atomics: results are run-to-run deterministic.
+// The pose lives in device memory and is re-read by the next launch, so `rounds` launches are
+// simply queued (or replayed from a CUDA graph): no host round-trip between rounds.
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <tuple>
+
+#include "common.cuh"
+#include "linalg.cuh"
+
+namespace vo {
+
+constexpr int PICP_THREADS = 256;
+constexpr int PICP_UNROLL = 4;
+constexpr int PICP_NACC = 32;  // 21 H + 6 b + chi_in + chi_out + n_in (as float bits of int) + 2 pad
+
+struct PicpDeviceState {
+  vo_picp_state s;       // what vo_picp_get_state copies back
+  unsigned int ticket;   // last-block-done counter
+};
+
+struct PicpParams {
+  const float* __restrict__ world;   // 3 floats / point
+  const float* __restrict__ image;   // 2 floats / point
+  const int2* __restrict__ pairs;    // (image idx, world idx)
+  int64_t n_pairs;
+  float K[9];                        // column-major
+  float z_near, z_far;               // ints promoted to float (camera.h:28)
+  float max_u, max_v;                // cols-1, rows-1            (camera.h:32-35)
+  float thr, damping;
+  int min_inliers;
+  int keep_outliers;
+  PicpDeviceState* st;
+  float* partials;                   // [gridDim.x][PICP_NACC]
+};
+
+// oneRound's tail (picp_solver.cpp:102-110), executed by one thread of the last block.
+__device__ void picp_solve_and_update(const PicpParams& p, const float* tot) {
+  vo_picp_state& s = p.st->s;
+  // upper triangle -> full symmetric H, column-major
+  float H[36];
+  {
+    int k = 0;
+    for (int r = 0; r < 6; ++r)
+      for (int c = r; c < 6; ++c) {
+        H[c * 6 + r] = tot[k];
+        H[r * 6 + c] = tot[k];
+        ++k;
+      }
+  }
+  float b[6];
+  for (int i = 0; i < 6; ++i) b[i] = tot[21 + i];
+  for (int i = 0; i < 6; ++i) H[i * 6 + i] += p.damping;  // :102
+  for (int i = 0; i < 36; ++i) s.H[i] = H[i];
+  for (int i = 0; i < 6; ++i) s.b[i] = b[i];
+  s.chi_inliers = tot[27];
+  s.chi_outliers = tot[28];
+  const int n_in = __float_as_int(tot[29]);
+  s.num_inliers = n_in;
+  s.rounds_done += 1;
+  if (n_in < p.min_inliers) {  // :103-107
+    s.last_ok = 0;
+    return;
+  }
+  float nb[6], dx[6];
+  for (int i = 0; i < 6; ++i) nb[i] = -b[i];
+  ldlt_solve_dev<6>(H, nb, dx);  // :109
+  // v2tEuler(dx): R = Rx(dx3)*Ry(dx4)*Rz(dx5), t = dx0..2   (utils.h:64-78)
+  const float sx = sinf(dx[3]), cx = cosf(dx[3]);
+  const float sy = sinf(dx[4]), cy = cosf(dx[4]);
+  const float sz = sinf(dx[5]), cz = cosf(dx[5]);
+  const float Rx[9] = {1, 0, 0, 0, cx, sx, 0, -sx, cx};
+  const float Ry[9] = {cy, 0, -sy, 0, 1, 0, sy, 0, cy};
+  const float Rz[9] = {cz, sz, 0, -sz, cz, 0, 0, 0, 1};
+  float Rxy[9], R[9];
+  mat3_mul_dev(Rx, Ry, Rxy);
+  mat3_mul_dev(Rxy, Rz, R);
+  // pose <- D * pose   (:110)
+  float Tn[16];
+  for (int j = 0; j < 4; ++j)
+    for (int i = 0; i < 3; ++i) {
+      float acc = (R[i] * s.T[j * 4] + R[3 + i] * s.T[j * 4 + 1]) + R[6 + i] * s.T[j * 4 + 2];
+      if (j == 3) acc += dx[i];
+      Tn[j * 4 + i] = acc;
+    }
+  Tn[3] = Tn[7] = Tn[11] = 0.f;
+  Tn[15] = 1.f;
+  for (int i = 0; i < 16; ++i) s.T[i] = Tn[i];
+  s.last_ok = 1;
+}
+
+// One correspondence: errorAndJacobian (:25-53) + the body of linearize's loop (:62-95).
+struct PicpAcc {
+  float h[21];
+  float b[6];
+  float chi_in, chi_out;
+  int n_in;
+};
+
+__device__ __forceinline__ void picp_point(const PicpParams& p, const float (&T)[12], float wx,
+                                           float wy, float wz, float mu, float mv, PicpAcc& a) {
+  // camera_point = world_in_camera * world_point  (camera.h:27, picp_solver.cpp:38)
+  const float px = fmaf(T[6], wz, fmaf(T[3], wy, T[0] * wx)) + T[9];
+  const float py = fmaf(T[7], wz, fmaf(T[4], wy, T[1] * wx)) + T[10];
+  const float pz = fmaf(T[8], wz, fmaf(T[5], wy, T[2] * wx)) + T[11];
+  if (pz > p.z_far || pz < p.z_near) return;  // camera.h:28
+  // phom = K * camera_point  (camera.h:30, picp_solver.cpp:43)
+  const float hx = fmaf(p.K[6], pz, fmaf(p.K[3], py, p.K[0] * px));
+  const float hy = fmaf(p.K[7], pz, fmaf(p.K[4], py, p.K[1] * px));
+  const float hz = fmaf(p.K[8], pz, fmaf(p.K[5], py, p.K[2] * px));
+  const float iz = 1.0f / hz;  // camera.h:31 / picp_solver.cpp:44 (IEEE division)
+  const float u = hx * iz, v = hy * iz;
+  if (u < 0.f || u > p.max_u) return;  // camera.h:32
+  if (v < 0.f || v > p.max_v) return;  // camera.h:34
+  const float e0 = u - mu, e1 = v - mv;  // :35
+  // A = Jp*K with Jp = [iz 0 -hx*iz^2; 0 iz -hy*iz^2]  ==  iz * (K_row{0,1} - {u,v} * K_row2)
+  float J0[6], J1[6];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    J0[j] = iz * fmaf(-u, p.K[j * 3 + 2], p.K[j * 3 + 0]);
+    J1[j] = iz * fmaf(-v, p.K[j * 3 + 2], p.K[j * 3 + 1]);
+  }
+  // J = [A | A*skew(-pc)],  skew(-pc) = [0 pz -py; -pz 0 px; py -px 0]   (:39-41, utils.h:96-102)
+  J0[3] = fmaf(J0[2], py, -J0[1] * pz);
+  J0[4] = fmaf(J0[0], pz, -J0[2] * px);
+  J0[5] = fmaf(J0[1], px, -J0[0] * py);
+  J1[3] = fmaf(J1[2], py, -J1[1] * pz);
+  J1[4] = fmaf(J1[0], pz, -J1[2] * px);
+  J1[5] = fmaf(J1[1], px, -J1[0] * py);
+  const float chi = fmaf(e1, e1, e0 * e0);  // :75
+  float lambda = 1.f;
+  if (chi > p.thr) {  // :78-83
+    a.chi_out += chi;
+    if (!p.keep_outliers) return;  // :90
+    lambda = sqrtf(p.thr / chi);
+  } else {  // :84-88
+    a.chi_in += chi;
+    a.n_in += 1;
+  }
+  // H += J^T J * lambda ; b += J^T e * lambda   (:92-93)
+  float L0[6], L1[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    L0[j] = J0[j] * lambda;
+    L1[j] = J1[j] * lambda;
+  }
+  int k = 0;
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+#pragma unroll
+    for (int c = r; c < 6; ++c) {
+      a.h[k] = fmaf(L0[r], J0[c], fmaf(L1[r], J1[c], a.h[k]));
+      ++k;
+    }
+    a.b[r] = fmaf(L0[r], e0, fmaf(L1[r], e1, a.b[r]));
+  }
+}
+
+__global__ void __launch_bounds__(PICP_THREADS, 2) picp_round_kernel(const PicpParams p) {
+  __shared__ float s_red[PICP_THREADS / 32][PICP_NACC];
+  __shared__ bool s_last;
+  const int tid = threadIdx.x;
+
+  float T[12];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) T[j * 3 + i] = p.st->s.T[j * 4 + i];
+
+  PicpAcc a;
+#pragma unroll
+  for (int i = 0; i < 21; ++i) a.h[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) a.b[i] = 0.f;
+  a.chi_in = a.chi_out = 0.f;
+  a.n_in = 0;
+
+  const int64_t stride = (int64_t)gridDim.x * PICP_THREADS;
+  for (int64_t base = (int64_t)blockIdx.x * PICP_THREADS + tid; base < p.n_pairs;
+       base += stride * PICP_UNROLL) {
+    int2 pr[PICP_UNROLL];
+    bool ok[PICP_UNROLL];
+#pragma unroll
+    for (int u = 0; u < PICP_UNROLL; ++u) {
+      const int64_t i = base + u * stride;
+      ok[u] = i < p.n_pairs;
+      pr[u] = ok[u] ? __ldg(p.pairs + i) : make_int2(0, 0);
+    }
+    float w[PICP_UNROLL][3];
+    float2 m[PICP_UNROLL];
+#pragma unroll
+    for (int u = 0; u < PICP_UNROLL; ++u) {
+      if (ok[u]) {
+        const float* wp = p.world + 3 * (int64_t)pr[u].y;  // .second -> world (:67)
+        w[u][0] = __ldg(wp);
+        w[u][1] = __ldg(wp + 1);
+        w[u][2] = __ldg(wp + 2);
+        m[u] = __ldg(reinterpret_cast<const float2*>(p.image) + pr[u].x);  // .first -> image (:66)
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PICP_UNROLL; ++u)
+      if (ok[u]) picp_point(p, T, w[u][0], w[u][1], w[u][2], m[u].x, m[u].y, a);
+  }
+
+  // ---- block reduction: shuffle within the warp, fixed-order sum across warps ----------------
+  float v[PICP_NACC];
+#pragma unroll
+  for (int i = 0; i < 21; ++i) v[i] = a.h[i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) v[21 + i] = a.b[i];
+  v[27] = a.chi_in;
+  v[28] = a.chi_out;
+  int n_in = a.n_in;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 29; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+    n_in += __shfl_xor_sync(0xffffffffu, n_in, o);
+  }
+  const int warp = tid >> 5, lane = tid & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 29; ++i) s_red[warp][i] = v[i];
+    s_red[warp][29] = __int_as_float(n_in);
+  }
+  __syncthreads();
+  if (warp == 0 && lane < 30) {
+    float* out = p.partials + (int64_t)blockIdx.x * PICP_NACC;
+    if (lane < 29) {
+      float s = s_red[0][lane];
+#pragma unroll
+      for (int wv = 1; wv < PICP_THREADS / 32; ++wv) s += s_red[wv][lane];
+      out[lane] = s;
+    } else {
+      int s = 0;
+#pragma unroll
+      for (int wv = 0; wv < PICP_THREADS / 32; ++wv) s += __float_as_int(s_red[wv][29]);
+      out[29] = __int_as_float(s);
+    }
+  }
+
+  // ---- last block: fixed-order sum over the blocks, solve, pose update -----------------------
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int t = atomicAdd(&p.st->ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  {
+    // warp w sums blocks w, w+W, ... for component `lane`; then warp 0 sums the W rows
+    constexpr int W = PICP_THREADS / 32;
+    float s = 0.f;
+    int si = 0;
+    if (lane < 30) {
+      for (int bk = warp; bk < (int)gridDim.x; bk += W) {
+        const float x = __ldcg(p.partials + (int64_t)bk * PICP_NACC + lane);
+        if (lane < 29) s += x;
+        else si += __float_as_int(x);
+      }
+    }
+    __syncthreads();
+    s_red[warp][lane] = (lane == 29) ? __int_as_float(si) : s;
+    __syncthreads();
+    if (warp == 0) {
+      float tot = 0.f;
+      int toti = 0;
+#pragma unroll
+      for (int wv = 0; wv < W; ++wv) {
+        if (lane == 29) toti += __float_as_int(s_red[wv][29]);
+        else tot += s_red[wv][lane];
+      }
+      s_red[0][lane] = (lane == 29) ? __int_as_float(toti) : tot;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      picp_solve_and_update(p, &s_red[0][0]);
+      p.st->ticket = 0u;
+    }
+  }
+}
+
+}  // namespace vo
+
+// =================================================================================================
+// host side
+// =================================================================================================
+using namespace vo;
+
+struct vo_picp_s {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  vo_camera cam{};
+  bool have_cam = false;
+  float thr = 1000.f, damping = 1.f;  // picp_solver.cpp:10-13
+  int32_t min_inliers = 0;
+  DevBuf world_buf, image_buf, pairs_buf, state_buf, partials_buf;
+  const float* world = nullptr;
+  const float* image = nullptr;
+  const int32_t* pairs = nullptr;
+  int64_t n_world = 0, n_image = 0, n_pairs = 0;
+  int grid = 0;
+  // CUDA graphs of `rounds` back-to-back launches, keyed by everything baked into the nodes
+  struct GraphKey {
+    const void *world, *image, *pairs, *partials;
+    int64_t n;
+    int keep, rounds, grid;
+    float thr, damping;
+    int min_inliers;
+    bool operator<(const GraphKey& o) const {
+      return std::tie(world, image, pairs, partials, n, keep, rounds, grid, thr, damping,
+                      min_inliers) < std::tie(o.world, o.image, o.pairs, o.partials, o.n, o.keep,
+                                              o.rounds, o.grid, o.thr, o.damping, o.min_inliers);
+    }
+  };
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+};
+
+static void picp_drop_graphs(vo_picp_s* h) {
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  h->graphs.clear();
+}
+
+static int picp_upload_state(vo_picp_s* h) {
+  int rc = h->state_buf.reserve(sizeof(PicpDeviceState));
+  if (rc) return rc;
+  PicpDeviceState st;
+  memset(&st, 0, sizeof(st));
+  memcpy(st.s.T, h->cam.T, sizeof(st.s.T));
+  st.s.last_ok = 1;
+  // pageable -> device copies are staged by the runtime before the call returns
+  VO_CUDA(cudaMemcpyAsync(h->state_buf.p, &st, sizeof(st), cudaMemcpyHostToDevice, h->stream));
+  return VO_OK;
+}
+
+static int picp_fill_params(vo_picp_s* h, int keep_outliers, PicpParams* p) {
+  p->world = h->world;
+  p->image = h->image;
+  p->pairs = reinterpret_cast<const int2*>(h->pairs);
+  p->n_pairs = h->n_pairs;
+  memcpy(p->K, h->cam.K, sizeof(p->K));
+  p->z_near = (float)h->cam.z_near;
+  p->z_far = (float)h->cam.z_far;
+  p->max_u = (float)(h->cam.cols - 1);
+  p->max_v = (float)(h->cam.rows - 1);
+  p->thr = h->thr;
+  p->damping = h->damping;
+  p->min_inliers = h->min_inliers;
+  p->keep_outliers = keep_outliers ? 1 : 0;
+  p->st = h->state_buf.as<PicpDeviceState>();
+  p->partials = h->partials_buf.as<float>();
+  return VO_OK;
+}
+
+static int picp_pick_grid(vo_picp_s* h) {
+  const int sms = num_sms(h->device);
+  int per_sm = 2;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, picp_round_kernel, PICP_THREADS, 0);
+  if (per_sm < 1) per_sm = 1;
+  const int64_t full = (int64_t)sms * per_sm;
+  const int64_t need =
+      (h->n_pairs + (int64_t)PICP_THREADS * PICP_UNROLL - 1) / ((int64_t)PICP_THREADS * PICP_UNROLL);
+  int64_t g = need < full ? need : full;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+extern "C" {
+
+int vo_picp_create(vo_picp_t* out, int device) {
+  VO_REQUIRE(out != nullptr, VO_ERR_ARG, "null handle pointer");
+  int n = 0;
+  VO_CUDA(cudaGetDeviceCount(&n));
+  VO_REQUIRE(device >= 0 && device < n, VO_ERR_ARG, "bad device ordinal");
+  DeviceGuard g(device);
+  vo_picp_s* h = new vo_picp_s();
+  h->device = device;
+  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    set_error("cudaStreamCreate -> %s", cudaGetErrorString(e));
+    delete h;
+    return VO_ERR_CUDA;
+  }
+  h->own_stream = true;
+  *out = h;
+  return VO_OK;
+}
+
+int vo_picp_destroy(vo_picp_t h) {
+  if (!h) return VO_OK;
+  DeviceGuard g(h->device);
+  cudaStreamSynchronize(h->stream);
+  picp_drop_graphs(h);
+  h->world_buf.release();
+  h->image_buf.release();
+  h->pairs_buf.release();
+  h->state_buf.release();
+  h->partials_buf.release();
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return VO_OK;
+}
+
+int vo_picp_set_stream(vo_picp_t h, void* cuda_stream) {
+  VO_REQUIRE(h != nullptr, VO_ERR_ARG, "null handle");
+  DeviceGuard g(h->device);
+  cudaStreamSynchronize(h->stream);
+  if (h->own_stream) {
+    cudaStreamDestroy(h->stream);
+    h->own_stream = false;
+  }
+  h->stream = static_cast<cudaStream_t>(cuda_stream);
+  return VO_OK;
+}
+
+int vo_picp_synchronize(vo_picp_t h) {
+  VO_REQUIRE(h != nullptr, VO_ERR_ARG, "null handle");
+  DeviceGuard g(h->device);
+  VO_CUDA(cudaStreamSynchronize(h->stream));
+  return VO_OK;
+}
+
+int vo_picp_set_params(vo_picp_t h, float kernel_threshold, float damping,
+                       int32_t min_num_inliers) {
+  VO_REQUIRE(h != nullptr, VO_ERR_ARG, "null handle");
+  h->thr = kernel_threshold;
+  h->damping = damping;
+  h->min_inliers = min_num_inliers;
+  return VO_OK;
+}
+
+static int picp_init_common(vo_picp_s* h, const vo_camera* cam, int64_t n_world, int64_t n_image) {
+  h->cam = *cam;
+  h->have_cam = true;
+  h->n_world = n_world;
+  h->n_image = n_image;
+  return picp_upload_state(h);
+}
+
+int vo_picp_init(vo_picp_t h, const vo_camera* cam, const float* world_host, int64_t n_world,
+                 const float* image_host, int64_t n_image) {
+  VO_REQUIRE(h != nullptr && cam != nullptr, VO_ERR_ARG, "null handle/camera");
+  VO_REQUIRE(n_world >= 0 && n_image >= 0, VO_ERR_ARG, "negative size");
+  VO_REQUIRE((world_host || n_world == 0) && (image_host || n_image == 0), VO_ERR_ARG,
+             "null points");
+  DeviceGuard g(h->device);
+  int rc = h->world_buf.reserve((size_t)n_world * 12 + 16);
+  if (rc) return rc;
+  rc = h->image_buf.reserve((size_t)n_image * 8 + 16);
+  if (rc) return rc;
+  if (n_world)
+    VO_CUDA(cudaMemcpyAsync(h->world_buf.p, world_host, (size_t)n_world * 12,
+                            cudaMemcpyHostToDevice, h->stream));
+  if (n_image)
+    VO_CUDA(cudaMemcpyAsync(h->image_buf.p, image_host, (size_t)n_image * 8,
+                            cudaMemcpyHostToDevice, h->stream));
+  h->world = h->world_buf.as<float>();
+  h->image = h->image_buf.as<float>();
+  rc = picp_init_common(h, cam, n_world, n_image);
+  if (rc) return rc;
+  // the reference borrows the vectors; we own a copy, so the caller may reuse them right away
+  VO_CUDA(cudaStreamSynchronize(h->stream));
+  return VO_OK;
+}
+
+int vo_picp_init_device(vo_picp_t h, const vo_camera* cam, const float* world_dev, int64_t n_world,
+                        const float* image_dev, int64_t n_image) {
+  VO_REQUIRE(h != nullptr && cam != nullptr, VO_ERR_ARG, "null handle/camera");
+  VO_REQUIRE(n_world >= 0 && n_image >= 0, VO_ERR_ARG, "negative size");
+  VO_REQUIRE((world_dev || n_world == 0) && (image_dev || n_image == 0), VO_ERR_ARG, "null points");
+  VO_REQUIRE((reinterpret_cast<uintptr_t>(image_dev) & 7u) == 0, VO_ERR_ARG,
+             "image points must be 8-byte aligned");
+  DeviceGuard g(h->device);
+  h->world = world_dev;
+  h->image = image_dev;
+  return picp_init_common(h, cam, n_world, n_image);
+}
+
+int vo_picp_set_correspondences(vo_picp_t h, const int32_t* pairs_host, int64_t n_pairs) {
+  VO_REQUIRE(h != nullptr, VO_ERR_ARG, "null handle");
+  VO_REQUIRE(n_pairs >= 0 && (pairs_host || n_pairs == 0), VO_ERR_ARG, "bad pairs");
+  DeviceGuard g(h->device);
+  // bounds check on the host: the reference indexes with operator[] (UB when out of range);
+  // we refuse instead of reading out of bounds on the device.
+  for (int64_t i = 0; i < n_pairs; ++i) {
+    const int32_t a = pairs_host[2 * i], b = pairs_host[2 * i + 1];
+    if (a < 0 || a >= h->n_image || b < 0 || b >= h->n_world) {
+      set_error("vo_picp_set_correspondences: pair %lld = (%d,%d) out of range", (long long)i, a, b);
+      return VO_ERR_ARG;
+    }
+  }
+  int rc = h->pairs_buf.reserve((size_t)n_pairs * 8 + 16);
+  if (rc) return rc;
+  if (n_pairs)
+    VO_CUDA(cudaMemcpyAsync(h->pairs_buf.p, pairs_host, (size_t)n_pairs * 8,
+                            cudaMemcpyHostToDevice, h->stream));
+  VO_CUDA(cudaStreamSynchronize(h->stream));
+  h->pairs = h->pairs_buf.as<int32_t>();
+  h->n_pairs = n_pairs;
+  return VO_OK;
+}
+
+int vo_picp_set_correspondences_device(vo_picp_t h, const int32_t* pairs_dev, int64_t n_pairs) {
+  VO_REQUIRE(h != nullptr, VO_ERR_ARG, "null handle");
+  VO_REQUIRE(n_pairs >= 0 && (pairs_dev || n_pairs == 0), VO_ERR_ARG, "bad pairs");
+  VO_REQUIRE((reinterpret_cast<uintptr_t>(pairs_dev) & 7u) == 0, VO_ERR_ARG,
+             "pairs must be 8-byte aligned");
+  h->pairs = pairs_dev;
+  h->n_pairs = n_pairs;
+  return VO_OK;
+}
+
+int vo_picp_compute(vo_picp_t h, int keep_outliers, int rounds) {
+  VO_REQUIRE(h != nullptr, VO_ERR_ARG, "null handle");
+  VO_REQUIRE(h->have_cam, VO_ERR_STATE, "init not called");
+  VO_REQUIRE(rounds >= 0, VO_ERR_ARG, "negative rounds");
+  if (rounds == 0) return VO_OK;
+  DeviceGuard g(h->device);
+  const int grid = picp_pick_grid(h);
+  int rc = h->partials_buf.reserve((size_t)grid * PICP_NACC * sizeof(float));
+  if (rc) return rc;
+  PicpParams p;
+  picp_fill_params(h, keep_outliers, &p);
+
+  if (rounds < 4) {
+    for (int r = 0; r < rounds; ++r) {
+      picp_round_kernel<<<grid, PICP_THREADS, 0, h->stream>>>(p);
+      VO_LAUNCH_CHECK();
+    }
+    return VO_OK;
+  }
+  // many rounds: replay a captured graph of `rounds` launches (one submit, no per-launch
+  // driver work between rounds)
+  vo_picp_s::GraphKey key{h->world, h->image, h->pairs, h->partials_buf.p, h->n_pairs,
+                          p.keep_outliers, rounds, grid, h->thr, h->damping, h->min_inliers};
+  auto it = h->graphs.find(key);
+  if (it == h->graphs.end()) {
+    if (h->graphs.size() > 16) picp_drop_graphs(h);
+    cudaGraph_t graph = nullptr;
+    VO_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    for (int r = 0; r < rounds; ++r)
+      picp_round_kernel<<<grid, PICP_THREADS, 0, h->stream>>>(p);
+    cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    if (e != cudaSuccess) {
+      set_error("cudaStreamEndCapture -> %s", cudaGetErrorString(e));
+      return VO_ERR_CUDA;
+    }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+      set_error("cudaGraphInstantiate -> %s", cudaGetErrorString(e));
+      return VO_ERR_CUDA;
+    }
+    it = h->graphs.emplace(key, exec).first;
+  }
+  VO_CUDA(cudaGraphLaunch(it->second, h->stream));
+  g_launches.fetch_add(rounds);
+  return VO_OK;
+}
+
+int vo_picp_one_round(vo_picp_t h, const int32_t* pairs_host, int64_t n_pairs, int keep_outliers) {
+  int rc = vo_picp_set_correspondences(h, pairs_host, n_pairs);
+  if (rc) return rc;
+  return vo_picp_compute(h, keep_outliers, 1);
+}
+
+int vo_picp_get_state(vo_picp_t h, vo_picp_state* out) {
+  VO_REQUIRE(h != nullptr && out != nullptr, VO_ERR_ARG, "null pointer");
+  VO_REQUIRE(h->have_cam, VO_ERR_STATE, "init not called");
+  DeviceGuard g(h->device);
+  VO_CUDA(cudaMemcpyAsync(out, h->state_buf.p, sizeof(vo_picp_state), cudaMemcpyDeviceToHost,
+                          h->stream));
+  VO_CUDA(cudaStreamSynchronize(h->stream));
+  return VO_OK;
+}
+
+}  // extern "C"
