@@ -16,9 +16,13 @@ $(LIB): $(OBJS)
 	@mkdir -p $(dir $@)
 	$(NVCC) -shared -o $@ $(OBJS) -lcudart_static -lpthread -ldl -lrt
 
+# triangulate.cu mirrors the oracle's operation order exactly, so it is compiled without FMA
+# contraction (-fmad=false): its results are then bit-identical to the CPU restatement.
+build/triangulate.o: EXTRA := -fmad=false
+
 build/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p build
-	$(NVCC) $(NVCCFLAGS) -Xptxas -v -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
+	$(NVCC) $(NVCCFLAGS) $(EXTRA) -Xptxas -v -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
 
 oracle:
 	$(MAKE) -C oracle

@@ -312,6 +312,7 @@ using namespace vo;
 struct vo_picp_s {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t capture_stream = nullptr;
   bool own_stream = false;
   vo_camera cam{};
   bool have_cam = false;
@@ -414,6 +415,7 @@ int vo_picp_destroy(vo_picp_t h) {
   DeviceGuard g(h->device);
   cudaStreamSynchronize(h->stream);
   picp_drop_graphs(h);
+  if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
   h->world_buf.release();
   h->image_buf.release();
   h->pairs_buf.release();
@@ -560,10 +562,14 @@ int vo_picp_compute(vo_picp_t h, int keep_outliers, int rounds) {
   if (it == h->graphs.end()) {
     if (h->graphs.size() > 16) picp_drop_graphs(h);
     cudaGraph_t graph = nullptr;
-    VO_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    // capture on a private stream: the caller's stream may be the legacy default stream,
+    // which cannot be captured
+    if (!h->capture_stream)
+      VO_CUDA(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
+    VO_CUDA(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
     for (int r = 0; r < rounds; ++r)
-      picp_round_kernel<<<grid, PICP_THREADS, 0, h->stream>>>(p);
-    cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+      picp_round_kernel<<<grid, PICP_THREADS, 0, h->capture_stream>>>(p);
+    cudaError_t e = cudaStreamEndCapture(h->capture_stream, &graph);
     if (e != cudaSuccess) {
       set_error("cudaStreamEndCapture -> %s", cudaGetErrorString(e));
       return VO_ERR_CUDA;

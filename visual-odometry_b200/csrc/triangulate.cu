@@ -147,7 +147,7 @@ __device__ __forceinline__ bool project_point_dev(const ProjParams& q, float wx,
   const float hx = (q.K[0] * px + q.K[3] * py) + q.K[6] * pz;
   const float hy = (q.K[1] * px + q.K[4] * py) + q.K[7] * pz;
   const float hz = (q.K[2] * px + q.K[5] * py) + q.K[8] * pz;
-  const float iz = 1.0f / hz;
+  const float iz = (float)(1.0 / (double)hz);  // camera.h:31: 1./z is a double, then demoted
   uv->x = hx * iz;
   uv->y = hy * iz;
   if (uv->x < 0.f || uv->x > q.max_u) return false;

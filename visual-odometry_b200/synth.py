@@ -186,6 +186,9 @@ def two_view_problem(n, seed=7, f=150.0, noise=0.0):
     K = default_K(f)
     pts = frustum_points3d(rng, n, K)
     X = generate_isometry3f(rng, 0.2)
+    # a mostly lateral baseline of 0.4-0.6 keeps the two-ray intersection well conditioned
+    X[:3, 3] = np.array([rng.choice([-1.0, 1.0]) * rng.uniform(0.4, 0.6), rng.uniform(-0.1, 0.1),
+                         rng.uniform(-0.1, 0.1)], dtype=np.float32)
     p1, ok1 = project_np(K, np.eye(4, dtype=np.float32), pts)
     p2, ok2 = project_np(K, X, pts)
     if noise > 0:
