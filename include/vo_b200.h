@@ -51,6 +51,8 @@ int64_t vo_launch_count(void);
 /* measured FP32 FFMA throughput (TFLOP/s) of a register-resident FMA loop on `device`;
  * used only as a roofline denominator in bench.py                                        */
 int vo_measure_ffma_peak(int device, double* tflops_out);
+/* the same with packed fma.rn.f32x2 (SASS FFMA2, two FMAs per lane per instruction)          */
+int vo_measure_ffma2_peak(int device, double* tflops_out);
 
 /* ==== (1) appearance nearest neighbour =================================================
  * replaces bruteForceBestMatch / bruteForceSearch   include/brute_force_search.h:3-41

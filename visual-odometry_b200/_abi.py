@@ -45,6 +45,7 @@ PROTOTYPES = {
     "vo_device_count": (C.c_int, []),
     "vo_launch_count": (C.c_int64, []),
     "vo_measure_ffma_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    "vo_measure_ffma2_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "vo_nn_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "vo_nn_destroy": (C.c_int, [C.c_void_p]),
     "vo_nn_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -140,7 +141,9 @@ def device_count():
     return n
 
 
-def measure_ffma_peak(device=0):
+def measure_ffma_peak(device=0, packed=False):
+    """FP32 FMA throughput in TFLOP/s: scalar FFMA, or packed FFMA2 (fma.rn.f32x2)."""
     out = C.c_double(0.0)
-    check(lib().vo_measure_ffma_peak(device, C.byref(out)), "vo_measure_ffma_peak")
+    fn = lib().vo_measure_ffma2_peak if packed else lib().vo_measure_ffma_peak
+    check(fn(device, C.byref(out)), "vo_measure_ffma_peak")
     return out.value

@@ -53,6 +53,35 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, f
   if (s == 123.456f) out[0] = s;  // keep the chains alive
 }
 
+// the same loop with packed fma.rn.f32x2 (SASS FFMA2): two FMAs per lane per issue slot
+__global__ void __launch_bounds__(256) ffma2_peak_kernel(float* out, int iters, float a, float b) {
+  unsigned long long x[8], A, B;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(A) : "f"(a));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(B) : "f"(b));
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const float v = threadIdx.x * 1e-3f + u;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x[u]) : "f"(v), "f"(v + 0.5f));
+  }
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x[k]) : "l"(A), "l"(B));
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x[k]));
+    s += lo + hi;
+  }
+  if (s == 123.456f) out[0] = s;
+}
+
 }  // namespace vo
 
 using namespace vo;
@@ -75,7 +104,16 @@ int vo_device_count(void) {
 
 int64_t vo_launch_count(void) { return g_launches.load(); }
 
+static int measure_peak(int device, double* tflops_out, bool packed);
+
 int vo_measure_ffma_peak(int device, double* tflops_out) {
+  return measure_peak(device, tflops_out, false);
+}
+int vo_measure_ffma2_peak(int device, double* tflops_out) {
+  return measure_peak(device, tflops_out, true);
+}
+
+static int measure_peak(int device, double* tflops_out, bool packed) {
   VO_REQUIRE(tflops_out != nullptr, VO_ERR_ARG, "null output");
   DeviceGuard g(device);
   float* d = nullptr;
@@ -88,13 +126,14 @@ int vo_measure_ffma_peak(int device, double* tflops_out) {
   double best = 0.0;
   for (int rep = 0; rep < 5; ++rep) {
     VO_CUDA(cudaEventRecord(e0, 0));
-    ffma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999f, 1e-3f);
+    if (packed) ffma2_peak_kernel<<<blocks, threads>>>(d, iters, 0.999f, 1e-3f);
+    else ffma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999f, 1e-3f);
     VO_LAUNCH_CHECK();
     VO_CUDA(cudaEventRecord(e1, 0));
     VO_CUDA(cudaEventSynchronize(e1));
     float ms = 0.f;
     VO_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    const double flops = 2.0 * 8 * 16 * (double)iters * threads * (double)blocks;
+    const double flops = (packed ? 2.0 : 1.0) * 2.0 * 8 * 16 * (double)iters * threads * (double)blocks;
     const double tf = flops / (ms * 1e-3) / 1e12;
     if (rep > 0 && tf > best) best = tf;
   }

@@ -226,9 +226,29 @@ __device__ __noinline__ float nn_rescan_tile(const float4* __restrict__ tile, in
   return bound;
 }
 
+// packed FP32 pairs: sm_100a executes fma.rn.f32x2 as ONE FFMA2 issue slot for two FMAs, and
+// ptxas folds a {x,x} pair into a scalar-broadcast operand (FFMA2 Rd, Ra.F32x2, Rb.F32, Rc.F32x2),
+// so two queries share every map coefficient without any packing instruction.
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b,
+                                                     unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 template <int TQ, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 nn_filter_kernel(const NNParams p) {
+  static_assert(TQ % 2 == 0, "queries are processed in FFMA2 pairs");
+  constexpr int TP = TQ / 2;
   extern __shared__ __align__(128) unsigned char nn_smem[];
   float4* tiles = reinterpret_cast<float4*>(nn_smem);
   uint64_t* full = reinterpret_cast<uint64_t*>(nn_smem + NN_STAGES * NN_TILE_BYTES);
@@ -255,25 +275,33 @@ nn_filter_kernel(const NNParams p) {
       }
   }
 
-  // queries of this thread, pre-scaled by -2, plus their filter thresholds and exact bounds
+  // queries of this thread, pre-scaled by -2 and packed two-by-two (query 2j in the low half,
+  // 2j+1 in the high half), plus per-query filter thresholds, exact bounds and running minima
   const float mm_max = __ldg(p.mm_max);
-  float qn[TQ][NN_DIM];
+  unsigned long long q2[TP][NN_DIM];
   float tq[TQ], bound[TQ], mn[TQ];
 #pragma unroll
-  for (int j = 0; j < TQ; ++j) {
-    const int64_t qi = qbase + (int64_t)j * THREADS + tid;
-    if (qi < p.n_queries) {
-      const float* src = p.queries + qi * (int64_t)p.query_stride + p.skip;
+  for (int jp = 0; jp < TP; ++jp) {
+    float qn[2][NN_DIM];
 #pragma unroll
-      for (int k = 0; k < NN_DIM; ++k) qn[j][k] = -2.f * __ldg(src + k);
-      tq[j] = nn_filter_threshold(qn[j], p.bound, mm_max);
-    } else {
+    for (int h = 0; h < 2; ++h) {
+      const int j = 2 * jp + h;
+      const int64_t qi = qbase + (int64_t)j * THREADS + tid;
+      if (qi < p.n_queries) {
+        const float* src = p.queries + qi * (int64_t)p.query_stride + p.skip;
 #pragma unroll
-      for (int k = 0; k < NN_DIM; ++k) qn[j][k] = 0.f;
-      tq[j] = -INFINITY;
+        for (int k = 0; k < NN_DIM; ++k) qn[h][k] = -2.f * __ldg(src + k);
+        tq[j] = nn_filter_threshold(qn[h], p.bound, mm_max);
+      } else {
+#pragma unroll
+        for (int k = 0; k < NN_DIM; ++k) qn[h][k] = 0.f;
+        tq[j] = -INFINITY;
+      }
+      bound[j] = p.bound;
+      mn[j] = INFINITY;
     }
-    bound[j] = p.bound;
-    mn[j] = INFINITY;
+#pragma unroll
+    for (int k = 0; k < NN_DIM; ++k) q2[jp][k] = f2_pack(qn[0][k], qn[1][k]);
   }
 
   int stage = 0;
@@ -287,20 +315,23 @@ nn_filter_kernel(const NNParams p) {
       const float4 a = tile[r * 3 + 0];
       const float4 b = tile[r * 3 + 1];
       const float4 c = tile[r * 3 + 2];
+      const unsigned long long mm2 = f2_pack(c.z, c.z);
 #pragma unroll
-      for (int j = 0; j < TQ; ++j) {
-        float acc = c.z;
-        acc = fmaf(qn[j][0], a.x, acc);
-        acc = fmaf(qn[j][1], a.y, acc);
-        acc = fmaf(qn[j][2], a.z, acc);
-        acc = fmaf(qn[j][3], a.w, acc);
-        acc = fmaf(qn[j][4], b.x, acc);
-        acc = fmaf(qn[j][5], b.y, acc);
-        acc = fmaf(qn[j][6], b.z, acc);
-        acc = fmaf(qn[j][7], b.w, acc);
-        acc = fmaf(qn[j][8], c.x, acc);
-        acc = fmaf(qn[j][9], c.y, acc);
-        mn[j] = fminf(mn[j], acc);
+      for (int jp = 0; jp < TP; ++jp) {
+        unsigned long long acc = f2_fma(q2[jp][0], f2_pack(a.x, a.x), mm2);
+        acc = f2_fma(q2[jp][1], f2_pack(a.y, a.y), acc);
+        acc = f2_fma(q2[jp][2], f2_pack(a.z, a.z), acc);
+        acc = f2_fma(q2[jp][3], f2_pack(a.w, a.w), acc);
+        acc = f2_fma(q2[jp][4], f2_pack(b.x, b.x), acc);
+        acc = f2_fma(q2[jp][5], f2_pack(b.y, b.y), acc);
+        acc = f2_fma(q2[jp][6], f2_pack(b.z, b.z), acc);
+        acc = f2_fma(q2[jp][7], f2_pack(b.w, b.w), acc);
+        acc = f2_fma(q2[jp][8], f2_pack(c.x, c.x), acc);
+        acc = f2_fma(q2[jp][9], f2_pack(c.y, c.y), acc);
+        float lo, hi;
+        f2_unpack(acc, lo, hi);
+        mn[2 * jp] = fminf(mn[2 * jp], lo);
+        mn[2 * jp + 1] = fminf(mn[2 * jp + 1], hi);
       }
     }
 
@@ -309,12 +340,19 @@ nn_filter_kernel(const NNParams p) {
     for (int j = 0; j < TQ; ++j) {
       if (mn[j] < tq[j]) {
         const int64_t qi = qbase + (int64_t)j * THREADS + tid;
-        const float nb = nn_rescan_tile(tile, t * NN_TM, p.n_rows, qn[j][0], qn[j][1], qn[j][2],
-                                        qn[j][3], qn[j][4], qn[j][5], qn[j][6], qn[j][7],
-                                        qn[j][8], qn[j][9], tq[j], bound[j], p.keys + qi);
+        float qn[NN_DIM];
+#pragma unroll
+        for (int k = 0; k < NN_DIM; ++k) {
+          float lo, hi;
+          f2_unpack(q2[j >> 1][k], lo, hi);
+          qn[k] = (j & 1) ? hi : lo;
+        }
+        const float nb = nn_rescan_tile(tile, t * NN_TM, p.n_rows, qn[0], qn[1], qn[2], qn[3], qn[4],
+                                        qn[5], qn[6], qn[7], qn[8], qn[9], tq[j], bound[j],
+                                        p.keys + qi);
         if (nb < bound[j]) {
           bound[j] = nb;
-          tq[j] = fminf(tq[j], nn_filter_threshold(qn[j], nb, mm_max));
+          tq[j] = fminf(tq[j], nn_filter_threshold(qn, nb, mm_max));
         }
       }
       mn[j] = INFINITY;
@@ -470,7 +508,7 @@ static int nn_launch_filter(vo_nn_s* h, const float* queries_dev, int64_t nq, in
   };
   if (nq > 8192) return launch(nn_filter_kernel<8, 256>, 8, 256);
   if (nq > 1024) return launch(nn_filter_kernel<2, 256>, 2, 256);
-  return launch(nn_filter_kernel<1, 128>, 1, 128);
+  return launch(nn_filter_kernel<2, 64>, 2, 64);
 }
 
 static int nn_set_map_common(vo_nn_s* h, const float* rows_dev, int64_t n_rows, int row_stride,

@@ -109,6 +109,8 @@ __device__ void picp_solve_and_update(const PicpParams& p, const float* tot) {
 }
 
 // One correspondence: errorAndJacobian (:25-53) + the body of linearize's loop (:62-95).
+// Branch-free: a rejected point (or a padding slot past the end, live == false) runs the same
+// instructions with weight 0, so a warp never diverges on the data.
 struct PicpAcc {
   float h[21];
   float b[6];
@@ -116,22 +118,34 @@ struct PicpAcc {
   int n_in;
 };
 
-__device__ __forceinline__ void picp_point(const PicpParams& p, const float (&T)[12], float wx,
-                                           float wy, float wz, float mu, float mv, PicpAcc& a) {
+// 1/x to within 1 ulp without the IEEE-division slow path: MUFU.RCP + one Newton step
+__device__ __forceinline__ float picp_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  const float e = fmaf(-x, r, 1.0f);
+  return fmaf(r, e, r);
+}
+
+__device__ __forceinline__ void picp_point(const PicpParams& p, const float (&T)[12], bool live,
+                                           float wx, float wy, float wz, float mu, float mv,
+                                           PicpAcc& a) {
   // camera_point = world_in_camera * world_point  (camera.h:27, picp_solver.cpp:38)
-  const float px = fmaf(T[6], wz, fmaf(T[3], wy, T[0] * wx)) + T[9];
-  const float py = fmaf(T[7], wz, fmaf(T[4], wy, T[1] * wx)) + T[10];
-  const float pz = fmaf(T[8], wz, fmaf(T[5], wy, T[2] * wx)) + T[11];
-  if (pz > p.z_far || pz < p.z_near) return;  // camera.h:28
+  float px = fmaf(T[6], wz, fmaf(T[3], wy, fmaf(T[0], wx, T[9])));
+  float py = fmaf(T[7], wz, fmaf(T[4], wy, fmaf(T[1], wx, T[10])));
+  float pz = fmaf(T[8], wz, fmaf(T[5], wy, fmaf(T[2], wx, T[11])));
+  bool valid = live && !(pz > p.z_far || pz < p.z_near);  // camera.h:28
+  // a rejected point continues as the harmless dummy (0,0,1) so that nothing overflows
+  px = valid ? px : 0.f;
+  py = valid ? py : 0.f;
+  pz = valid ? pz : 1.f;
   // phom = K * camera_point  (camera.h:30, picp_solver.cpp:43)
   const float hx = fmaf(p.K[6], pz, fmaf(p.K[3], py, p.K[0] * px));
   const float hy = fmaf(p.K[7], pz, fmaf(p.K[4], py, p.K[1] * px));
   const float hz = fmaf(p.K[8], pz, fmaf(p.K[5], py, p.K[2] * px));
-  const float iz = 1.0f / hz;  // camera.h:31 / picp_solver.cpp:44 (IEEE division)
+  const float iz = picp_rcp(hz);  // camera.h:31 / picp_solver.cpp:44
   const float u = hx * iz, v = hy * iz;
-  if (u < 0.f || u > p.max_u) return;  // camera.h:32
-  if (v < 0.f || v > p.max_v) return;  // camera.h:34
-  const float e0 = u - mu, e1 = v - mv;  // :35
+  valid = valid && !(u < 0.f || u > p.max_u) && !(v < 0.f || v > p.max_v);  // camera.h:32-35
+  const float e0 = u - mu, e1 = v - mv;                                      // :35
   // A = Jp*K with Jp = [iz 0 -hx*iz^2; 0 iz -hy*iz^2]  ==  iz * (K_row{0,1} - {u,v} * K_row2)
   float J0[6], J1[6];
 #pragma unroll
@@ -147,21 +161,19 @@ __device__ __forceinline__ void picp_point(const PicpParams& p, const float (&T)
   J1[4] = fmaf(J1[0], pz, -J1[2] * px);
   J1[5] = fmaf(J1[1], px, -J1[0] * py);
   const float chi = fmaf(e1, e1, e0 * e0);  // :75
-  float lambda = 1.f;
-  if (chi > p.thr) {  // :78-83
-    a.chi_out += chi;
-    if (!p.keep_outliers) return;  // :90
-    lambda = sqrtf(p.thr / chi);
-  } else {  // :84-88
-    a.chi_in += chi;
-    a.n_in += 1;
-  }
+  const bool outlier = chi > p.thr;         // :78
+  float lambda = outlier ? 0.f : 1.f;       // dropped outliers weigh 0 (:90)
+  if (outlier && p.keep_outliers) lambda = sqrtf(p.thr / chi);  // :80
+  const float w = valid ? lambda : 0.f;
+  a.chi_out += (valid && outlier) ? chi : 0.f;   // :82
+  a.chi_in += (valid && !outlier) ? chi : 0.f;   // :86
+  a.n_in += (valid && !outlier) ? 1 : 0;         // :87
   // H += J^T J * lambda ; b += J^T e * lambda   (:92-93)
   float L0[6], L1[6];
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    L0[j] = J0[j] * lambda;
-    L1[j] = J1[j] * lambda;
+    L0[j] = J0[j] * w;
+    L1[j] = J1[j] * w;
   }
   int k = 0;
 #pragma unroll
@@ -175,10 +187,39 @@ __device__ __forceinline__ void picp_point(const PicpParams& p, const float (&T)
   }
 }
 
+struct PicpBatch {
+  float w[PICP_UNROLL][3];
+  float2 m[PICP_UNROLL];
+};
+
+// pairs of one batch; slots past the end re-read the last pair (always in bounds) and are
+// masked out with live == false when they are consumed
+__device__ __forceinline__ void picp_load_pairs(const PicpParams& p, int64_t base, int64_t stride,
+                                                int2 (&pr)[PICP_UNROLL]) {
+#pragma unroll
+  for (int u = 0; u < PICP_UNROLL; ++u) {
+    int64_t i = base + u * stride;
+    i = i < p.n_pairs ? i : p.n_pairs - 1;
+    pr[u] = __ldg(p.pairs + i);
+  }
+}
+__device__ __forceinline__ void picp_gather(const PicpParams& p, const int2 (&pr)[PICP_UNROLL],
+                                            PicpBatch& b) {
+#pragma unroll
+  for (int u = 0; u < PICP_UNROLL; ++u) {
+    const float* wp = p.world + 3 * (int64_t)pr[u].y;  // .second -> world (:67)
+    b.w[u][0] = __ldg(wp);
+    b.w[u][1] = __ldg(wp + 1);
+    b.w[u][2] = __ldg(wp + 2);
+    b.m[u] = __ldg(reinterpret_cast<const float2*>(p.image) + pr[u].x);  // .first -> image (:66)
+  }
+}
+
 __global__ void __launch_bounds__(PICP_THREADS, 2) picp_round_kernel(const PicpParams p) {
   __shared__ float s_red[PICP_THREADS / 32][PICP_NACC];
   __shared__ bool s_last;
   const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
 
   float T[12];
 #pragma unroll
@@ -194,32 +235,27 @@ __global__ void __launch_bounds__(PICP_THREADS, 2) picp_round_kernel(const PicpP
   a.chi_in = a.chi_out = 0.f;
   a.n_in = 0;
 
+  // ---- software-pipelined stream over the correspondences --------------------------------------
+  // while batch k is being linearised, the point gathers of batch k+1 and the pair loads of batch
+  // k+2 are in flight, so every warp always has independent loads outstanding
   const int64_t stride = (int64_t)gridDim.x * PICP_THREADS;
-  for (int64_t base = (int64_t)blockIdx.x * PICP_THREADS + tid; base < p.n_pairs;
-       base += stride * PICP_UNROLL) {
-    int2 pr[PICP_UNROLL];
-    bool ok[PICP_UNROLL];
+  const int64_t step = stride * PICP_UNROLL;
+  int64_t base = (int64_t)blockIdx.x * PICP_THREADS + tid;
+  if (p.n_pairs > 0 && base < p.n_pairs) {
+    int2 pr_next[PICP_UNROLL];
+    PicpBatch cur, nxt;
+    picp_load_pairs(p, base, stride, pr_next);
+    picp_gather(p, pr_next, cur);
+    picp_load_pairs(p, base + step, stride, pr_next);
+    for (; base < p.n_pairs; base += step) {
+      picp_gather(p, pr_next, nxt);                         // batch k+1 points
+      picp_load_pairs(p, base + 2 * step, stride, pr_next);  // batch k+2 pairs
 #pragma unroll
-    for (int u = 0; u < PICP_UNROLL; ++u) {
-      const int64_t i = base + u * stride;
-      ok[u] = i < p.n_pairs;
-      pr[u] = ok[u] ? __ldg(p.pairs + i) : make_int2(0, 0);
+      for (int u = 0; u < PICP_UNROLL; ++u)
+        picp_point(p, T, base + u * stride < p.n_pairs, cur.w[u][0], cur.w[u][1], cur.w[u][2],
+                   cur.m[u].x, cur.m[u].y, a);
+      cur = nxt;
     }
-    float w[PICP_UNROLL][3];
-    float2 m[PICP_UNROLL];
-#pragma unroll
-    for (int u = 0; u < PICP_UNROLL; ++u) {
-      if (ok[u]) {
-        const float* wp = p.world + 3 * (int64_t)pr[u].y;  // .second -> world (:67)
-        w[u][0] = __ldg(wp);
-        w[u][1] = __ldg(wp + 1);
-        w[u][2] = __ldg(wp + 2);
-        m[u] = __ldg(reinterpret_cast<const float2*>(p.image) + pr[u].x);  // .first -> image (:66)
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < PICP_UNROLL; ++u)
-      if (ok[u]) picp_point(p, T, w[u][0], w[u][1], w[u][2], m[u].x, m[u].y, a);
   }
 
   // ---- block reduction: shuffle within the warp, fixed-order sum across warps ----------------
@@ -237,7 +273,6 @@ __global__ void __launch_bounds__(PICP_THREADS, 2) picp_round_kernel(const PicpP
     for (int i = 0; i < 29; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
     n_in += __shfl_xor_sync(0xffffffffu, n_in, o);
   }
-  const int warp = tid >> 5, lane = tid & 31;
   if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < 29; ++i) s_red[warp][i] = v[i];
@@ -270,15 +305,24 @@ __global__ void __launch_bounds__(PICP_THREADS, 2) picp_round_kernel(const PicpP
   if (!s_last) return;
   __threadfence();
   {
-    // warp w sums blocks w, w+W, ... for component `lane`; then warp 0 sums the W rows
+    // warp w sums blocks w, w+W, ... for component `lane` (8 independent loads in flight per
+    // step, combined in a fixed order); then warp 0 sums the W rows
     constexpr int W = PICP_THREADS / 32;
+    constexpr int B = 8;
     float s = 0.f;
     int si = 0;
-    if (lane < 30) {
-      for (int bk = warp; bk < (int)gridDim.x; bk += W) {
-        const float x = __ldcg(p.partials + (int64_t)bk * PICP_NACC + lane);
-        if (lane < 29) s += x;
-        else si += __float_as_int(x);
+    const int nb = (int)gridDim.x;
+    for (int bk0 = warp; bk0 < nb; bk0 += W * B) {
+      float x[B];
+#pragma unroll
+      for (int q = 0; q < B; ++q) {
+        const int bk = bk0 + q * W;
+        x[q] = (bk < nb && lane < 30) ? __ldcg(p.partials + (int64_t)bk * PICP_NACC + lane) : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < B; ++q) {
+        if (lane == 29) si += __float_as_int(x[q]);
+        else s += x[q];
       }
     }
     __syncthreads();

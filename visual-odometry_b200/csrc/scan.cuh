@@ -30,60 +30,32 @@ inline ScanWorkspace scan_workspace_at(void* base, int64_t num_tiles) {
 }
 
 #ifdef __CUDACC__
+// The status word carries flag and count in ONE 64-bit value and nothing else is published
+// through it, so relaxed (L2-coherent, non-caching) accesses are sufficient — an acquire load
+// would invalidate the SM's L1 on every poll.
 __device__ __forceinline__ unsigned long long scan_ld(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void scan_st(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Executed by ONE full warp of the block.  `total` = successes in this tile (warp-uniform).
-// Returns the number of successes in all earlier tiles.
-__device__ __forceinline__ long long scan_lookback(unsigned long long* status, int tile,
-                                                   long long total) {
-  const int lane = threadIdx.x & 31;
-  if (tile == 0) {
-    if (lane == 0) scan_st(status, SCAN_PREFIX | (unsigned long long)total);
-    return 0;
-  }
-  if (lane == 0) scan_st(status + tile, SCAN_AGG | (unsigned long long)total);
-  long long excl = 0;
-  int idx = tile - 1;
-  while (true) {
-    const int j = idx - lane;
-    unsigned long long v = SCAN_PREFIX;  // "tiles before tile 0": prefix 0
-    if (j >= 0) {
-      do {
-        v = scan_ld(status + j);
-      } while ((v >> 62) == 0ull);
-    }
-    const unsigned pm = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
-    const int first = pm ? (__ffs(pm) - 1) : 32;
-    long long c = (lane <= first) ? (long long)(v & SCAN_MASK) : 0ll;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    excl += c;
-    if (pm) break;
-    idx -= 32;
-  }
-  if (lane == 0) scan_st(status + tile, SCAN_PREFIX | (unsigned long long)(excl + total));
-  return excl;
-}
-
-// Block-wide helper: given each thread's per-item flags (ITEMS of them, item j of lane l of warp
-// w sits at tile position w*32*ITEMS + j*32 + l) computes for every item its global output rank.
-// Returns the exclusive prefix of the tile and the tile total through the out-params; rank[j] is
-// only meaningful where flag[j] is set.
+// Block-wide helper: given each thread's per-item flags (ITEMS of them; item j of lane l of warp
+// w sits at tile position w*32*ITEMS + j*32 + l) computes every item's global output rank.
+// The look-back is done by the WHOLE block: thread i inspects predecessor tile-1-i, so one
+// round covers THREADS predecessors — the prefix front advances THREADS tiles per L2 round trip
+// instead of 32, which keeps the serial chain far above HBM speed.
+// rank[j] is only meaningful where flag[j] is set.
 template <int THREADS, int ITEMS>
 __device__ __forceinline__ void scan_tile_ranks(const ScanWorkspace& ws, int tile,
                                                 const bool (&flag)[ITEMS], long long (&rank)[ITEMS],
                                                 long long* tile_excl, int* tile_total) {
   constexpr int WARPS = THREADS / 32;
   __shared__ int s_warp_tot[WARPS];
-  __shared__ long long s_excl;
-  __shared__ int s_total;
+  __shared__ long long s_lb_sum[WARPS];
+  __shared__ int s_lb_has[WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
   int local[ITEMS];
@@ -96,28 +68,57 @@ __device__ __forceinline__ void scan_tile_ranks(const ScanWorkspace& ws, int til
   }
   if (lane == 0) s_warp_tot[warp] = run;
   __syncthreads();
-  if (warp == 0) {
-    int x = (lane < WARPS) ? s_warp_tot[lane] : 0;
-    int incl = x;
+  int warp_off = 0, total = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += y;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (lane < WARPS) s_warp_tot[lane] = incl - x;  // exclusive warp offsets
-    const long long excl = scan_lookback(ws.status, tile, (long long)total);
-    if (lane == 0) {
-      s_excl = excl;
-      s_total = total;
-    }
+  for (int w = 0; w < WARPS; ++w) {
+    const int x = s_warp_tot[w];
+    warp_off += (w < warp) ? x : 0;
+    total += x;
   }
-  __syncthreads();
-  const long long base = s_excl + s_warp_tot[warp];
+  long long excl = 0;
+  if (tile == 0) {
+    if (threadIdx.x == 0) scan_st(ws.status, SCAN_PREFIX | (unsigned long long)total);
+  } else {
+    if (threadIdx.x == 0) scan_st(ws.status + tile, SCAN_AGG | (unsigned long long)total);
+    int idx = tile - 1;
+    while (true) {
+      const int j = idx - (int)threadIdx.x;
+      unsigned long long v = SCAN_PREFIX;  // "tiles before tile 0": prefix 0
+      if (j >= 0) {
+        do {
+          v = scan_ld(ws.status + j);
+        } while ((v >> 62) == 0ull);
+      }
+      const unsigned pm = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
+      const int first = pm ? (__ffs(pm) - 1) : 32;
+      long long c = (lane <= first) ? (long long)(v & SCAN_MASK) : 0ll;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      __syncthreads();  // previous round's (and s_warp_tot's) readers are done
+      if (lane == 0) {
+        s_lb_sum[warp] = c;
+        s_lb_has[warp] = pm != 0u;
+      }
+      __syncthreads();
+      bool done = false;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) {
+        if (!done) {
+          excl += s_lb_sum[w];
+          done = s_lb_has[w] != 0;
+        }
+      }
+      if (done) break;
+      idx -= THREADS;
+    }
+    if (threadIdx.x == 0)
+      scan_st(ws.status + tile, SCAN_PREFIX | (unsigned long long)(excl + total));
+  }
+  const long long base = excl + warp_off;
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) rank[j] = base + local[j];
-  *tile_excl = s_excl;
-  *tile_total = s_total;
+  *tile_excl = excl;
+  *tile_total = total;
 }
 #endif
 
