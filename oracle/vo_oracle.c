@@ -98,13 +98,17 @@ void oracle_nn_radius_search(const float* map, int64_t n_rows, int row_stride, i
 /* ------------------------------------------------------------------------------------------
  * small fixed-size algebra, column-major, one rounding per operation
  * ---------------------------------------------------------------------------------------- */
+/* Fixed-size products are coefficient-based in Eigen: each coefficient is
+ * lhs.row(i).cwiseProduct(rhs.col(j)).sum(), and a 3-term sum is unrolled by halves
+ * (redux_novec_unroller):  s0 + (s1 + s2). */
 static void mat3_vec(const float* M, const float v[3], float out[3]) {
-  for (int i = 0; i < 3; ++i) out[i] = (M[i] * v[0] + M[3 + i] * v[1]) + M[6 + i] * v[2];
+  for (int i = 0; i < 3; ++i) out[i] = M[i] * v[0] + (M[3 + i] * v[1] + M[6 + i] * v[2]);
 }
-/* Isometry3f * Vector3f = linear*v + translation (T is a column-major 4x4). */
+/* Isometry3f * Vector3f: res = translation; res += linear*v  (Transform.h,
+ * transform_right_product_impl) -> t + (s0 + (s1 + s2)).  T is a column-major 4x4. */
 static void iso_point(const float* T, const float p[3], float out[3]) {
   for (int i = 0; i < 3; ++i)
-    out[i] = ((T[i] * p[0] + T[4 + i] * p[1]) + T[8 + i] * p[2]) + T[12 + i];
+    out[i] = T[12 + i] + (T[i] * p[0] + (T[4 + i] * p[1] + T[8 + i] * p[2]));
 }
 
 /* camera.h:25-37 */
@@ -231,7 +235,7 @@ void oracle_ldlt_solve(int n, const float* A_in, const float* rhs, float* x) {
 static void mat3_mul(const float* A, const float* B, float* C) {
   for (int j = 0; j < 3; ++j)
     for (int i = 0; i < 3; ++i)
-      C[j * 3 + i] = (A[i] * B[j * 3] + A[3 + i] * B[j * 3 + 1]) + A[6 + i] * B[j * 3 + 2];
+      C[j * 3 + i] = A[i] * B[j * 3] + (A[3 + i] * B[j * 3 + 1] + A[6 + i] * B[j * 3 + 2]);
 }
 void oracle_v2t_euler(const float v[6], float T[16]) {
   const float sx = sinf(v[3]), cx = cosf(v[3]);
@@ -274,12 +278,12 @@ static int picp_error_and_jacobian(const oracle_camera* cam, const float wp[3],
   float A[6];
   for (int j = 0; j < 3; ++j)
     for (int i = 0; i < 2; ++i)
-      A[j * 2 + i] = (Jp[i] * cam->K[j * 3] + Jp[2 + i] * cam->K[j * 3 + 1]) +
-                     Jp[4 + i] * cam->K[j * 3 + 2];
+      A[j * 2 + i] = Jp[i] * cam->K[j * 3] +
+                     (Jp[2 + i] * cam->K[j * 3 + 1] + Jp[4 + i] * cam->K[j * 3 + 2]);
   for (int j = 0; j < 3; ++j)
     for (int i = 0; i < 2; ++i) {
       J[j * 2 + i] = A[j * 2 + i];
-      J[(3 + j) * 2 + i] = (A[i] * S[j * 3] + A[2 + i] * S[j * 3 + 1]) + A[4 + i] * S[j * 3 + 2];
+      J[(3 + j) * 2 + i] = A[i] * S[j * 3] + (A[2 + i] * S[j * 3 + 1] + A[4 + i] * S[j * 3 + 2]);
     }
   return 1;
 }
@@ -343,7 +347,7 @@ int oracle_picp_one_round(oracle_picp_state* st, const oracle_camera* cam_params
   /* :110  pose <- D * pose (isometry product: R = Rd*R, t = Rd*t + td) */
   for (int j = 0; j < 4; ++j)
     for (int i = 0; i < 3; ++i) {
-      float acc = (D[i] * st->T[j * 4] + D[4 + i] * st->T[j * 4 + 1]) + D[8 + i] * st->T[j * 4 + 2];
+      float acc = D[i] * st->T[j * 4] + (D[4 + i] * st->T[j * 4 + 1] + D[8 + i] * st->T[j * 4 + 2]);
       if (j == 3) acc = acc + D[12 + i];
       Tn[j * 4 + i] = acc;
     }
@@ -460,23 +464,21 @@ int oracle_picp_one_round_f64(double T[16], double H[36], double b[6], double st
 /* ------------------------------------------------------------------------------------------
  * triangulation
  * ---------------------------------------------------------------------------------------- */
-/* 3x3 inverse by cofactors / determinant (what Eigen's fixed-size inverse() does). */
+/* Matrix3f::inverse(): Eigen's compute_inverse_size3 — cofactor_3x3<i,j> with cyclic indices,
+ * determinant = cofactors_col0 . matrix.col(0) (3-term sum by halves), result(i,j) =
+ * cofactor<j,i> * (1/det). */
+static float cof3(const float* M, int i, int j) {
+  const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+#define m(r, c) M[(c) * 3 + (r)]
+  return m(i1, j1) * m(i2, j2) - m(i1, j2) * m(i2, j1);
+}
 static void mat3_inverse(const float* M, float* out) {
-#define m(i, j) M[(j) * 3 + (i)]
-  const float c00 = m(1, 1) * m(2, 2) - m(1, 2) * m(2, 1);
-  const float c10 = m(1, 2) * m(2, 0) - m(1, 0) * m(2, 2);
-  const float c20 = m(1, 0) * m(2, 1) - m(1, 1) * m(2, 0);
-  const float det = (m(0, 0) * c00 + m(0, 1) * c10) + m(0, 2) * c20;
+  const float c0 = cof3(M, 0, 0), c1 = cof3(M, 1, 0), c2 = cof3(M, 2, 0);
+  const float det = c0 * m(0, 0) + (c1 * m(1, 0) + c2 * m(2, 0));
   const float id = 1.f / det;
-  out[0] = c00 * id;
-  out[1] = c10 * id;
-  out[2] = c20 * id;
-  out[3] = (m(0, 2) * m(2, 1) - m(0, 1) * m(2, 2)) * id;
-  out[4] = (m(0, 0) * m(2, 2) - m(0, 2) * m(2, 0)) * id;
-  out[5] = (m(0, 1) * m(2, 0) - m(0, 0) * m(2, 1)) * id;
-  out[6] = (m(0, 1) * m(1, 2) - m(0, 2) * m(1, 1)) * id;
-  out[7] = (m(0, 2) * m(1, 0) - m(0, 0) * m(1, 2)) * id;
-  out[8] = (m(0, 0) * m(1, 1) - m(0, 1) * m(1, 0)) * id;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      out[j * 3 + i] = (i == 0 ? (j == 0 ? c0 : (j == 1 ? c1 : c2)) : cof3(M, j, i)) * id;
 #undef m
 }
 
@@ -485,12 +487,12 @@ static int triangulate_point(const float d1[3], const float d2[3], const float p
   /* D = [-d1 d2];  ss = -(D^T D).ldlt().solve(D^T p2)   :37-40 */
   float nd1[3] = {-d1[0], -d1[1], -d1[2]};
   float A[4], rhs[2], ss[2];
-  A[0] = (nd1[0] * nd1[0] + nd1[1] * nd1[1]) + nd1[2] * nd1[2];
-  A[1] = (d2[0] * nd1[0] + d2[1] * nd1[1]) + d2[2] * nd1[2];
-  A[2] = (nd1[0] * d2[0] + nd1[1] * d2[1]) + nd1[2] * d2[2];
-  A[3] = (d2[0] * d2[0] + d2[1] * d2[1]) + d2[2] * d2[2];
-  rhs[0] = (nd1[0] * p2[0] + nd1[1] * p2[1]) + nd1[2] * p2[2];
-  rhs[1] = (d2[0] * p2[0] + d2[1] * p2[1]) + d2[2] * p2[2];
+  A[0] = nd1[0] * nd1[0] + (nd1[1] * nd1[1] + nd1[2] * nd1[2]);
+  A[1] = d2[0] * nd1[0] + (d2[1] * nd1[1] + d2[2] * nd1[2]);
+  A[2] = nd1[0] * d2[0] + (nd1[1] * d2[1] + nd1[2] * d2[2]);
+  A[3] = d2[0] * d2[0] + (d2[1] * d2[1] + d2[2] * d2[2]);
+  rhs[0] = nd1[0] * p2[0] + (nd1[1] * p2[1] + nd1[2] * p2[2]);
+  rhs[1] = d2[0] * p2[0] + (d2[1] * p2[1] + d2[2] * p2[2]);
   oracle_ldlt_solve(2, A, rhs, ss);
   ss[0] = -ss[0];
   ss[1] = -ss[1];

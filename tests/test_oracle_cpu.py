@@ -207,3 +207,22 @@ def test_synth_hash_numpy_torch_identical(synth):
     m = synth.nn_map_rows_np(0, 5000)
     exact = (np.arange(64) % 4) < 2
     assert np.array_equal(q[exact, 1:], m[target[exact], 1:])
+
+
+def test_device_ldlt_source_is_bit_identical_to_oracle_on_host(tmp_path):
+    """linalg.cuh's register-resident LDL^T (what the PICP and triangulation kernels run) is
+    plain C++: compile it for the host without FMA contraction and compare it bit for bit with
+    oracle_ldlt_solve on SPD, indefinite, singular and badly scaled systems."""
+    import subprocess
+
+    root = os.path.dirname(HERE)
+    exe = str(tmp_path / "ldlt_host_check")
+    subprocess.check_call(["make", "-C", os.path.join(root, "oracle")], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17",
+                           "-I", os.path.join(root, "visual-odometry_b200", "csrc"),
+                           os.path.join(HERE, "ldlt_host_check.cpp"),
+                           os.path.join(root, "oracle", "libvo_oracle.so"),
+                           "-Wl,-rpath," + os.path.join(root, "oracle"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "bad6=0 bad2=0" in out.stdout

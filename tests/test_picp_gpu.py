@@ -126,3 +126,53 @@ def test_large_n_vs_f64_truth(vo, oracle, synth):
     assert s.numInliers() == int(o.stats64[2])
     print("oracle(float,sequential) vs f64:", rel(o.H(), o.H64m()), " gpu vs f64:", rel(H, o.H64m()))
     s.close()
+
+
+def test_pinhole_kernel_bit_identical_to_general(vo, synth, monkeypatch):
+    """K = [fx 0 cx; 0 fy cy; 0 0 1] selects the structurally-sparse instantiation; it must give
+    the same bits as the general-K kernel (forced with VO_PICP_FORCE_GENERAL=1)."""
+    pr = synth.picp_problem(30000, seed=26, outlier_frac=0.1)
+    cam = vo.Camera(pr["rows"], pr["cols"], pr["z_near"], pr["z_far"], pr["K"], np.eye(4))
+    res = []
+    for force in ("0", "1"):
+        monkeypatch.setenv("VO_PICP_FORCE_GENERAL", force)
+        for keep in (False, True):
+            s = vo.PICPSolver(0)
+            s.setKernelThreshold(500.0)
+            s.init(cam, pr["world"], pr["image"])
+            s.set_correspondences(pr["pairs"])
+            s.compute(keep, 5)
+            st = s.state()
+            res.append((force, keep, list(st.T), list(st.H), list(st.b), st.chi_inliers,
+                        st.chi_outliers, st.num_inliers))
+            s.close()
+    assert res[0][2:] == res[2][2:]
+    assert res[1][2:] == res[3][2:]
+
+
+def test_general_camera_matrix(vo, oracle, synth):
+    """a K with skew and a non-unit K22 goes through the general kernel."""
+    pr = synth.picp_problem(5000, seed=27)
+    K = pr["K"].copy()
+    K[0, 1] = 0.7
+    K[2, 2] = 1.0
+    K[1, 0] = 0.01
+    uv, ok = synth.project_np(K, pr["T_gt"], pr["world"])
+    _, ok0 = synth.project_np(K, np.eye(4, dtype=np.float32), pr["world"])
+    keep = np.nonzero(ok & ok0)[0].astype(np.int32)
+    pairs = np.stack([keep, keep], 1).astype(np.int32)
+    cam = vo.Camera(480, 640, 0, 10, K, np.eye(4))
+    ocam = oracle.make_camera(480, 640, 0, 10, K, np.eye(4))
+    s = vo.PICPSolver(0)
+    s.setKernelThreshold(10000.0)
+    s.init(cam, pr["world"], uv)
+    o = oracle.PicpOracle(ocam, pr["world"], uv, thr=10000.0)
+    for r in range(10):
+        s.oneRound(pairs, False)
+        o.one_round_f64(pairs, False)
+        if r == 0:
+            assert rel(s.H(), o.H64m()) <= TOL
+            assert rel(s.b(), o.b64) <= TOL
+        assert rel(s.pose(), o.pose64()) <= 20 * TOL
+    assert np.allclose(s.pose(), pr["T_gt"], atol=5e-4)
+    s.close()

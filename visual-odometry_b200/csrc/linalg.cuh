@@ -1,89 +1,107 @@
 // linalg.cuh — tiny fixed-size device linear algebra shared by picp.cu and triangulate.cu.
 #pragma once
+#include <math.h>
+#ifdef __CUDACC__
 #include "common.cuh"
+#endif
 
 namespace vo {
 
 // ---- pivoted LDL^T solve, same algorithm as Eigen's LDLT (picp_solver.cpp:109) -------------
+#if defined(__CUDACC__)
+#define VO_HD __host__ __device__ __forceinline__
+#else
+#define VO_HD inline
+#endif
+
+// Pivoted LDL^T solve with the operation sequence of Eigen's LDLT (ldlt_inplace<Lower>::unblocked
+// + LDLT::_solve_impl; picp_solver.cpp:109, utils.cpp:40) — the same sequence as
+// oracle_ldlt_solve.  Everything lives in registers: all loops have compile-time bounds after
+// unrolling, and the only run-time quantity, the pivot row, is applied through conditional swaps
+// with static indices, so no local-memory array is ever indexed dynamically (the single thread
+// that solves the 6x6 system sits on the critical path of every Gauss-Newton round).
 template <int N>
-__device__ void ldlt_solve_dev(float* A /* N*N col-major, destroyed */, const float* rhs, float* x) {
+VO_HD void ldlt_solve_dev(float* A /* N*N col-major, destroyed */, const float* rhs, float* x) {
   int tr[N];
-  float tmp[N];
 #define AT(i, j) A[(j) * N + (i)]
+#define VO_CSWAP(c, u, v)       \
+  {                             \
+    const float _a = (u), _b = (v); \
+    (u) = (c) ? _b : _a;        \
+    (v) = (c) ? _a : _b;        \
+  }
+#pragma unroll
   for (int k = 0; k < N; ++k) {
     int piv = k;
     float big = fabsf(AT(k, k));
-    for (int i = k + 1; i < N; ++i)
-      if (fabsf(AT(i, i)) > big) {
-        big = fabsf(AT(i, i));
-        piv = i;
-      }
-    tr[k] = piv;
-    if (piv != k) {
-      for (int j = 0; j < k; ++j) {
-        const float t = AT(k, j);
-        AT(k, j) = AT(piv, j);
-        AT(piv, j) = t;
-      }
-      for (int i = piv + 1; i < N; ++i) {
-        const float t = AT(i, k);
-        AT(i, k) = AT(i, piv);
-        AT(i, piv) = t;
-      }
-      {
-        const float t = AT(k, k);
-        AT(k, k) = AT(piv, piv);
-        AT(piv, piv) = t;
-      }
-      for (int i = k + 1; i < piv; ++i) {
-        const float t = AT(i, k);
-        AT(i, k) = AT(piv, i);
-        AT(piv, i) = t;
-      }
+#pragma unroll
+    for (int i = k + 1; i < N; ++i) {
+      const float d = fabsf(AT(i, i));
+      const bool g = d > big;
+      big = g ? d : big;
+      piv = g ? i : piv;
     }
-    const int rs = N - k - 1;
+    tr[k] = piv;
+#pragma unroll
+    for (int c = k + 1; c < N; ++c) {  // symmetric swap k <-> c inside the lower triangle
+      const bool sw = (piv == c);
+#pragma unroll
+      for (int j = 0; j < k; ++j) VO_CSWAP(sw, AT(k, j), AT(c, j));
+#pragma unroll
+      for (int i = c + 1; i < N; ++i) VO_CSWAP(sw, AT(i, k), AT(i, c));
+      VO_CSWAP(sw, AT(k, k), AT(c, c));
+#pragma unroll
+      for (int i = k + 1; i < c; ++i) VO_CSWAP(sw, AT(i, k), AT(c, i));
+    }
     if (k > 0) {
+      float tmp[N];
+#pragma unroll
       for (int j = 0; j < k; ++j) tmp[j] = AT(j, j) * AT(k, j);
       float acc = 0.f;
-      for (int j = 0; j < k; ++j) acc += AT(k, j) * tmp[j];
-      AT(k, k) -= acc;
-      for (int i = 0; i < rs; ++i) {
+#pragma unroll
+      for (int j = 0; j < k; ++j) acc = acc + AT(k, j) * tmp[j];
+      AT(k, k) = AT(k, k) - acc;
+#pragma unroll
+      for (int i = k + 1; i < N; ++i) {
         float a2 = 0.f;
-        for (int j = 0; j < k; ++j) a2 += AT(k + 1 + i, j) * tmp[j];
-        AT(k + 1 + i, k) -= a2;
+#pragma unroll
+        for (int j = 0; j < k; ++j) a2 = a2 + AT(i, j) * tmp[j];
+        AT(i, k) = AT(i, k) - a2;
       }
     }
     const float akk = AT(k, k);
-    if (rs > 0 && fabsf(akk) > 0.f)
-      for (int i = 0; i < rs; ++i) AT(k + 1 + i, k) = AT(k + 1 + i, k) / akk;
+    const bool nz = fabsf(akk) > 0.f;
+#pragma unroll
+    for (int i = k + 1; i < N; ++i) AT(i, k) = nz ? AT(i, k) / akk : AT(i, k);
   }
   float y[N];
+#pragma unroll
   for (int i = 0; i < N; ++i) y[i] = rhs[i];
+#pragma unroll
   for (int k = 0; k < N; ++k)
-    if (tr[k] != k) {
-      const float t = y[k];
-      y[k] = y[tr[k]];
-      y[tr[k]] = t;
-    }
+#pragma unroll
+    for (int c = k + 1; c < N; ++c) VO_CSWAP(tr[k] == c, y[k], y[c]);
+#pragma unroll
   for (int i = 0; i < N; ++i)
-    for (int j = 0; j < i; ++j) y[i] -= AT(i, j) * y[j];
-  for (int i = 0; i < N; ++i) {
-    if (fabsf(AT(i, i)) > 1.17549435e-38f) y[i] = y[i] / AT(i, i);
-    else y[i] = 0.f;
-  }
+#pragma unroll
+    for (int j = 0; j < i; ++j) y[i] = y[i] - AT(i, j) * y[j];
+#pragma unroll
+  for (int i = 0; i < N; ++i) y[i] = (fabsf(AT(i, i)) > 1.17549435e-38f) ? y[i] / AT(i, i) : 0.f;
+#pragma unroll
   for (int i = N - 1; i >= 0; --i)
-    for (int j = i + 1; j < N; ++j) y[i] -= AT(j, i) * y[j];
+#pragma unroll
+    for (int j = i + 1; j < N; ++j) y[i] = y[i] - AT(j, i) * y[j];
+#pragma unroll
   for (int k = N - 1; k >= 0; --k)
-    if (tr[k] != k) {
-      const float t = y[k];
-      y[k] = y[tr[k]];
-      y[tr[k]] = t;
-    }
+#pragma unroll
+    for (int c = k + 1; c < N; ++c) VO_CSWAP(tr[k] == c, y[k], y[c]);
+#pragma unroll
   for (int i = 0; i < N; ++i) x[i] = y[i];
+#undef VO_CSWAP
 #undef AT
 }
 
-__device__ __forceinline__ void mat3_mul_dev(const float* A, const float* B, float* C) {
+VO_HD void mat3_mul_dev(const float* A, const float* B, float* C) {
   for (int j = 0; j < 3; ++j)
     for (int i = 0; i < 3; ++i)
       C[j * 3 + i] = (A[i] * B[j * 3] + A[3 + i] * B[j * 3 + 1]) + A[6 + i] * B[j * 3 + 2];

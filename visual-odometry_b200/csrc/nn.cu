@@ -259,20 +259,27 @@ nn_filter_kernel(const NNParams p) {
   if (tile_begin >= tile_end) return;  // uniform for the CTA
   const int64_t qbase = (int64_t)blockIdx.y * (THREADS * TQ);
 
+  // full[s]: TMA bytes of stage s have landed (1 producer arrival + tx count);
+  // empty[s]: every warp is done reading stage s (one arrival per warp).  No block-wide barrier
+  // in the main loop: warps drift up to NN_STAGES-1 tiles apart.
+  constexpr int WARPS = THREADS / 32;
+  uint64_t* empty = full + NN_STAGES;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < NN_STAGES; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < NN_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], WARPS);
+    }
     mbar_fence_init();
   }
   __syncthreads();
+  int64_t issued = tile_begin;  // next tile to request (meaningful in thread 0 only)
   if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < NN_STAGES; ++s)
-      if (tile_begin + s < tile_end) {
-        mbar_arrive_expect_tx(&full[s], NN_TILE_BYTES);
-        tma_load_1d(tiles + s * (NN_TM * 3), p.packed + (tile_begin + s) * (NN_TM * 3),
-                    NN_TILE_BYTES, &full[s]);
-      }
+    for (; issued < tile_end && issued < tile_begin + NN_STAGES; ++issued) {
+      const int s = (int)(issued - tile_begin);
+      mbar_arrive_expect_tx(&full[s], NN_TILE_BYTES);
+      tma_load_1d(tiles + s * (NN_TM * 3), p.packed + issued * (NN_TM * 3), NN_TILE_BYTES, &full[s]);
+    }
   }
 
   // queries of this thread, pre-scaled by -2 and packed two-by-two (query 2j in the low half,
@@ -358,11 +365,24 @@ nn_filter_kernel(const NNParams p) {
       mn[j] = INFINITY;
     }
 
-    __syncthreads();  // every warp is done with this stage -> refill it
-    if (tid == 0 && t + NN_STAGES < tile_end) {
-      mbar_arrive_expect_tx(&full[stage], NN_TILE_BYTES);
-      tma_load_1d(tiles + stage * (NN_TM * 3), p.packed + (t + NN_STAGES) * (NN_TM * 3),
-                  NN_TILE_BYTES, &full[stage]);
+    // this warp is done with the stage
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&empty[stage]);
+    // producer (thread 0): refill every stage that ALL warps have released; block only if the
+    // tile this warp needs next has not been requested yet
+    if (tid == 0) {
+      while (issued < tile_end) {
+        const int64_t k = issued - tile_begin;           // k >= NN_STAGES here
+        const int s = (int)(k % NN_STAGES);
+        const uint32_t par = (uint32_t)((k / NN_STAGES - 1) & 1);  // phase of the tile being replaced
+        if (!mbar_try_wait(&empty[s], par)) {
+          if (issued > t + 1) break;                     // tile t+1 is already on its way
+          mbar_wait(&empty[s], par);
+        }
+        mbar_arrive_expect_tx(&full[s], NN_TILE_BYTES);
+        tma_load_1d(tiles + s * (NN_TM * 3), p.packed + issued * (NN_TM * 3), NN_TILE_BYTES, &full[s]);
+        ++issued;
+      }
     }
     if (++stage == NN_STAGES) {
       stage = 0;
@@ -482,7 +502,7 @@ static int nn_launch_filter(vo_nn_s* h, const float* queries_dev, int64_t nq, in
   p.keys = h->keys.as<unsigned long long>();
 
   const int sms = num_sms(h->device);
-  const size_t smem = NN_STAGES * NN_TILE_BYTES + NN_STAGES * sizeof(uint64_t);
+  const size_t smem = NN_STAGES * NN_TILE_BYTES + 2 * NN_STAGES * sizeof(uint64_t);
   auto splits_for = [&](int64_t qtiles, int64_t resident) {
     // Every wave should be full: with one query tile per blockIdx.y and `resident` CTAs alive at
     // once, `resident` map splits make each query tile exactly one wave.  Small maps get fewer,
@@ -506,7 +526,9 @@ static int nn_launch_filter(vo_nn_s* h, const float* queries_dev, int64_t nq, in
     VO_LAUNCH_CHECK();
     return VO_OK;
   };
-  if (nq > 8192) return launch(nn_filter_kernel<8, 256>, 8, 256);
+  // 8 queries/thread x 384 threads: 160 registers x 384 fills the 64K-register file of an SM with
+  // 12 warps (3 per scheduler), the most that fit at this register tile
+  if (nq > 8192) return launch(nn_filter_kernel<8, 384>, 8, 384);
   if (nq > 1024) return launch(nn_filter_kernel<2, 256>, 2, 256);
   return launch(nn_filter_kernel<2, 64>, 2, 64);
 }

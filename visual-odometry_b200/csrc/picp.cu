@@ -19,6 +19,7 @@
 // The pose lives in device memory and is re-read by the next launch, so `rounds` launches are
 // simply queued (or replayed from a CUDA graph): no host round-trip between rounds.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -60,7 +61,9 @@ __device__ void picp_solve_and_update(const PicpParams& p, const float* tot) {
   float H[36];
   {
     int k = 0;
+#pragma unroll
     for (int r = 0; r < 6; ++r)
+#pragma unroll
       for (int c = r; c < 6; ++c) {
         H[c * 6 + r] = tot[k];
         H[r * 6 + c] = tot[k];
@@ -68,9 +71,13 @@ __device__ void picp_solve_and_update(const PicpParams& p, const float* tot) {
       }
   }
   float b[6];
+#pragma unroll
   for (int i = 0; i < 6; ++i) b[i] = tot[21 + i];
+#pragma unroll
   for (int i = 0; i < 6; ++i) H[i * 6 + i] += p.damping;  // :102
+#pragma unroll
   for (int i = 0; i < 36; ++i) s.H[i] = H[i];
+#pragma unroll
   for (int i = 0; i < 6; ++i) s.b[i] = b[i];
   s.chi_inliers = tot[27];
   s.chi_outliers = tot[28];
@@ -82,6 +89,7 @@ __device__ void picp_solve_and_update(const PicpParams& p, const float* tot) {
     return;
   }
   float nb[6], dx[6];
+#pragma unroll
   for (int i = 0; i < 6; ++i) nb[i] = -b[i];
   ldlt_solve_dev<6>(H, nb, dx);  // :109
   // v2tEuler(dx): R = Rx(dx3)*Ry(dx4)*Rz(dx5), t = dx0..2   (utils.h:64-78)
@@ -96,7 +104,9 @@ __device__ void picp_solve_and_update(const PicpParams& p, const float* tot) {
   mat3_mul_dev(Rxy, Rz, R);
   // pose <- D * pose   (:110)
   float Tn[16];
+#pragma unroll
   for (int j = 0; j < 4; ++j)
+#pragma unroll
     for (int i = 0; i < 3; ++i) {
       float acc = (R[i] * s.T[j * 4] + R[3 + i] * s.T[j * 4 + 1]) + R[6 + i] * s.T[j * 4 + 2];
       if (j == 3) acc += dx[i];
@@ -104,13 +114,20 @@ __device__ void picp_solve_and_update(const PicpParams& p, const float* tot) {
     }
   Tn[3] = Tn[7] = Tn[11] = 0.f;
   Tn[15] = 1.f;
+#pragma unroll
   for (int i = 0; i < 16; ++i) s.T[i] = Tn[i];
   s.last_ok = 1;
 }
 
 // One correspondence: errorAndJacobian (:25-53) + the body of linearize's loop (:62-95).
-// Branch-free: a rejected point (or a padding slot past the end, live == false) runs the same
-// instructions with weight 0, so a warp never diverges on the data.
+// Branch-free: a rejected point runs the same instructions with weight 0, so a warp never
+// diverges on the data.
+//
+// PINHOLE == true is selected by the host when K is exactly [fx 0 cx; 0 fy cy; 0 0 1] (the only
+// form the reference's mains ever build: picp_solver_test.cpp:52-54, camera.dat).  Every product
+// with a structural zero of K, and every term of J^T J that contains one, is dropped at compile
+// time; the surviving operations are the same FMAs in the same order, so the result is
+// bit-identical to the general-K path (tests/test_picp_gpu.py checks this).
 struct PicpAcc {
   float h[21];
   float b[6];
@@ -126,40 +143,62 @@ __device__ __forceinline__ float picp_rcp(float x) {
   return fmaf(r, e, r);
 }
 
-__device__ __forceinline__ void picp_point(const PicpParams& p, const float (&T)[12], bool live,
-                                           float wx, float wy, float wz, float mu, float mv,
-                                           PicpAcc& a) {
+template <bool PINHOLE>
+__device__ __forceinline__ void picp_point(const PicpParams& p, const float (&T)[12], float wx,
+                                           float wy, float wz, float mu, float mv, PicpAcc& a) {
   // camera_point = world_in_camera * world_point  (camera.h:27, picp_solver.cpp:38)
   float px = fmaf(T[6], wz, fmaf(T[3], wy, fmaf(T[0], wx, T[9])));
   float py = fmaf(T[7], wz, fmaf(T[4], wy, fmaf(T[1], wx, T[10])));
   float pz = fmaf(T[8], wz, fmaf(T[5], wy, fmaf(T[2], wx, T[11])));
-  bool valid = live && !(pz > p.z_far || pz < p.z_near);  // camera.h:28
+  bool valid = !(pz > p.z_far || pz < p.z_near);  // camera.h:28
   // a rejected point continues as the harmless dummy (0,0,1) so that nothing overflows
   px = valid ? px : 0.f;
   py = valid ? py : 0.f;
   pz = valid ? pz : 1.f;
   // phom = K * camera_point  (camera.h:30, picp_solver.cpp:43)
-  const float hx = fmaf(p.K[6], pz, fmaf(p.K[3], py, p.K[0] * px));
-  const float hy = fmaf(p.K[7], pz, fmaf(p.K[4], py, p.K[1] * px));
-  const float hz = fmaf(p.K[8], pz, fmaf(p.K[5], py, p.K[2] * px));
+  float hx, hy, hz;
+  if (PINHOLE) {
+    hx = fmaf(p.K[6], pz, p.K[0] * px);
+    hy = fmaf(p.K[7], pz, p.K[4] * py);
+    hz = pz;
+  } else {
+    hx = fmaf(p.K[6], pz, fmaf(p.K[3], py, p.K[0] * px));
+    hy = fmaf(p.K[7], pz, fmaf(p.K[4], py, p.K[1] * px));
+    hz = fmaf(p.K[8], pz, fmaf(p.K[5], py, p.K[2] * px));
+  }
   const float iz = picp_rcp(hz);  // camera.h:31 / picp_solver.cpp:44
   const float u = hx * iz, v = hy * iz;
   valid = valid && !(u < 0.f || u > p.max_u) && !(v < 0.f || v > p.max_v);  // camera.h:32-35
   const float e0 = u - mu, e1 = v - mv;                                      // :35
   // A = Jp*K with Jp = [iz 0 -hx*iz^2; 0 iz -hy*iz^2]  ==  iz * (K_row{0,1} - {u,v} * K_row2)
-  float J0[6], J1[6];
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    J0[j] = iz * fmaf(-u, p.K[j * 3 + 2], p.K[j * 3 + 0]);
-    J1[j] = iz * fmaf(-v, p.K[j * 3 + 2], p.K[j * 3 + 1]);
-  }
   // J = [A | A*skew(-pc)],  skew(-pc) = [0 pz -py; -pz 0 px; py -px 0]   (:39-41, utils.h:96-102)
-  J0[3] = fmaf(J0[2], py, -J0[1] * pz);
-  J0[4] = fmaf(J0[0], pz, -J0[2] * px);
-  J0[5] = fmaf(J0[1], px, -J0[0] * py);
-  J1[3] = fmaf(J1[2], py, -J1[1] * pz);
-  J1[4] = fmaf(J1[0], pz, -J1[2] * px);
-  J1[5] = fmaf(J1[1], px, -J1[0] * py);
+  float J0[6], J1[6];
+  if (PINHOLE) {
+    J0[0] = iz * p.K[0];
+    J0[1] = 0.f;
+    J0[2] = iz * (p.K[6] - u);
+    J1[0] = 0.f;
+    J1[1] = iz * p.K[4];
+    J1[2] = iz * (p.K[7] - v);
+    J0[3] = J0[2] * py;
+    J0[4] = fmaf(J0[0], pz, -J0[2] * px);
+    J0[5] = -(J0[0] * py);
+    J1[3] = fmaf(J1[2], py, -J1[1] * pz);
+    J1[4] = -(J1[2] * px);
+    J1[5] = J1[1] * px;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      J0[j] = iz * fmaf(-u, p.K[j * 3 + 2], p.K[j * 3 + 0]);
+      J1[j] = iz * fmaf(-v, p.K[j * 3 + 2], p.K[j * 3 + 1]);
+    }
+    J0[3] = fmaf(J0[2], py, -J0[1] * pz);
+    J0[4] = fmaf(J0[0], pz, -J0[2] * px);
+    J0[5] = fmaf(J0[1], px, -J0[0] * py);
+    J1[3] = fmaf(J1[2], py, -J1[1] * pz);
+    J1[4] = fmaf(J1[0], pz, -J1[2] * px);
+    J1[5] = fmaf(J1[1], px, -J1[0] * py);
+  }
   const float chi = fmaf(e1, e1, e0 * e0);  // :75
   const bool outlier = chi > p.thr;         // :78
   float lambda = outlier ? 0.f : 1.f;       // dropped outliers weigh 0 (:90)
@@ -180,10 +219,18 @@ __device__ __forceinline__ void picp_point(const PicpParams& p, const float (&T)
   for (int r = 0; r < 6; ++r) {
 #pragma unroll
     for (int c = r; c < 6; ++c) {
-      a.h[k] = fmaf(L0[r], J0[c], fmaf(L1[r], J1[c], a.h[k]));
+      const bool z0 = PINHOLE && (r == 1 || c == 1);  // J0[1] == 0
+      const bool z1 = PINHOLE && (r == 0 || c == 0);  // J1[0] == 0
+      float hk = a.h[k];
+      if (!z1) hk = fmaf(L1[r], J1[c], hk);
+      if (!z0) hk = fmaf(L0[r], J0[c], hk);
+      a.h[k] = hk;
       ++k;
     }
-    a.b[r] = fmaf(L0[r], e0, fmaf(L1[r], e1, a.b[r]));
+    float bk = a.b[r];
+    if (!(PINHOLE && r == 0)) bk = fmaf(L1[r], e1, bk);
+    if (!(PINHOLE && r == 1)) bk = fmaf(L0[r], e0, bk);
+    a.b[r] = bk;
   }
 }
 
@@ -192,16 +239,10 @@ struct PicpBatch {
   float2 m[PICP_UNROLL];
 };
 
-// pairs of one batch; slots past the end re-read the last pair (always in bounds) and are
-// masked out with live == false when they are consumed
-__device__ __forceinline__ void picp_load_pairs(const PicpParams& p, int64_t base, int64_t stride,
+__device__ __forceinline__ void picp_load_pairs(const int2* __restrict__ pp, int stride,
                                                 int2 (&pr)[PICP_UNROLL]) {
 #pragma unroll
-  for (int u = 0; u < PICP_UNROLL; ++u) {
-    int64_t i = base + u * stride;
-    i = i < p.n_pairs ? i : p.n_pairs - 1;
-    pr[u] = __ldg(p.pairs + i);
-  }
+  for (int u = 0; u < PICP_UNROLL; ++u) pr[u] = __ldg(pp + (int64_t)u * stride);
 }
 __device__ __forceinline__ void picp_gather(const PicpParams& p, const int2 (&pr)[PICP_UNROLL],
                                             PicpBatch& b) {
@@ -215,6 +256,7 @@ __device__ __forceinline__ void picp_gather(const PicpParams& p, const int2 (&pr
   }
 }
 
+template <bool PINHOLE>
 __global__ void __launch_bounds__(PICP_THREADS, 2) picp_round_kernel(const PicpParams p) {
   __shared__ float s_red[PICP_THREADS / 32][PICP_NACC];
   __shared__ bool s_last;
@@ -236,25 +278,38 @@ __global__ void __launch_bounds__(PICP_THREADS, 2) picp_round_kernel(const PicpP
   a.n_in = 0;
 
   // ---- software-pipelined stream over the correspondences --------------------------------------
-  // while batch k is being linearised, the point gathers of batch k+1 and the pair loads of batch
-  // k+2 are in flight, so every warp always has independent loads outstanding
-  const int64_t stride = (int64_t)gridDim.x * PICP_THREADS;
-  const int64_t step = stride * PICP_UNROLL;
-  int64_t base = (int64_t)blockIdx.x * PICP_THREADS + tid;
-  if (p.n_pairs > 0 && base < p.n_pairs) {
+  // thread t owns items t, t+stride, t+2*stride, ...; they are consumed in batches of PICP_UNROLL.
+  // While batch k is being linearised, the point gathers of batch k+1 and the pair loads of batch
+  // k+2 are in flight, so every warp always has independent loads outstanding.
+  const int n = (int)p.n_pairs;
+  const int stride = (int)gridDim.x * PICP_THREADS;
+  const int i0 = (int)blockIdx.x * PICP_THREADS + tid;
+  const int mine = i0 < n ? (n - i0 + stride - 1) / stride : 0;  // items of this thread
+  const int nb = mine / PICP_UNROLL;                             // full batches
+  const int2* pp = p.pairs + i0;
+  const int64_t bstep = (int64_t)stride * PICP_UNROLL;
+  {
     int2 pr_next[PICP_UNROLL];
     PicpBatch cur, nxt;
-    picp_load_pairs(p, base, stride, pr_next);
-    picp_gather(p, pr_next, cur);
-    picp_load_pairs(p, base + step, stride, pr_next);
-    for (; base < p.n_pairs; base += step) {
-      picp_gather(p, pr_next, nxt);                         // batch k+1 points
-      picp_load_pairs(p, base + 2 * step, stride, pr_next);  // batch k+2 pairs
+    if (nb > 0) {
+      picp_load_pairs(pp, stride, pr_next);
+      picp_gather(p, pr_next, cur);
+    }
+    if (nb > 1) picp_load_pairs(pp + bstep, stride, pr_next);
+    for (int bi = 0; bi < nb; ++bi) {
+      if (bi + 1 < nb) picp_gather(p, pr_next, nxt);                               // batch k+1 points
+      if (bi + 2 < nb) picp_load_pairs(pp + (int64_t)(bi + 2) * bstep, stride, pr_next);  // k+2 pairs
 #pragma unroll
       for (int u = 0; u < PICP_UNROLL; ++u)
-        picp_point(p, T, base + u * stride < p.n_pairs, cur.w[u][0], cur.w[u][1], cur.w[u][2],
-                   cur.m[u].x, cur.m[u].y, a);
+        picp_point<PINHOLE>(p, T, cur.w[u][0], cur.w[u][1], cur.w[u][2], cur.m[u].x, cur.m[u].y, a);
       cur = nxt;
+    }
+    // the (< PICP_UNROLL) leftover items of this thread
+    for (int m = nb * PICP_UNROLL; m < mine; ++m) {
+      const int2 pr = __ldg(pp + (int64_t)m * stride);
+      const float* wp = p.world + 3 * (int64_t)pr.y;
+      const float2 im = __ldg(reinterpret_cast<const float2*>(p.image) + pr.x);
+      picp_point<PINHOLE>(p, T, __ldg(wp), __ldg(wp + 1), __ldg(wp + 2), im.x, im.y, a);
     }
   }
 
@@ -305,19 +360,19 @@ __global__ void __launch_bounds__(PICP_THREADS, 2) picp_round_kernel(const PicpP
   if (!s_last) return;
   __threadfence();
   {
-    // warp w sums blocks w, w+W, ... for component `lane` (8 independent loads in flight per
+    // warp w sums blocks w, w+W, ... for component `lane` (16 independent loads in flight per
     // step, combined in a fixed order); then warp 0 sums the W rows
     constexpr int W = PICP_THREADS / 32;
-    constexpr int B = 8;
+    constexpr int B = 16;
     float s = 0.f;
     int si = 0;
-    const int nb = (int)gridDim.x;
-    for (int bk0 = warp; bk0 < nb; bk0 += W * B) {
+    const int nblk = (int)gridDim.x;
+    for (int bk0 = warp; bk0 < nblk; bk0 += W * B) {
       float x[B];
 #pragma unroll
       for (int q = 0; q < B; ++q) {
         const int bk = bk0 + q * W;
-        x[q] = (bk < nb && lane < 30) ? __ldcg(p.partials + (int64_t)bk * PICP_NACC + lane) : 0.f;
+        x[q] = (bk < nblk && lane < 30) ? __ldcg(p.partials + (int64_t)bk * PICP_NACC + lane) : 0.f;
       }
 #pragma unroll
       for (int q = 0; q < B; ++q) {
@@ -361,6 +416,7 @@ struct vo_picp_s {
   vo_camera cam{};
   bool have_cam = false;
   float thr = 1000.f, damping = 1.f;  // picp_solver.cpp:10-13
+  bool force_general = false;         // VO_PICP_FORCE_GENERAL=1: never use the pinhole kernel
   int32_t min_inliers = 0;
   DevBuf world_buf, image_buf, pairs_buf, state_buf, partials_buf;
   const float* world = nullptr;
@@ -423,7 +479,7 @@ static int picp_fill_params(vo_picp_s* h, int keep_outliers, PicpParams* p) {
 static int picp_pick_grid(vo_picp_s* h) {
   const int sms = num_sms(h->device);
   int per_sm = 2;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, picp_round_kernel, PICP_THREADS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, picp_round_kernel<false>, PICP_THREADS, 0);
   if (per_sm < 1) per_sm = 1;
   const int64_t full = (int64_t)sms * per_sm;
   const int64_t need =
@@ -450,6 +506,8 @@ int vo_picp_create(vo_picp_t* out, int device) {
     return VO_ERR_CUDA;
   }
   h->own_stream = true;
+  const char* fg = getenv("VO_PICP_FORCE_GENERAL");
+  h->force_general = fg != nullptr && fg[0] == '1';
   *out = h;
   return VO_OK;
 }
@@ -547,7 +605,8 @@ int vo_picp_init_device(vo_picp_t h, const vo_camera* cam, const float* world_de
 
 int vo_picp_set_correspondences(vo_picp_t h, const int32_t* pairs_host, int64_t n_pairs) {
   VO_REQUIRE(h != nullptr, VO_ERR_ARG, "null handle");
-  VO_REQUIRE(n_pairs >= 0 && (pairs_host || n_pairs == 0), VO_ERR_ARG, "bad pairs");
+  VO_REQUIRE(n_pairs >= 0 && n_pairs < (1LL << 31) && (pairs_host || n_pairs == 0), VO_ERR_ARG,
+             "bad pairs");
   DeviceGuard g(h->device);
   // bounds check on the host: the reference indexes with operator[] (UB when out of range);
   // we refuse instead of reading out of bounds on the device.
@@ -571,7 +630,8 @@ int vo_picp_set_correspondences(vo_picp_t h, const int32_t* pairs_host, int64_t 
 
 int vo_picp_set_correspondences_device(vo_picp_t h, const int32_t* pairs_dev, int64_t n_pairs) {
   VO_REQUIRE(h != nullptr, VO_ERR_ARG, "null handle");
-  VO_REQUIRE(n_pairs >= 0 && (pairs_dev || n_pairs == 0), VO_ERR_ARG, "bad pairs");
+  VO_REQUIRE(n_pairs >= 0 && n_pairs < (1LL << 31) && (pairs_dev || n_pairs == 0), VO_ERR_ARG,
+             "bad pairs");
   VO_REQUIRE((reinterpret_cast<uintptr_t>(pairs_dev) & 7u) == 0, VO_ERR_ARG,
              "pairs must be 8-byte aligned");
   h->pairs = pairs_dev;
@@ -591,9 +651,14 @@ int vo_picp_compute(vo_picp_t h, int keep_outliers, int rounds) {
   PicpParams p;
   picp_fill_params(h, keep_outliers, &p);
 
+  // K == [fx 0 cx; 0 fy cy; 0 0 1] exactly -> the structurally-sparse instantiation
+  const float* K = h->cam.K;
+  const bool pinhole = !h->force_general && K[1] == 0.f && K[2] == 0.f && K[3] == 0.f &&
+                       K[5] == 0.f && K[8] == 1.f;
+  auto kernel = pinhole ? picp_round_kernel<true> : picp_round_kernel<false>;
   if (rounds < 4) {
     for (int r = 0; r < rounds; ++r) {
-      picp_round_kernel<<<grid, PICP_THREADS, 0, h->stream>>>(p);
+      kernel<<<grid, PICP_THREADS, 0, h->stream>>>(p);
       VO_LAUNCH_CHECK();
     }
     return VO_OK;
@@ -601,7 +666,8 @@ int vo_picp_compute(vo_picp_t h, int keep_outliers, int rounds) {
   // many rounds: replay a captured graph of `rounds` launches (one submit, no per-launch
   // driver work between rounds)
   vo_picp_s::GraphKey key{h->world, h->image, h->pairs, h->partials_buf.p, h->n_pairs,
-                          p.keep_outliers, rounds, grid, h->thr, h->damping, h->min_inliers};
+                          p.keep_outliers, rounds, pinhole ? -grid : grid, h->thr, h->damping,
+                          h->min_inliers};
   auto it = h->graphs.find(key);
   if (it == h->graphs.end()) {
     if (h->graphs.size() > 16) picp_drop_graphs(h);
@@ -611,8 +677,7 @@ int vo_picp_compute(vo_picp_t h, int keep_outliers, int rounds) {
     if (!h->capture_stream)
       VO_CUDA(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
     VO_CUDA(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
-    for (int r = 0; r < rounds; ++r)
-      picp_round_kernel<<<grid, PICP_THREADS, 0, h->capture_stream>>>(p);
+    for (int r = 0; r < rounds; ++r) kernel<<<grid, PICP_THREADS, 0, h->capture_stream>>>(p);
     cudaError_t e = cudaStreamEndCapture(h->capture_stream, &graph);
     if (e != cudaSuccess) {
       set_error("cudaStreamEndCapture -> %s", cudaGetErrorString(e));

@@ -47,12 +47,13 @@ __device__ __forceinline__ bool triangulate_point_dev(const float (&d1)[3], cons
                                                       const float (&t)[3], float (&p)[3]) {
   const float n0 = -d1[0], n1 = -d1[1], n2 = -d1[2];  // D.col(0) = -d1
   float A[4], rhs[2], ss[2];
-  A[0] = (n0 * n0 + n1 * n1) + n2 * n2;  // D^T D
-  A[1] = (d2[0] * n0 + d2[1] * n1) + d2[2] * n2;
+  // fixed-size Eigen products sum three terms as s0 + (s1 + s2) (see oracle/vo_oracle.c)
+  A[0] = n0 * n0 + (n1 * n1 + n2 * n2);  // D^T D
+  A[1] = d2[0] * n0 + (d2[1] * n1 + d2[2] * n2);
   A[2] = A[1];
-  A[3] = (d2[0] * d2[0] + d2[1] * d2[1]) + d2[2] * d2[2];
-  rhs[0] = (n0 * t[0] + n1 * t[1]) + n2 * t[2];  // D^T p2
-  rhs[1] = (d2[0] * t[0] + d2[1] * t[1]) + d2[2] * t[2];
+  A[3] = d2[0] * d2[0] + (d2[1] * d2[1] + d2[2] * d2[2]);
+  rhs[0] = n0 * t[0] + (n1 * t[1] + n2 * t[2]);  // D^T p2
+  rhs[1] = d2[0] * t[0] + (d2[1] * t[1] + d2[2] * t[2]);
   ldlt_solve_dev<2>(A, rhs, ss);  // :40
   const float s0 = -ss[0], s1 = -ss[1];
   if (s0 < 0.f || s1 < 0.f) return false;  // :41
@@ -94,8 +95,8 @@ __global__ void __launch_bounds__(TRI_THREADS) triangulate_kernel(const TriParam
       float d1[3], d2[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        d1[i] = (q.iK[i] * a[j].x + q.iK[3 + i] * a[j].y) + q.iK[6 + i];        // iK*[p1;1]   :91
-        d2[i] = (q.iRiK[i] * b[j].x + q.iRiK[3 + i] * b[j].y) + q.iRiK[6 + i];  // iRiK*[p2;1] :94
+        d1[i] = q.iK[i] * a[j].x + (q.iK[3 + i] * a[j].y + q.iK[6 + i]);        // iK*[p1;1]   :91
+        d2[i] = q.iRiK[i] * b[j].x + (q.iRiK[3 + i] * b[j].y + q.iRiK[6 + i]);  // iRiK*[p2;1] :94
       }
       ok[j] = triangulate_point_dev(d1, d2, t, P[j]);
     }
@@ -140,13 +141,13 @@ struct ProjParams {
 // Camera::projectPoint, camera.h:25-37
 __device__ __forceinline__ bool project_point_dev(const ProjParams& q, float wx, float wy, float wz,
                                                   float2* uv) {
-  const float px = ((q.T[0] * wx + q.T[3] * wy) + q.T[6] * wz) + q.T[9];
-  const float py = ((q.T[1] * wx + q.T[4] * wy) + q.T[7] * wz) + q.T[10];
-  const float pz = ((q.T[2] * wx + q.T[5] * wy) + q.T[8] * wz) + q.T[11];
+  const float px = q.T[9] + (q.T[0] * wx + (q.T[3] * wy + q.T[6] * wz));
+  const float py = q.T[10] + (q.T[1] * wx + (q.T[4] * wy + q.T[7] * wz));
+  const float pz = q.T[11] + (q.T[2] * wx + (q.T[5] * wy + q.T[8] * wz));
   if (pz > q.z_far || pz < q.z_near) return false;
-  const float hx = (q.K[0] * px + q.K[3] * py) + q.K[6] * pz;
-  const float hy = (q.K[1] * px + q.K[4] * py) + q.K[7] * pz;
-  const float hz = (q.K[2] * px + q.K[5] * py) + q.K[8] * pz;
+  const float hx = q.K[0] * px + (q.K[3] * py + q.K[6] * pz);
+  const float hy = q.K[1] * px + (q.K[4] * py + q.K[7] * pz);
+  const float hz = q.K[2] * px + (q.K[5] * py + q.K[8] * pz);
   const float iz = (float)(1.0 / (double)hz);  // camera.h:31: 1./z is a double, then demoted
   uv->x = hx * iz;
   uv->y = hy * iz;
@@ -193,31 +194,26 @@ __global__ void __launch_bounds__(TRI_THREADS) project_points_kernel(const ProjP
 
 // ---- host-side precomputation (one rounding per operation, like the reference build) ----------
 static void h_mat3_vec(const float* M, const float v[3], float out[3]) {
-  for (int i = 0; i < 3; ++i) out[i] = (M[i] * v[0] + M[3 + i] * v[1]) + M[6 + i] * v[2];
+  for (int i = 0; i < 3; ++i) out[i] = M[i] * v[0] + (M[3 + i] * v[1] + M[6 + i] * v[2]);
 }
 static void h_mat3_mul(const float* A, const float* B, float* C) {
   for (int j = 0; j < 3; ++j)
     for (int i = 0; i < 3; ++i)
-      C[j * 3 + i] = (A[i] * B[j * 3] + A[3 + i] * B[j * 3 + 1]) + A[6 + i] * B[j * 3 + 2];
+      C[j * 3 + i] = A[i] * B[j * 3] + (A[3 + i] * B[j * 3 + 1] + A[6 + i] * B[j * 3 + 2]);
 }
-// cofactor inverse, the fixed-size path behind Matrix3f::inverse()
+// cofactor inverse, the fixed-size path behind Matrix3f::inverse(): cyclic cofactors, determinant
+// expanded along column 0, result(i,j) = cofactor(j,i) / det
+static float h_cof3(const float* M, int i, int j) {
+  const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+  return M[j1 * 3 + i1] * M[j2 * 3 + i2] - M[j2 * 3 + i1] * M[j1 * 3 + i2];
+}
 static void h_mat3_inverse(const float* M, float* out) {
-#define m(i, j) M[(j) * 3 + (i)]
-  const float c00 = m(1, 1) * m(2, 2) - m(1, 2) * m(2, 1);
-  const float c10 = m(1, 2) * m(2, 0) - m(1, 0) * m(2, 2);
-  const float c20 = m(1, 0) * m(2, 1) - m(1, 1) * m(2, 0);
-  const float det = (m(0, 0) * c00 + m(0, 1) * c10) + m(0, 2) * c20;
+  const float c0 = h_cof3(M, 0, 0), c1 = h_cof3(M, 1, 0), c2 = h_cof3(M, 2, 0);
+  const float det = c0 * M[0] + (c1 * M[1] + c2 * M[2]);
   const float id = 1.f / det;
-  out[0] = c00 * id;
-  out[1] = c10 * id;
-  out[2] = c20 * id;
-  out[3] = (m(0, 2) * m(2, 1) - m(0, 1) * m(2, 2)) * id;
-  out[4] = (m(0, 0) * m(2, 2) - m(0, 2) * m(2, 0)) * id;
-  out[5] = (m(0, 1) * m(2, 0) - m(0, 0) * m(2, 1)) * id;
-  out[6] = (m(0, 1) * m(1, 2) - m(0, 2) * m(1, 1)) * id;
-  out[7] = (m(0, 2) * m(1, 0) - m(0, 0) * m(1, 2)) * id;
-  out[8] = (m(0, 0) * m(1, 1) - m(0, 1) * m(1, 0)) * id;
-#undef m
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      out[j * 3 + i] = (i == 0 ? (j == 0 ? c0 : (j == 1 ? c1 : c2)) : h_cof3(M, j, i)) * id;
 }
 
 static void tri_precompute(const float K[9], const float X[16], TriParams* q) {
