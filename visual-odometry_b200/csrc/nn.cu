@@ -192,14 +192,19 @@ __device__ __forceinline__ float nn_filter_threshold(const float (&qn)[NN_DIM], 
 }
 
 // Slow path (rare): re-scan one tile for one query, exact arithmetic for the candidates.
-// Returns the tightened exact bound.
+// The running exact bound is NOT kept in registers: it is the d2 stored in the query's global key
+// (possibly improved by another map split in the meantime).  A candidate is merged when
+// d2 < norm^2 (strict, brute_force_search.h:35) and d2 <= best-so-far; among equal d2 the packed
+// atomicMin keeps the lowest row (the reference's first-match-wins order).  Returns the new bound.
 __device__ __noinline__ float nn_rescan_tile(const float4* __restrict__ tile, int64_t row0,
                                              int64_t n_rows, float qn0, float qn1, float qn2,
                                              float qn3, float qn4, float qn5, float qn6, float qn7,
-                                             float qn8, float qn9, float tq, float bound,
+                                             float qn8, float qn9, float tq, float radius2,
                                              unsigned long long* key) {
   const float q[NN_DIM] = {-0.5f * qn0, -0.5f * qn1, -0.5f * qn2, -0.5f * qn3, -0.5f * qn4,
                            -0.5f * qn5, -0.5f * qn6, -0.5f * qn7, -0.5f * qn8, -0.5f * qn9};
+  const unsigned long long k0 = *reinterpret_cast<volatile unsigned long long*>(key);
+  float best = (k0 == NN_KEY_NONE) ? radius2 : __uint_as_float(static_cast<unsigned int>(k0 >> 32));
   for (int r = 0; r < NN_TM; ++r) {
     const float4 a = tile[r * 3 + 0], b = tile[r * 3 + 1], c = tile[r * 3 + 2];
     float acc = c.z;
@@ -217,13 +222,13 @@ __device__ __noinline__ float nn_rescan_tile(const float4* __restrict__ tile, in
       const int64_t row = row0 + r;
       const float m[NN_DIM] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y};
       const float d2 = ref_sqdist<NN_DIM>(m, q);
-      if (row < n_rows && d2 < bound) {  // strict '<' : brute_force_search.h:35
-        bound = d2;
+      if (row < n_rows && d2 < radius2 && d2 <= best) {
+        best = d2;
         atomicMin(key, nn_pack_key(d2, static_cast<uint32_t>(row)));
       }
     }
   }
-  return bound;
+  return best;
 }
 
 // packed FP32 pairs: sm_100a executes fma.rn.f32x2 as ONE FFMA2 issue slot for two FMAs, and
@@ -244,14 +249,49 @@ __device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsig
   return d;
 }
 
+__device__ __forceinline__ float f_min3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));  // SASS FMNMX3
+  return r;
+}
+
+// one map row against the TP query pairs of this thread: 10 FFMA2 per pair of queries
+template <int TP>
+__device__ __forceinline__ void nn_row(const float4* __restrict__ row,
+                                       const unsigned long long (&q2)[TP][NN_DIM],
+                                       unsigned long long (&acc)[TP]) {
+  const float4 a = row[0];
+  const float4 b = row[1];
+  const float4 c = row[2];
+  const unsigned long long mm2 = f2_pack(c.z, c.z);
+#pragma unroll
+  for (int jp = 0; jp < TP; ++jp) {
+    unsigned long long x = f2_fma(q2[jp][0], f2_pack(a.x, a.x), mm2);
+    x = f2_fma(q2[jp][1], f2_pack(a.y, a.y), x);
+    x = f2_fma(q2[jp][2], f2_pack(a.z, a.z), x);
+    x = f2_fma(q2[jp][3], f2_pack(a.w, a.w), x);
+    x = f2_fma(q2[jp][4], f2_pack(b.x, b.x), x);
+    x = f2_fma(q2[jp][5], f2_pack(b.y, b.y), x);
+    x = f2_fma(q2[jp][6], f2_pack(b.z, b.z), x);
+    x = f2_fma(q2[jp][7], f2_pack(b.w, b.w), x);
+    x = f2_fma(q2[jp][8], f2_pack(c.x, c.x), x);
+    acc[jp] = f2_fma(q2[jp][9], f2_pack(c.y, c.y), x);
+  }
+}
+
 template <int TQ, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 nn_filter_kernel(const NNParams p) {
   static_assert(TQ % 2 == 0, "queries are processed in FFMA2 pairs");
+  static_assert(NN_TM % 2 == 0, "rows are folded into the running minimum two at a time");
   constexpr int TP = TQ / 2;
+  constexpr int WARPS = THREADS / 32;
   extern __shared__ __align__(128) unsigned char nn_smem[];
   float4* tiles = reinterpret_cast<float4*>(nn_smem);
   uint64_t* full = reinterpret_cast<uint64_t*>(nn_smem + NN_STAGES * NN_TILE_BYTES);
+  uint64_t* empty = full + NN_STAGES;
+  // per-thread filter thresholds live in shared memory: they are read once per tile, not per row
+  float* tq_s = reinterpret_cast<float*>(empty + NN_STAGES);  // [TQ][THREADS]
 
   const int tid = threadIdx.x;
   const int64_t tile_begin = (int64_t)blockIdx.x * p.tiles_per_split;
@@ -262,8 +302,6 @@ nn_filter_kernel(const NNParams p) {
   // full[s]: TMA bytes of stage s have landed (1 producer arrival + tx count);
   // empty[s]: every warp is done reading stage s (one arrival per warp).  No block-wide barrier
   // in the main loop: warps drift up to NN_STAGES-1 tiles apart.
-  constexpr int WARPS = THREADS / 32;
-  uint64_t* empty = full + NN_STAGES;
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < NN_STAGES; ++s) {
@@ -283,10 +321,10 @@ nn_filter_kernel(const NNParams p) {
   }
 
   // queries of this thread, pre-scaled by -2 and packed two-by-two (query 2j in the low half,
-  // 2j+1 in the high half), plus per-query filter thresholds, exact bounds and running minima
+  // 2j+1 in the high half), and the per-query running minima of  d^2 - |q|^2
   const float mm_max = __ldg(p.mm_max);
   unsigned long long q2[TP][NN_DIM];
-  float tq[TQ], bound[TQ], mn[TQ];
+  float mn[TQ];
 #pragma unroll
   for (int jp = 0; jp < TP; ++jp) {
     float qn[2][NN_DIM];
@@ -294,17 +332,18 @@ nn_filter_kernel(const NNParams p) {
     for (int h = 0; h < 2; ++h) {
       const int j = 2 * jp + h;
       const int64_t qi = qbase + (int64_t)j * THREADS + tid;
+      float t;
       if (qi < p.n_queries) {
         const float* src = p.queries + qi * (int64_t)p.query_stride + p.skip;
 #pragma unroll
         for (int k = 0; k < NN_DIM; ++k) qn[h][k] = -2.f * __ldg(src + k);
-        tq[j] = nn_filter_threshold(qn[h], p.bound, mm_max);
+        t = nn_filter_threshold(qn[h], p.bound, mm_max);
       } else {
 #pragma unroll
         for (int k = 0; k < NN_DIM; ++k) qn[h][k] = 0.f;
-        tq[j] = -INFINITY;
+        t = -INFINITY;
       }
-      bound[j] = p.bound;
+      tq_s[j * THREADS + tid] = t;
       mn[j] = INFINITY;
     }
 #pragma unroll
@@ -318,34 +357,25 @@ nn_filter_kernel(const NNParams p) {
     const float4* __restrict__ tile = tiles + stage * (NN_TM * 3);
 
 #pragma unroll 2
-    for (int r = 0; r < NN_TM; ++r) {
-      const float4 a = tile[r * 3 + 0];
-      const float4 b = tile[r * 3 + 1];
-      const float4 c = tile[r * 3 + 2];
-      const unsigned long long mm2 = f2_pack(c.z, c.z);
+    for (int r = 0; r < NN_TM; r += 2) {
+      unsigned long long acc0[TP], acc1[TP];
+      nn_row<TP>(tile + r * 3, q2, acc0);
+      nn_row<TP>(tile + r * 3 + 3, q2, acc1);
 #pragma unroll
-      for (int jp = 0; jp < TP; ++jp) {
-        unsigned long long acc = f2_fma(q2[jp][0], f2_pack(a.x, a.x), mm2);
-        acc = f2_fma(q2[jp][1], f2_pack(a.y, a.y), acc);
-        acc = f2_fma(q2[jp][2], f2_pack(a.z, a.z), acc);
-        acc = f2_fma(q2[jp][3], f2_pack(a.w, a.w), acc);
-        acc = f2_fma(q2[jp][4], f2_pack(b.x, b.x), acc);
-        acc = f2_fma(q2[jp][5], f2_pack(b.y, b.y), acc);
-        acc = f2_fma(q2[jp][6], f2_pack(b.z, b.z), acc);
-        acc = f2_fma(q2[jp][7], f2_pack(b.w, b.w), acc);
-        acc = f2_fma(q2[jp][8], f2_pack(c.x, c.x), acc);
-        acc = f2_fma(q2[jp][9], f2_pack(c.y, c.y), acc);
-        float lo, hi;
-        f2_unpack(acc, lo, hi);
-        mn[2 * jp] = fminf(mn[2 * jp], lo);
-        mn[2 * jp + 1] = fminf(mn[2 * jp + 1], hi);
+      for (int jp = 0; jp < TP; ++jp) {  // two rows per 3-input minimum
+        float l0, h0, l1, h1;
+        f2_unpack(acc0[jp], l0, h0);
+        f2_unpack(acc1[jp], l1, h1);
+        mn[2 * jp] = f_min3(mn[2 * jp], l0, l1);
+        mn[2 * jp + 1] = f_min3(mn[2 * jp + 1], h0, h1);
       }
     }
 
     // rare: some row of this tile may be within the bound for some query of this thread
 #pragma unroll
     for (int j = 0; j < TQ; ++j) {
-      if (mn[j] < tq[j]) {
+      const float tqj = tq_s[j * THREADS + tid];
+      if (mn[j] < tqj) {
         const int64_t qi = qbase + (int64_t)j * THREADS + tid;
         float qn[NN_DIM];
 #pragma unroll
@@ -355,12 +385,10 @@ nn_filter_kernel(const NNParams p) {
           qn[k] = (j & 1) ? hi : lo;
         }
         const float nb = nn_rescan_tile(tile, t * NN_TM, p.n_rows, qn[0], qn[1], qn[2], qn[3], qn[4],
-                                        qn[5], qn[6], qn[7], qn[8], qn[9], tq[j], bound[j],
+                                        qn[5], qn[6], qn[7], qn[8], qn[9], tqj, p.bound,
                                         p.keys + qi);
-        if (nb < bound[j]) {
-          bound[j] = nb;
-          tq[j] = fminf(tq[j], nn_filter_threshold(qn, nb, mm_max));
-        }
+        // tighten: later rows only matter if they can reach d2 <= nb
+        tq_s[j * THREADS + tid] = fminf(tqj, nn_filter_threshold(qn, nb, mm_max));
       }
       mn[j] = INFINITY;
     }
@@ -502,7 +530,10 @@ static int nn_launch_filter(vo_nn_s* h, const float* queries_dev, int64_t nq, in
   p.keys = h->keys.as<unsigned long long>();
 
   const int sms = num_sms(h->device);
-  const size_t smem = NN_STAGES * NN_TILE_BYTES + 2 * NN_STAGES * sizeof(uint64_t);
+  auto smem_for = [](int tq, int threads) {
+    return (size_t)NN_STAGES * NN_TILE_BYTES + 2 * NN_STAGES * sizeof(uint64_t) +
+           (size_t)tq * threads * sizeof(float);
+  };
   auto splits_for = [&](int64_t qtiles, int64_t resident) {
     // Every wave should be full: with one query tile per blockIdx.y and `resident` CTAs alive at
     // once, `resident` map splits make each query tile exactly one wave.  Small maps get fewer,
@@ -514,6 +545,7 @@ static int nn_launch_filter(vo_nn_s* h, const float* queries_dev, int64_t nq, in
   };
   auto launch = [&](auto kernel, int tq, int threads) -> int {
     const int64_t qtiles = (nq + (int64_t)tq * threads - 1) / ((int64_t)tq * threads);
+    const size_t smem = smem_for(tq, threads);
     VO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     VO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));

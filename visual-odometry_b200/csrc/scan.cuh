@@ -5,8 +5,11 @@
 // ranks them with warp ballots, and obtains the number of successes in all EARLIER tiles through
 // a decoupled look-back over 64-bit status words  [2-bit flag | 62-bit count]  — one pass over
 // the data, no second kernel.  Tile ids are handed out by an atomic ticket so a tile can only
-// ever wait on tiles that have already started (forward progress without co-residency
-// assumptions).
+// ever wait on tiles that have already been claimed by a running block (forward progress without
+// co-residency assumptions).  Blocks are persistent and software-pipelined: a block claims and
+// starts loading its NEXT tile before it looks back for the current one, so the memory system
+// stays busy while the prefix chain resolves (a block holding tile t and t' > t only ever waits
+// on tiles < t, hence no cycle).
 #pragma once
 #include "common.cuh"
 
@@ -42,23 +45,18 @@ __device__ __forceinline__ void scan_st(unsigned long long* p, unsigned long lon
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Block-wide helper: given each thread's per-item flags (ITEMS of them; item j of lane l of warp
-// w sits at tile position w*32*ITEMS + j*32 + l) computes every item's global output rank.
-// The look-back is done by the WHOLE block: thread i inspects predecessor tile-1-i, so one
-// round covers THREADS predecessors — the prefix front advances THREADS tiles per L2 round trip
-// instead of 32, which keeps the serial chain far above HBM speed.
-// rank[j] is only meaningful where flag[j] is set.
+// Step 1 of a tile: rank the tile's items with warp ballots and publish the tile total.
+// Item j of lane l of warp w sits at tile position w*32*ITEMS + j*32 + l.  On return local[j] is
+// the item's rank inside the tile (meaningful where flag[j] is set) and *tile_total the number of
+// selected items of the tile.  Contains one __syncthreads().
 template <int THREADS, int ITEMS>
-__device__ __forceinline__ void scan_tile_ranks(const ScanWorkspace& ws, int tile,
-                                                const bool (&flag)[ITEMS], long long (&rank)[ITEMS],
-                                                long long* tile_excl, int* tile_total) {
+__device__ __forceinline__ void scan_tile_post(const ScanWorkspace& ws, int tile,
+                                               const bool (&flag)[ITEMS], int (&local)[ITEMS],
+                                               int* tile_total) {
   constexpr int WARPS = THREADS / 32;
   __shared__ int s_warp_tot[WARPS];
-  __shared__ long long s_lb_sum[WARPS];
-  __shared__ int s_lb_has[WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  int local[ITEMS];
   int run = 0;
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
@@ -75,50 +73,68 @@ __device__ __forceinline__ void scan_tile_ranks(const ScanWorkspace& ws, int til
     warp_off += (w < warp) ? x : 0;
     total += x;
   }
-  long long excl = 0;
-  if (tile == 0) {
-    if (threadIdx.x == 0) scan_st(ws.status, SCAN_PREFIX | (unsigned long long)total);
-  } else {
-    if (threadIdx.x == 0) scan_st(ws.status + tile, SCAN_AGG | (unsigned long long)total);
-    int idx = tile - 1;
-    while (true) {
-      const int j = idx - (int)threadIdx.x;
-      unsigned long long v = SCAN_PREFIX;  // "tiles before tile 0": prefix 0
-      if (j >= 0) {
-        do {
-          v = scan_ld(ws.status + j);
-        } while ((v >> 62) == 0ull);
-      }
-      const unsigned pm = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
-      const int first = pm ? (__ffs(pm) - 1) : 32;
-      long long c = (lane <= first) ? (long long)(v & SCAN_MASK) : 0ll;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-      __syncthreads();  // previous round's (and s_warp_tot's) readers are done
-      if (lane == 0) {
-        s_lb_sum[warp] = c;
-        s_lb_has[warp] = pm != 0u;
-      }
-      __syncthreads();
-      bool done = false;
-#pragma unroll
-      for (int w = 0; w < WARPS; ++w) {
-        if (!done) {
-          excl += s_lb_sum[w];
-          done = s_lb_has[w] != 0;
-        }
-      }
-      if (done) break;
-      idx -= THREADS;
-    }
-    if (threadIdx.x == 0)
-      scan_st(ws.status + tile, SCAN_PREFIX | (unsigned long long)(excl + total));
-  }
-  const long long base = excl + warp_off;
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j) rank[j] = base + local[j];
-  *tile_excl = excl;
+  for (int j = 0; j < ITEMS; ++j) local[j] += warp_off;
+  if (threadIdx.x == 0)
+    scan_st(ws.status + tile, (tile == 0 ? SCAN_PREFIX : SCAN_AGG) | (unsigned long long)total);
   *tile_total = total;
+}
+
+// Step 2: number of selected items in all EARLIER tiles.  The look-back is done by the WHOLE
+// block: thread i inspects predecessor tile-1-i, so one round covers THREADS predecessors.
+// Contains __syncthreads(); every thread returns the same value.
+template <int THREADS>
+__device__ __forceinline__ long long scan_tile_lookback(const ScanWorkspace& ws, int tile,
+                                                        int total) {
+  constexpr int WARPS = THREADS / 32;
+  __shared__ long long s_lb_sum[WARPS];
+  __shared__ int s_lb_has[WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (tile == 0) return 0;
+  long long excl = 0;
+  int idx = tile - 1;
+  while (true) {
+    const int j = idx - (int)threadIdx.x;
+    unsigned long long v = SCAN_PREFIX;  // "tiles before tile 0": prefix 0
+    if (j >= 0) {
+      do {
+        v = scan_ld(ws.status + j);
+      } while ((v >> 62) == 0ull);
+    }
+    const unsigned pm = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
+    const int first = pm ? (__ffs(pm) - 1) : 32;
+    long long c = (lane <= first) ? (long long)(v & SCAN_MASK) : 0ll;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    __syncthreads();  // readers of the previous round are done
+    if (lane == 0) {
+      s_lb_sum[warp] = c;
+      s_lb_has[warp] = pm != 0u;
+    }
+    __syncthreads();
+    bool done = false;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) {
+      if (!done) {
+        excl += s_lb_sum[w];
+        done = s_lb_has[w] != 0;
+      }
+    }
+    if (done) break;
+    idx -= THREADS;
+  }
+  if (threadIdx.x == 0)
+    scan_st(ws.status + tile, SCAN_PREFIX | (unsigned long long)(excl + total));
+  return excl;
+}
+
+// Dynamic tile id for a persistent block (one __syncthreads()).
+__device__ __forceinline__ int scan_take_ticket(const ScanWorkspace& ws) {
+  __shared__ int s_ticket;
+  __syncthreads();  // previous readers of s_ticket are done
+  if (threadIdx.x == 0) s_ticket = (int)atomicAdd(ws.ticket, 1u);
+  __syncthreads();
+  return s_ticket;
 }
 #endif
 
