@@ -3,32 +3,41 @@
 // The reference compacts successes sequentially (n_success counter, src/utils.cpp:96-100 and
 // src/camera.cpp:31-33).  On the device every tile of TILE items computes its items and flags,
 // ranks them with warp ballots, and obtains the number of successes in all EARLIER tiles through
-// a decoupled look-back over 64-bit status words  [2-bit flag | 62-bit count]  — one pass over
-// the data, no second kernel.  Tile ids are handed out by an atomic ticket so a tile can only
+// two levels of 64-bit status words (per tile, and per group of tiles) — one pass over the
+// data, no second kernel.  Tile ids are handed out by an atomic ticket so a tile can only
 // ever wait on tiles that have already been claimed by a running block (forward progress without
-// co-residency assumptions).  Blocks are persistent and software-pipelined: a block claims and
-// starts loading its NEXT tile before it looks back for the current one, so the memory system
-// stays busy while the prefix chain resolves (a block holding tile t and t' > t only ever waits
-// on tiles < t, hence no cycle).
+// co-residency assumptions).
 #pragma once
 #include "common.cuh"
 
 namespace vo {
 
-constexpr unsigned long long SCAN_AGG = 1ull << 62;     // tile total published
-constexpr unsigned long long SCAN_PREFIX = 2ull << 62;  // inclusive prefix published
-constexpr unsigned long long SCAN_MASK = (1ull << 62) - 1;
+// status word of a tile: bit 63 = "posted", low bits = number of selected items in the tile.
+// group word: high 24 bits = tiles of the group that have posted, low 40 bits = their sum.
+constexpr unsigned long long SCAN_POSTED = 1ull << 63;
+constexpr unsigned long long SCAN_VALUE_MASK = (1ull << 40) - 1;
+constexpr int SCAN_GROUP_SHIFT = 40;
 
 struct ScanWorkspace {
-  unsigned long long* status;  // [num_tiles], zero-initialised before the launch
+  unsigned long long* status;  // [num_tiles]   zero-initialised before the launch
+  unsigned long long* groups;  // [num_groups]  zero-initialised before the launch
   unsigned int* ticket;        // zero-initialised before the launch
+  int group_tiles;             // tiles per group
 };
 
-inline int64_t scan_workspace_bytes(int64_t num_tiles) { return (num_tiles + 1) * 8 + 64; }
+// tiles per group: at least 64, and few enough groups (<= 256) that one block-wide poll covers
+// all of them
+inline int scan_group_tiles(int64_t num_tiles) {
+  int64_t g = (num_tiles + 255) / 256;
+  return (int)(g < 64 ? 64 : g);
+}
+inline int64_t scan_workspace_bytes(int64_t num_tiles) { return (num_tiles + 256 + 2) * 8 + 64; }
 inline ScanWorkspace scan_workspace_at(void* base, int64_t num_tiles) {
   ScanWorkspace w;
+  w.group_tiles = scan_group_tiles(num_tiles);
   w.status = reinterpret_cast<unsigned long long*>(base);
-  w.ticket = reinterpret_cast<unsigned int*>(w.status + num_tiles);
+  w.groups = w.status + num_tiles;
+  w.ticket = reinterpret_cast<unsigned int*>(w.groups + 257);
   return w;
 }
 
@@ -45,7 +54,8 @@ __device__ __forceinline__ void scan_st(unsigned long long* p, unsigned long lon
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Step 1 of a tile: rank the tile's items with warp ballots and publish the tile total.
+// Step 1 of a tile: rank the tile's items with warp ballots and publish the tile total, both as
+// the tile's own status word and as one atomic add into its group's (count, sum) word.
 // Item j of lane l of warp w sits at tile position w*32*ITEMS + j*32 + l.  On return local[j] is
 // the item's rank inside the tile (meaningful where flag[j] is set) and *tile_total the number of
 // selected items of the tile.  Contains one __syncthreads().
@@ -75,60 +85,55 @@ __device__ __forceinline__ void scan_tile_post(const ScanWorkspace& ws, int tile
   }
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) local[j] += warp_off;
-  if (threadIdx.x == 0)
-    scan_st(ws.status + tile, (tile == 0 ? SCAN_PREFIX : SCAN_AGG) | (unsigned long long)total);
+  if (threadIdx.x == 0) {
+    scan_st(ws.status + tile, SCAN_POSTED | (unsigned long long)total);
+    atomicAdd(ws.groups + tile / ws.group_tiles,
+              (1ull << SCAN_GROUP_SHIFT) | (unsigned long long)total);
+  }
   *tile_total = total;
 }
 
-// Step 2: number of selected items in all EARLIER tiles.  The look-back is done by the WHOLE
-// block: thread i inspects predecessor tile-1-i, so one round covers THREADS predecessors.
-// Contains __syncthreads(); every thread returns the same value.
+// Step 2: number of selected items in all EARLIER tiles
+//     = sum of the COMPLETE groups before this tile's group  (one word each)
+//     + sum of the earlier tiles of its own group            (one word each).
+// There is no prefix to propagate from tile to tile: every tile sums independently as soon as
+// its predecessors have posted, with the whole block polling (thread i takes word i), so the
+// only serial dependency left is the unavoidable one — an ordered output position needs the
+// counts of everything before it.  Contains __syncthreads(); every thread returns the same value.
 template <int THREADS>
-__device__ __forceinline__ long long scan_tile_lookback(const ScanWorkspace& ws, int tile,
-                                                        int total) {
+__device__ __forceinline__ long long scan_tile_lookback(const ScanWorkspace& ws, int tile) {
   constexpr int WARPS = THREADS / 32;
   __shared__ long long s_lb_sum[WARPS];
-  __shared__ int s_lb_has[WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (tile == 0) return 0;
-  long long excl = 0;
-  int idx = tile - 1;
-  while (true) {
-    const int j = idx - (int)threadIdx.x;
-    unsigned long long v = SCAN_PREFIX;  // "tiles before tile 0": prefix 0
-    if (j >= 0) {
-      do {
-        v = scan_ld(ws.status + j);
-      } while ((v >> 62) == 0ull);
-    }
-    const unsigned pm = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
-    const int first = pm ? (__ffs(pm) - 1) : 32;
-    long long c = (lane <= first) ? (long long)(v & SCAN_MASK) : 0ll;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    __syncthreads();  // readers of the previous round are done
-    if (lane == 0) {
-      s_lb_sum[warp] = c;
-      s_lb_has[warp] = pm != 0u;
-    }
-    __syncthreads();
-    bool done = false;
-#pragma unroll
-    for (int w = 0; w < WARPS; ++w) {
-      if (!done) {
-        excl += s_lb_sum[w];
-        done = s_lb_has[w] != 0;
-      }
-    }
-    if (done) break;
-    idx -= THREADS;
+  const int G = ws.group_tiles;
+  const int g = tile / G;
+  long long c = 0;
+  for (int idx = (int)threadIdx.x; idx < g; idx += THREADS) {
+    unsigned long long v;
+    do {
+      v = scan_ld(ws.groups + idx);
+    } while ((int)(v >> SCAN_GROUP_SHIFT) != G);
+    c += (long long)(v & SCAN_VALUE_MASK);
   }
-  if (threadIdx.x == 0)
-    scan_st(ws.status + tile, SCAN_PREFIX | (unsigned long long)(excl + total));
+  for (int idx = g * G + (int)threadIdx.x; idx < tile; idx += THREADS) {
+    unsigned long long v;
+    do {
+      v = scan_ld(ws.status + idx);
+    } while ((v & SCAN_POSTED) == 0ull);
+    c += (long long)(v & SCAN_VALUE_MASK);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  __syncthreads();  // s_lb_sum may still be read by a previous call
+  if (lane == 0) s_lb_sum[warp] = c;
+  __syncthreads();
+  long long excl = 0;
+#pragma unroll
+  for (int w = 0; w < WARPS; ++w) excl += s_lb_sum[w];
   return excl;
 }
 
-// Dynamic tile id for a persistent block (one __syncthreads()).
+// Dynamic tile id (two __syncthreads()).
 __device__ __forceinline__ int scan_take_ticket(const ScanWorkspace& ws) {
   __shared__ int s_ticket;
   __syncthreads();  // previous readers of s_ticket are done

@@ -7,9 +7,11 @@
 // Both are HBM-bound elementwise maps followed by the reference's sequential "n_success"
 // compaction.  Each is ONE kernel: a tile of 1024 correspondences is loaded with coalesced 8-byte
 // pair reads + gathered 8-byte image points, solved in registers, ranked with warp ballots, and
-// the tile's output offset comes from a decoupled look-back (scan.cuh) — 44 algorithmic bytes
-// per correspondence (8 pair + 8 + 8 points in, 12 point + 8 pair out), touched once.
+// the tile's output offset is the sum of the two-level status words of everything before it
+// (scan.cuh) — 44 algorithmic bytes per correspondence (8 pair + 8 + 8 points in, 12 point +
+// 8 pair out), touched once.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -62,87 +64,67 @@ __device__ __forceinline__ bool triangulate_point_dev(const float (&d1)[3], cons
   return true;
 }
 
-struct TriLoads {
-  int2 c[TRI_ITEMS];
-  float2 a[TRI_ITEMS], b[TRI_ITEMS];
-  bool in[TRI_ITEMS];
-};
-__device__ __forceinline__ void tri_load_corr(const TriParams& q, int tile, TriLoads& L) {
+// One tile of THREADS*ITEMS correspondences per block.  Item j of lane l of warp w sits at tile
+// position w*32*ITEMS + j*32 + l, so every load and store of a warp is a contiguous run.
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS) triangulate_kernel(const TriParams q) {
+  constexpr int TILE = THREADS * ITEMS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t warp_base = (int64_t)tile * TRI_TILE + (int64_t)warp * (32 * TRI_ITEMS);
+  const int tile = scan_take_ticket(q.ws);
+  const int64_t warp_base = (int64_t)tile * TILE + (int64_t)warp * (32 * ITEMS);
+
+  int2 c[ITEMS];
+  bool in[ITEMS];
 #pragma unroll
-  for (int j = 0; j < TRI_ITEMS; ++j) {
+  for (int j = 0; j < ITEMS; ++j) {
     const int64_t i = warp_base + j * 32 + lane;
-    L.in[j] = i < q.n_corr;
-    L.c[j] = L.in[j] ? __ldg(q.corr + i) : make_int2(0, 0);
+    in[j] = i < q.n_corr;
+    c[j] = in[j] ? __ldg(q.corr + i) : make_int2(0, 0);
   }
-}
-__device__ __forceinline__ void tri_load_points(const TriParams& q, TriLoads& L) {
+  float2 a[ITEMS], b[ITEMS];
 #pragma unroll
-  for (int j = 0; j < TRI_ITEMS; ++j)
-    if (L.in[j]) {
-      L.a[j] = __ldg(q.p1 + L.c[j].x);  // .first  -> image 1   (utils.cpp:87)
-      L.b[j] = __ldg(q.p2 + L.c[j].y);  // .second -> image 2   (utils.cpp:88)
+  for (int j = 0; j < ITEMS; ++j)
+    if (in[j]) {
+      a[j] = __ldg(q.p1 + c[j].x);  // .first  -> image 1   (utils.cpp:87)
+      b[j] = __ldg(q.p2 + c[j].y);  // .second -> image 2   (utils.cpp:88)
     }
-}
-
-__global__ void __launch_bounds__(TRI_THREADS) triangulate_kernel(const TriParams q) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float P[ITEMS][3];
+  bool ok[ITEMS];
   const float t[3] = {q.t[0], q.t[1], q.t[2]};
-  TriLoads nxt;
-  int tile = scan_take_ticket(q.ws);
-  if (tile < q.num_tiles) {
-    tri_load_corr(q, tile, nxt);
-    tri_load_points(q, nxt);
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    ok[j] = false;
+    if (in[j]) {
+      float d1[3], d2[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        d1[i] = q.iK[i] * a[j].x + (q.iK[3 + i] * a[j].y + q.iK[6 + i]);        // iK*[p1;1]   :91
+        d2[i] = q.iRiK[i] * b[j].x + (q.iRiK[3 + i] * b[j].y + q.iRiK[6 + i]);  // iRiK*[p2;1] :94
+      }
+      ok[j] = triangulate_point_dev(d1, d2, t, P[j]);
+    }
   }
-  while (tile < q.num_tiles) {
-    const TriLoads cur = nxt;
-    // claim the next tile and start its coalesced pair loads before touching this tile's data
-    const int ntile = scan_take_ticket(q.ws);
-    if (ntile < q.num_tiles) tri_load_corr(q, ntile, nxt);
-
-    float P[TRI_ITEMS][3];
-    bool ok[TRI_ITEMS];
+  int local[ITEMS];
+  int total;
+  scan_tile_post<THREADS, ITEMS>(q.ws, tile, ok, local, &total);
+  const long long excl = scan_tile_lookback<THREADS>(q.ws, tile);
 #pragma unroll
-    for (int j = 0; j < TRI_ITEMS; ++j) {
-      ok[j] = false;
-      if (cur.in[j]) {
-        float d1[3], d2[3];
+  for (int j = 0; j < ITEMS; ++j)
+    if (ok[j]) {
+      const long long k = excl + local[j];
+      q.out_points[3 * k + 0] = P[j][0];
+      q.out_points[3 * k + 1] = P[j][1];
+      q.out_points[3 * k + 2] = P[j][2];
+      if (q.out_corr_new) q.out_corr_new[k] = make_int2(c[j].y, (int)k);  // (idx_second, k) :97
+      if (q.out_src) q.out_src[k] = (int32_t)(warp_base + j * 32 + lane);
+      if (q.out_app) {  // :127 — the appearance travels with the point
+        const float2* src = reinterpret_cast<const float2*>(q.app2 + 10 * (int64_t)c[j].y);
+        float2* dst = reinterpret_cast<float2*>(q.out_app + 10 * k);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          d1[i] = q.iK[i] * cur.a[j].x + (q.iK[3 + i] * cur.a[j].y + q.iK[6 + i]);        // :91
-          d2[i] = q.iRiK[i] * cur.b[j].x + (q.iRiK[3 + i] * cur.b[j].y + q.iRiK[6 + i]);  // :94
-        }
-        ok[j] = triangulate_point_dev(d1, d2, t, P[j]);
+        for (int i = 0; i < 5; ++i) dst[i] = __ldg(src + i);
       }
     }
-    int local[TRI_ITEMS];
-    int total;
-    scan_tile_post<TRI_THREADS, TRI_ITEMS>(q.ws, tile, ok, local, &total);
-    // the next tile's point gathers are in flight while this tile's prefix is resolved
-    if (ntile < q.num_tiles) tri_load_points(q, nxt);
-    const long long excl = scan_tile_lookback<TRI_THREADS>(q.ws, tile, total);
-
-    const int64_t warp_base = (int64_t)tile * TRI_TILE + (int64_t)warp * (32 * TRI_ITEMS);
-#pragma unroll
-    for (int j = 0; j < TRI_ITEMS; ++j)
-      if (ok[j]) {
-        const long long k = excl + local[j];
-        q.out_points[3 * k + 0] = P[j][0];
-        q.out_points[3 * k + 1] = P[j][1];
-        q.out_points[3 * k + 2] = P[j][2];
-        if (q.out_corr_new) q.out_corr_new[k] = make_int2(cur.c[j].y, (int)k);  // (idx_second, k) :97
-        if (q.out_src) q.out_src[k] = (int32_t)(warp_base + j * 32 + lane);
-        if (q.out_app) {  // :127 — the appearance travels with the point
-          const float2* src = reinterpret_cast<const float2*>(q.app2 + 10 * (int64_t)cur.c[j].y);
-          float2* dst = reinterpret_cast<float2*>(q.out_app + 10 * k);
-#pragma unroll
-          for (int i = 0; i < 5; ++i) dst[i] = __ldg(src + i);
-        }
-      }
-    if (tile == q.num_tiles - 1 && threadIdx.x == 0) *q.n_success = excl + total;
-    tile = ntile;
-  }
+  if (tile == q.num_tiles - 1 && threadIdx.x == 0) *q.n_success = excl + total;
 }
 
 // ---- Camera::projectPoints -----------------------------------------------------------------------
@@ -179,52 +161,34 @@ __device__ __forceinline__ bool project_point_dev(const ProjParams& q, float wx,
 
 __global__ void __launch_bounds__(TRI_THREADS) project_points_kernel(const ProjParams q) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float w[TRI_ITEMS][3];
-  auto load = [&](int tile) {
-    const int64_t warp_base = (int64_t)tile * TRI_TILE + (int64_t)warp * (32 * TRI_ITEMS);
+  const int tile = scan_take_ticket(q.ws);
+  const int64_t warp_base = (int64_t)tile * TRI_TILE + (int64_t)warp * (32 * TRI_ITEMS);
+  float2 uv[TRI_ITEMS];
+  bool ok[TRI_ITEMS], in[TRI_ITEMS];
 #pragma unroll
-    for (int j = 0; j < TRI_ITEMS; ++j) {
-      const int64_t i = warp_base + j * 32 + lane;
-      if (i < q.n) {
-        const float* src = q.world + 3 * i;
-        w[j][0] = __ldg(src);
-        w[j][1] = __ldg(src + 1);
-        w[j][2] = __ldg(src + 2);
-      }
+  for (int j = 0; j < TRI_ITEMS; ++j) {
+    const int64_t i = warp_base + j * 32 + lane;
+    in[j] = i < q.n;
+    ok[j] = false;
+    if (in[j]) {
+      const float* w = q.world + 3 * i;
+      ok[j] = project_point_dev(q, __ldg(w), __ldg(w + 1), __ldg(w + 2), &uv[j]);
+      if (!ok[j]) uv[j] = make_float2(-1.f, -1.f);  // camera.cpp:21,30
     }
-  };
-  int tile = scan_take_ticket(q.ws);
-  if (tile < q.num_tiles) load(tile);
-  while (tile < q.num_tiles) {
-    const int64_t warp_base = (int64_t)tile * TRI_TILE + (int64_t)warp * (32 * TRI_ITEMS);
-    float2 uv[TRI_ITEMS];
-    bool ok[TRI_ITEMS], in[TRI_ITEMS];
+  }
+  int local[TRI_ITEMS];
+  int total;
+  scan_tile_post<TRI_THREADS, TRI_ITEMS>(q.ws, tile, ok, local, &total);
+  const long long excl = scan_tile_lookback<TRI_THREADS>(q.ws, tile);
 #pragma unroll
-    for (int j = 0; j < TRI_ITEMS; ++j) {
-      in[j] = warp_base + j * 32 + lane < q.n;
-      ok[j] = false;
-      if (in[j]) {
-        ok[j] = project_point_dev(q, w[j][0], w[j][1], w[j][2], &uv[j]);
-        if (!ok[j]) uv[j] = make_float2(-1.f, -1.f);  // camera.cpp:21,30
-      }
-    }
-    const int ntile = scan_take_ticket(q.ws);
-    if (ntile < q.num_tiles) load(ntile);  // in flight during the look-back
-    int local[TRI_ITEMS];
-    int total;
-    scan_tile_post<TRI_THREADS, TRI_ITEMS>(q.ws, tile, ok, local, &total);
-    const long long excl = scan_tile_lookback<TRI_THREADS>(q.ws, tile, total);
-#pragma unroll
-    for (int j = 0; j < TRI_ITEMS; ++j) {
-      if (!in[j]) continue;
-      if (q.keep_indices) q.out[warp_base + j * 32 + lane] = uv[j];
-      else if (ok[j]) q.out[excl + local[j]] = uv[j];
-    }
-    if (tile == q.num_tiles - 1 && threadIdx.x == 0) {
-      q.counts[1] = excl + total;
-      q.counts[0] = q.keep_indices ? (long long)q.n : excl + total;
-    }
-    tile = ntile;
+  for (int j = 0; j < TRI_ITEMS; ++j) {
+    if (!in[j]) continue;
+    if (q.keep_indices) q.out[warp_base + j * 32 + lane] = uv[j];
+    else if (ok[j]) q.out[excl + local[j]] = uv[j];
+  }
+  if (tile == q.num_tiles - 1 && threadIdx.x == 0) {
+    q.counts[1] = excl + total;
+    q.counts[0] = q.keep_indices ? (long long)q.n : excl + total;
   }
 }
 
@@ -266,23 +230,12 @@ static void tri_precompute(const float K[9], const float X[16], TriParams* q) {
   h_mat3_mul(iR, q->iK, q->iRiK);
 }
 
-// persistent grid: every SM filled to its occupancy limit, never more blocks than tiles
-static int64_t persistent_grid(int64_t tiles, const void* kernel) {
-  int dev = 0, sms = 148, per_sm = 4;
-  cudaGetDevice(&dev);
-  sms = num_sms(dev);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TRI_THREADS, 0) != cudaSuccess ||
-      per_sm < 1)
-    per_sm = 1;
-  const int64_t full = (int64_t)sms * per_sm;
-  return tiles < full ? tiles : full;
-}
-
 static int tri_launch(cudaStream_t stream, const float K[9], const float X[16], const int32_t* corr,
                       int64_t n, const float* p1, const float* p2, const float* app2, float* out_pts,
                       int32_t* out_corr_new, float* out_app, int32_t* out_src, int64_t* n_success,
                       void* workspace) {
-  const int64_t tiles = (n + TRI_TILE - 1) / TRI_TILE;
+  const int tile_items = TRI_TILE;
+  const int64_t tiles = (n + tile_items - 1) / tile_items;
   VO_REQUIRE(tiles < (1LL << 31), VO_ERR_UNSUPPORTED, "too many correspondences");
   if (n == 0) {
     VO_CUDA(cudaMemsetAsync(n_success, 0, sizeof(int64_t), stream));
@@ -303,8 +256,7 @@ static int tri_launch(cudaStream_t stream, const float K[9], const float X[16], 
   q.n_success = reinterpret_cast<long long*>(n_success);
   q.ws = scan_workspace_at(workspace, tiles);
   q.num_tiles = (int)tiles;
-  triangulate_kernel<<<(unsigned)persistent_grid(tiles, (const void*)triangulate_kernel), TRI_THREADS,
-                       0, stream>>>(q);
+  triangulate_kernel<TRI_THREADS, TRI_ITEMS><<<(unsigned)tiles, TRI_THREADS, 0, stream>>>(q);
   VO_LAUNCH_CHECK();
   return VO_OK;
 }
@@ -455,8 +407,7 @@ int vo_project_points(int device, const vo_camera* cam, const float* world_host,
   q.counts = cx->cnt.as<long long>();
   q.ws = scan_workspace_at(cx->ws.p, tiles);
   q.num_tiles = (int)tiles;
-  project_points_kernel<<<(unsigned)persistent_grid(tiles, (const void*)project_points_kernel),
-                          TRI_THREADS, 0, s>>>(q);
+  project_points_kernel<<<(unsigned)tiles, TRI_THREADS, 0, s>>>(q);
   VO_LAUNCH_CHECK();
   long long counts[2] = {0, 0};
   VO_CUDA(cudaMemcpyAsync(counts, cx->cnt.p, sizeof(counts), cudaMemcpyDeviceToHost, s));
