@@ -113,13 +113,25 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU legs (the oracle; the ONLY place bench.py touches oracle/)
 # ---------------------------------------------------------------------------------------------
+def cpu_kind():
+    """'reference' when oracle/_ref (the reference's own bruteForceBestMatch template, compiled
+    from /root/reference by oracle/build_ref.sh) travelled with the repo, else the C port."""
+    import ref_lib
+
+    return "reference" if ref_lib.available() else "port"
+
+
 def cpu_nn_queries_per_s(map_host, queries_host, threads):
     import oracle_lib as oracle
+    import ref_lib
 
-    oracle.lib()
+    use_ref = ref_lib.available()
+    (ref_lib if use_ref else oracle).lib()
     chunks = [c for c in np.array_split(np.arange(len(queries_host)), threads) if len(c)]
 
     def work(ix):
+        if use_ref:
+            return ref_lib.nn_best_match_inplace(map_host, queries_host[ix], RADIUS)
         return oracle.nn_best_match(map_host, queries_host[ix], RADIUS)[0]
 
     t0 = time.perf_counter()
@@ -130,9 +142,10 @@ def cpu_nn_queries_per_s(map_host, queries_host, threads):
 
 
 def reference_arm(args):
-    """--impl reference: the reference's CPU algorithm (oracle port: the reference cannot be
-    built on the GPU box) on all host cores; each step = a bounded query sample
-    against the FULL map."""
+    """--impl reference: the reference's CPU path for the metric — its bruteForceBestMatch
+    template (oracle/_ref, prebuilt from the reference sources; the C port if that is absent) on
+    all host cores, one thread per query slice; each step = a bounded query sample against the
+    FULL map."""
     synth = importlib.import_module("visual-odometry_b200.synth")
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -165,7 +178,7 @@ def reference_arm(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"appearance NN: {Q} queries x {M}-row 10-D map, radius {RADIUS}",
                    "map_rows": M, "queries": Q},
-        "cpu_baseline": {"value": val, "unit": "queries/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": val, "unit": "queries/s", "cores": cores, "kind": cpu_kind(),
                          "sample": f"{per_step} queries x full {M}-row map per step, "
                                    f"{cores} threads over queries"},
         "e2e": {"value": val, "unit": "queries/s", "h2d_bytes_per_step": 0,
@@ -375,14 +388,13 @@ def ours_arm(args):
     # ---- inputs: map replicated on every GPU (generated in place), queries sharded -----------
     map_dev = synth.nn_map_torch(M, dev)
     q_np, target = synth.nn_queries_np(Q, M)
-    lo, hi = rank * Q // world, (rank + 1) * Q // world
+    sharding = importlib.import_module("visual-odometry_b200.sharding")
+    lo, hi = sharding.shard_bounds(Q, world, rank)
     q_shard_host = torch.from_numpy(q_np[lo:hi]).pin_memory()
     q_shard = q_shard_host.to(dev)
     nq = hi - lo
     idx_shard = torch.empty(nq, dtype=torch.int32, device=dev)
     idx_all = torch.empty(Q, dtype=torch.int32, device=dev) if world > 1 else idx_shard
-    counts = [((r + 1) * Q // world) - (r * Q // world) for r in range(world)]
-    even = len(set(counts)) == 1
 
     nn = vo.NNIndex(local)
     nn.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -392,13 +404,8 @@ def ours_arm(args):
     torch.cuda.empty_cache()
 
     def gather():
-        if world == 1:
-            return
-        if even:
-            dist.all_gather_into_tensor(idx_all, idx_shard)
-        else:
-            outs = list(idx_all.split(counts))
-            dist.all_gather(outs, idx_shard)
+        if world > 1:
+            sharding.gather_indices(dist, idx_shard, idx_all, Q)
 
     def step():
         nn.best_match_device(q_shard.data_ptr(), nq, 11, RADIUS, idx_shard.data_ptr())
@@ -432,7 +439,6 @@ def ours_arm(args):
     t0 = time.perf_counter()
     for _ in range(args.steps):
         estep()
-        gather_host = None
     e2e_s = (time.perf_counter() - t0) / args.steps
     if dist is not None:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -490,7 +496,8 @@ def ours_arm(args):
                          "nominal_fp32_tflops": NOMINAL_FP32_TFLOPS,
                          "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS,
                          "kernel_ms": kms},
-            "cpu_baseline": {"value": cpu_qps, "unit": "queries/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": cpu_qps, "unit": "queries/s", "cores": cores,
+                             "kind": cpu_kind(),
                              "sample": f"{sample_q} queries x full {M}-row map, {cores} threads"},
             "parity": {"planted_answers_equal": planted_ok, "oracle_sample_equal": oracle_equal,
                        "oracle_sample": sample_q, "rule": "bit-exact indices"},

@@ -75,6 +75,32 @@ void ref_nn_best_match(const float* map, int64_t n_rows, const float* queries, i
   }
 }
 
+// The same template instantiated over the caller's buffer IN PLACE (no copy of the map): a
+// minimal iterator over tightly packed Vector11f rows.  Read-only, so several host threads may
+// search the same map concurrently (bench.py's CPU arm).
+namespace {
+struct RowIterator {
+  using value_type = Vector11f;
+  Vector11f* p;
+  Vector11f& operator*() const { return *p; }
+  RowIterator& operator++() {
+    ++p;
+    return *this;
+  }
+  bool operator!=(const RowIterator& o) const { return p != o.p; }
+};
+static_assert(sizeof(Vector11f) == 11 * sizeof(float), "rows must be tightly packed");
+}  // namespace
+void ref_nn_best_match_inplace(const float* map, int64_t n_rows, const float* queries,
+                               int64_t n_queries, float norm, int32_t* best_idx) {
+  Vector11f* rows = reinterpret_cast<Vector11f*>(const_cast<float*>(map));
+  const Vector11f* q = reinterpret_cast<const Vector11f*>(queries);
+  for (int64_t i = 0; i < n_queries; ++i) {
+    Vector11f* hit = bruteForceBestMatch(RowIterator{rows}, RowIterator{rows + n_rows}, q[i], norm);
+    best_idx[i] = hit ? (int32_t)(hit - rows) : -1;
+  }
+}
+
 // bruteForceSearch (include/brute_force_search.h:3-20)
 void ref_nn_radius_search(const float* map, int64_t n_rows, const float* queries, int64_t n_queries,
                           float norm, int32_t* counts, int32_t* idx_out, int32_t max_per_query) {

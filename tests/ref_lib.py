@@ -22,6 +22,7 @@ def lib():
         L = C.CDLL(_SO)
         vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
         L.ref_nn_best_match.argtypes = [vp, i64, vp, i64, f32, vp, vp]
+        L.ref_nn_best_match_inplace.argtypes = [vp, i64, vp, i64, f32, vp]
         L.ref_nn_radius_search.argtypes = [vp, i64, vp, i64, f32, vp, vp, i32]
         L.ref_kdtree_best_match.argtypes = [vp, i64, vp, i64, f32, C.c_int, C.c_int, vp]
         L.ref_project_points.argtypes = [C.c_int] * 4 + [vp, vp, vp, i64, C.c_int, vp,
@@ -57,6 +58,15 @@ def nn_best_match(rows, queries, norm):
     d2 = np.empty(len(queries), np.float32)
     lib().ref_nn_best_match(_p(rows), len(rows), _p(queries), len(queries), norm, _p(idx), _p(d2))
     return idx, d2
+
+
+def nn_best_match_inplace(rows, queries, norm):
+    """bruteForceBestMatch over the caller's (M,11) float32 buffer, no copy; thread-safe."""
+    assert rows.dtype == np.float32 and rows.flags.c_contiguous and rows.shape[1] == 11
+    queries = _f32(queries)
+    idx = np.empty(len(queries), np.int32)
+    lib().ref_nn_best_match_inplace(_p(rows), len(rows), _p(queries), len(queries), norm, _p(idx))
+    return idx
 
 
 def nn_radius_search(rows, queries, norm, max_per_query):

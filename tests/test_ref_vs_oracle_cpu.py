@@ -24,6 +24,7 @@ def test_nn_best_match_bit_exact(oracle, synth):
         oi, od = oracle.nn_best_match(m, q, norm)
         assert np.array_equal(ri, oi)
         assert np.array_equal(rd[ri >= 0], od[ri >= 0])
+        assert np.array_equal(ref_lib.nn_best_match_inplace(m, q, norm), oi)
 
 
 def test_nn_radius_search_exact(oracle):
