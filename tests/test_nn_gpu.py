@@ -52,6 +52,23 @@ def test_planted_random_vs_oracle(vo, oracle, synth, M, Q):
     assert np.array_equal(idx[exact], target[exact])
 
 
+@pytest.mark.parametrize("Q", [9216 + 1, 9216 + 212, 9216 + 600, 9216 + 1500, 9216 + 2000,
+                               9216 + 3000, 12500])
+def test_remainder_launch_variants_vs_oracle(vo, oracle, synth, Q):
+    """Batches above 8192 queries run whole 3072-query tiles plus ONE remainder launch whose
+    register tile depends on the remainder size; every variant must give the oracle's answers."""
+    M = 4099
+    m = synth.nn_map_rows_np(0, M)
+    q, _ = synth.nn_queries_np(Q, M)
+    nn = vo.NNIndex(0)
+    nn.set_map(m)
+    idx, d2 = nn.best_match(q, 0.1, want_d2=True)
+    nn.close()
+    oi, od = oracle.nn_best_match(m, q, 0.1)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(d2[oi >= 0], od[oi >= 0])
+
+
 def test_large_radius_true_argmin(vo, oracle):
     """radius large enough that EVERY row is a candidate: exercises the bound-tightening path."""
     rng = np.random.RandomState(5)

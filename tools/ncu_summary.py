@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Summarise one .ncu-rep (ncu --set full) into the handful of numbers DESIGN.md / bench.py quote.
+Usage: ncu_summary.py report.ncu-rep  -> markdown on stdout (needs `ncu` on PATH, no GPU)."""
+import csv, io, subprocess, sys
+
+WANT = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size",
+    "launch__registers_per_thread", "launch__occupancy_limit_registers",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fmalite.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum",
+    "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum",
+    "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "sm__cycles_elapsed.avg.per_second",
+]
+rep = sys.argv[1]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units = rows[0], rows[1]
+for r in rows[2:]:
+    col = dict(zip(hdr, zip(units, r)))
+    print(f"### {col['Kernel Name'][1]}  (grid {col['Grid Size'][1]}, block {col['Block Size'][1]})\n")
+    print("| metric | value | unit |\n|---|---|---|")
+    for w in WANT:
+        if w in col:
+            print(f"| `{w}` | {col[w][1]} | {col[w][0]} |")
+    print()

@@ -231,24 +231,6 @@ __device__ __noinline__ float nn_rescan_tile(const float4* __restrict__ tile, in
   return best;
 }
 
-// packed FP32 pairs: sm_100a executes fma.rn.f32x2 as ONE FFMA2 issue slot for two FMAs, and
-// ptxas folds a {x,x} pair into a scalar-broadcast operand (FFMA2 Rd, Ra.F32x2, Rb.F32, Rc.F32x2),
-// so two queries share every map coefficient without any packing instruction.
-__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b,
-                                                     unsigned long long c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-
 __device__ __forceinline__ float f_min3(float a, float b, float c) {
   float r;
   asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));  // SASS FMNMX3
@@ -543,26 +525,47 @@ static int nn_launch_filter(vo_nn_s* h, const float* queries_dev, int64_t nq, in
     if (qtiles * s < resident) s = std::min<int64_t>(h->n_tiles, (resident + qtiles - 1) / qtiles);
     return std::max<int64_t>(1, s);
   };
-  auto launch = [&](auto kernel, int tq, int threads) -> int {
-    const int64_t qtiles = (nq + (int64_t)tq * threads - 1) / ((int64_t)tq * threads);
+  // one launch over the query range [q0, q0+cnt)
+  auto launch = [&](auto kernel, int tq, int threads, int64_t q0, int64_t cnt) -> int {
+    NNParams r = p;
+    r.queries = queries_dev + q0 * (int64_t)qstride;
+    r.keys = p.keys + q0;
+    r.n_queries = cnt;
+    const int64_t qtiles = (cnt + (int64_t)tq * threads - 1) / ((int64_t)tq * threads);
     const size_t smem = smem_for(tq, threads);
     VO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     VO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     const int64_t splits = splits_for(qtiles, (int64_t)sms * std::max(per_sm, 1));
-    p.tiles_per_split = (h->n_tiles + splits - 1) / splits;
-    const int64_t nsplit = (h->n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+    r.tiles_per_split = (h->n_tiles + splits - 1) / splits;
+    const int64_t nsplit = (h->n_tiles + r.tiles_per_split - 1) / r.tiles_per_split;
     VO_REQUIRE(qtiles <= 65535, VO_ERR_UNSUPPORTED, "too many query tiles for one launch");
     dim3 grid((unsigned)nsplit, (unsigned)qtiles);
-    kernel<<<grid, threads, smem, h->stream>>>(p);
+    kernel<<<grid, threads, smem, h->stream>>>(r);
     VO_LAUNCH_CHECK();
     return VO_OK;
   };
+  // a batch too small for the wide register tile
+  auto launch_small = [&](int64_t q0, int64_t cnt) -> int {
+    if (cnt > 1024) return launch(nn_filter_kernel<2, 256>, 2, 256, q0, cnt);
+    return launch(nn_filter_kernel<2, 64>, 2, 64, q0, cnt);
+  };
   // 8 queries/thread x 384 threads: 160 registers x 384 fills the 64K-register file of an SM with
-  // 12 warps (3 per scheduler), the most that fit at this register tile
-  if (nq > 8192) return launch(nn_filter_kernel<8, 384>, 8, 384);
-  if (nq > 1024) return launch(nn_filter_kernel<2, 256>, 2, 256);
-  return launch(nn_filter_kernel<2, 64>, 2, 64);
+  // 12 warps (3 per scheduler), the most that fit at this register tile.  One such query tile
+  // (3072 queries) against the whole map is exactly one wave of the chip, so a batch is cut into
+  // whole tiles plus ONE remainder launch whose per-thread query count is the smallest that holds
+  // it: a sharded batch (Q/8 = 12500 queries = 4.07 tiles) then costs 4 waves plus a thin one
+  // instead of 5 (what near-linear scaling of the query-sharded sweep hinges on).
+  constexpr int64_t WIDE = 8 * 384;
+  if (nq <= 8192) return launch_small(0, nq);
+  const int64_t full = nq / WIDE * WIDE, rem = nq - full;
+  int rc = launch(nn_filter_kernel<8, 384>, 8, 384, 0, full);
+  if (rc || rem == 0) return rc;
+  if (rem <= 512) return launch(nn_filter_kernel<2, 256>, 2, 256, full, rem);
+  if (rem <= 2 * 384) return launch(nn_filter_kernel<2, 384>, 2, 384, full, rem);
+  if (rem <= 4 * 384) return launch(nn_filter_kernel<4, 384>, 4, 384, full, rem);
+  if (rem <= 6 * 384) return launch(nn_filter_kernel<6, 384>, 6, 384, full, rem);
+  return launch(nn_filter_kernel<8, 384>, 8, 384, full, rem);
 }
 
 static int nn_set_map_common(vo_nn_s* h, const float* rows_dev, int64_t n_rows, int row_stride,

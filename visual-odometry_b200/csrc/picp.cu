@@ -30,7 +30,7 @@
 
 namespace vo {
 
-constexpr int PICP_THREADS = 256;
+constexpr int PICP_THREADS = 384;
 constexpr int PICP_UNROLL = 4;
 constexpr int PICP_NACC = 32;  // 21 H + 6 b + chi_in + chi_out + n_in (as float bits of int) + 2 pad
 
@@ -119,117 +119,159 @@ __device__ void picp_solve_and_update(const PicpParams& p, const float* tot) {
   s.last_ok = 1;
 }
 
-// One correspondence: errorAndJacobian (:25-53) + the body of linearize's loop (:62-95).
+// Two correspondences at a time: errorAndJacobian (:25-53) + the body of linearize's loop (:62-95).
 // Branch-free: a rejected point runs the same instructions with weight 0, so a warp never
 // diverges on the data.
+//
+// Packed arithmetic.  At 28 B per point the kernel is HBM-bound only if its instruction stream
+// stays well under the issue rate 6.5 TB/s implies; the scalar formulation (136 instructions per
+// point, 88 of them FP32) was issue-bound (ncu: 70 % issue-active, "not selected" the top stall).
+// The two lanes of sm_100a's packed FP32 pairs (fma/mul/add.rn.f32x2 -> SASS FFMA2/FMUL2/FADD2,
+// one issue slot for two operations) therefore carry TWO POINTS: every FP32 instruction of the
+// per-point math is issued once per pair.  Each lane performs exactly the scalar operation
+// sequence, so results do not depend on which lane a point lands in; the accumulators are
+// lane-split partial sums, added together once after the loop.
 //
 // PINHOLE == true is selected by the host when K is exactly [fx 0 cx; 0 fy cy; 0 0 1] (the only
 // form the reference's mains ever build: picp_solver_test.cpp:52-54, camera.dat).  Every product
 // with a structural zero of K, and every term of J^T J that contains one, is dropped at compile
 // time; the surviving operations are the same FMAs in the same order, so the result is
 // bit-identical to the general-K path (tests/test_picp_gpu.py checks this).
+typedef unsigned long long f2_t;
+
 struct PicpAcc {
-  float h[21];
-  float b[6];
-  float chi_in, chi_out;
+  f2_t h[21];  // upper triangle of sum(lambda J^T J), lanes = the two point slots
+  f2_t b[6];
+  f2_t chi_in, chi_out;
   int n_in;
 };
 
+// per-thread constants of a round
+struct PicpConsts {
+  float T[12];  // world-in-camera: 3x3 linear (column-major) then translation
+};
+
 // 1/x to within 1 ulp without the IEEE-division slow path: MUFU.RCP + one Newton step
-__device__ __forceinline__ float picp_rcp(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  const float e = fmaf(-x, r, 1.0f);
-  return fmaf(r, e, r);
+__device__ __forceinline__ f2_t picp_rcp2(f2_t x) {
+  float x0, x1, r0, r1;
+  f2_unpack(x, x0, x1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(x0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(x1));
+  const f2_t r = f2_pack(r0, r1);
+  const f2_t e = f2_fma(x, f2_mul(r, f2_bc(-1.f)), f2_bc(1.0f));  // 1 - x*r
+  return f2_fma(r, e, r);
 }
 
-template <bool PINHOLE>
-__device__ __forceinline__ void picp_point(const PicpParams& p, const float (&T)[12], float wx,
-                                           float wy, float wz, float mu, float mv, PicpAcc& a) {
+__device__ __forceinline__ f2_t f2_sel(bool c0, bool c1, f2_t a, f2_t b) {
+  float a0, a1, b0, b1;
+  f2_unpack(a, a0, a1);
+  f2_unpack(b, b0, b1);
+  return f2_pack(c0 ? a0 : b0, c1 ? a1 : b1);
+}
+
+template <bool PINHOLE, bool KEEP>
+__device__ __forceinline__ void picp_point2(const PicpParams& p, const PicpConsts& c, f2_t wx,
+                                            f2_t wy, f2_t wz, f2_t mu, f2_t mv, bool have1,
+                                            PicpAcc& a) {
+  const float* T = c.T;
+  const f2_t neg1 = f2_bc(-1.f);
   // camera_point = world_in_camera * world_point  (camera.h:27, picp_solver.cpp:38)
-  float px = fmaf(T[6], wz, fmaf(T[3], wy, fmaf(T[0], wx, T[9])));
-  float py = fmaf(T[7], wz, fmaf(T[4], wy, fmaf(T[1], wx, T[10])));
-  float pz = fmaf(T[8], wz, fmaf(T[5], wy, fmaf(T[2], wx, T[11])));
-  bool valid = !(pz > p.z_far || pz < p.z_near);  // camera.h:28
+  f2_t px = f2_fma(f2_bc(T[6]), wz, f2_fma(f2_bc(T[3]), wy, f2_fma(f2_bc(T[0]), wx, f2_bc(T[9]))));
+  f2_t py = f2_fma(f2_bc(T[7]), wz, f2_fma(f2_bc(T[4]), wy, f2_fma(f2_bc(T[1]), wx, f2_bc(T[10]))));
+  f2_t pz = f2_fma(f2_bc(T[8]), wz, f2_fma(f2_bc(T[5]), wy, f2_fma(f2_bc(T[2]), wx, f2_bc(T[11]))));
+  float pz0, pz1;
+  f2_unpack(pz, pz0, pz1);
+  bool valid0 = !(pz0 > p.z_far || pz0 < p.z_near);  // camera.h:28
+  bool valid1 = have1 && !(pz1 > p.z_far || pz1 < p.z_near);
   // a rejected point continues as the harmless dummy (0,0,1) so that nothing overflows
-  px = valid ? px : 0.f;
-  py = valid ? py : 0.f;
-  pz = valid ? pz : 1.f;
+  px = f2_sel(valid0, valid1, px, 0ull);
+  py = f2_sel(valid0, valid1, py, 0ull);
+  pz = f2_sel(valid0, valid1, pz, f2_bc(1.f));
   // phom = K * camera_point  (camera.h:30, picp_solver.cpp:43)
-  float hx, hy, hz;
+  f2_t hx, hy, hz;
   if (PINHOLE) {
-    hx = fmaf(p.K[6], pz, p.K[0] * px);
-    hy = fmaf(p.K[7], pz, p.K[4] * py);
+    hx = f2_fma(f2_bc(p.K[6]), pz, f2_mul(f2_bc(p.K[0]), px));
+    hy = f2_fma(f2_bc(p.K[7]), pz, f2_mul(f2_bc(p.K[4]), py));
     hz = pz;
   } else {
-    hx = fmaf(p.K[6], pz, fmaf(p.K[3], py, p.K[0] * px));
-    hy = fmaf(p.K[7], pz, fmaf(p.K[4], py, p.K[1] * px));
-    hz = fmaf(p.K[8], pz, fmaf(p.K[5], py, p.K[2] * px));
+    hx = f2_fma(f2_bc(p.K[6]), pz, f2_fma(f2_bc(p.K[3]), py, f2_mul(f2_bc(p.K[0]), px)));
+    hy = f2_fma(f2_bc(p.K[7]), pz, f2_fma(f2_bc(p.K[4]), py, f2_mul(f2_bc(p.K[1]), px)));
+    hz = f2_fma(f2_bc(p.K[8]), pz, f2_fma(f2_bc(p.K[5]), py, f2_mul(f2_bc(p.K[2]), px)));
   }
-  const float iz = picp_rcp(hz);  // camera.h:31 / picp_solver.cpp:44
-  const float u = hx * iz, v = hy * iz;
-  valid = valid && !(u < 0.f || u > p.max_u) && !(v < 0.f || v > p.max_v);  // camera.h:32-35
-  const float e0 = u - mu, e1 = v - mv;                                      // :35
+  const f2_t iz = picp_rcp2(hz);  // camera.h:31 / picp_solver.cpp:44
+  const f2_t u = f2_mul(hx, iz), v = f2_mul(hy, iz);
+  float u0, u1, v0, v1;
+  f2_unpack(u, u0, u1);
+  f2_unpack(v, v0, v1);
+  valid0 = valid0 && !(u0 < 0.f || u0 > p.max_u) && !(v0 < 0.f || v0 > p.max_v);  // camera.h:32-35
+  valid1 = valid1 && !(u1 < 0.f || u1 > p.max_u) && !(v1 < 0.f || v1 > p.max_v);
+  const f2_t e0 = f2_fma(mu, neg1, u), e1 = f2_fma(mv, neg1, v);  // e = proj - meas (:35)
   // A = Jp*K with Jp = [iz 0 -hx*iz^2; 0 iz -hy*iz^2]  ==  iz * (K_row{0,1} - {u,v} * K_row2)
   // J = [A | A*skew(-pc)],  skew(-pc) = [0 pz -py; -pz 0 px; py -px 0]   (:39-41, utils.h:96-102)
-  float J0[6], J1[6];
+  const f2_t npx = f2_mul(px, neg1), npy = f2_mul(py, neg1), npz = f2_mul(pz, neg1);
+  f2_t J0[6], J1[6];
   if (PINHOLE) {
-    J0[0] = iz * p.K[0];
-    J0[1] = 0.f;
-    J0[2] = iz * (p.K[6] - u);
-    J1[0] = 0.f;
-    J1[1] = iz * p.K[4];
-    J1[2] = iz * (p.K[7] - v);
-    J0[3] = J0[2] * py;
-    J0[4] = fmaf(J0[0], pz, -J0[2] * px);
-    J0[5] = -(J0[0] * py);
-    J1[3] = fmaf(J1[2], py, -J1[1] * pz);
-    J1[4] = -(J1[2] * px);
-    J1[5] = J1[1] * px;
+    J0[0] = f2_mul(iz, f2_bc(p.K[0]));
+    J0[1] = 0ull;
+    J0[2] = f2_mul(iz, f2_fma(u, neg1, f2_bc(p.K[6])));
+    J1[0] = 0ull;
+    J1[1] = f2_mul(iz, f2_bc(p.K[4]));
+    J1[2] = f2_mul(iz, f2_fma(v, neg1, f2_bc(p.K[7])));
+    J0[3] = f2_mul(J0[2], py);
+    J0[4] = f2_fma(J0[0], pz, f2_mul(J0[2], npx));
+    J0[5] = f2_mul(J0[0], npy);
+    J1[3] = f2_fma(J1[2], py, f2_mul(J1[1], npz));
+    J1[4] = f2_mul(J1[2], npx);
+    J1[5] = f2_mul(J1[1], px);
   } else {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      J0[j] = iz * fmaf(-u, p.K[j * 3 + 2], p.K[j * 3 + 0]);
-      J1[j] = iz * fmaf(-v, p.K[j * 3 + 2], p.K[j * 3 + 1]);
+      J0[j] = f2_mul(iz, f2_fma(u, f2_bc(-p.K[j * 3 + 2]), f2_bc(p.K[j * 3 + 0])));
+      J1[j] = f2_mul(iz, f2_fma(v, f2_bc(-p.K[j * 3 + 2]), f2_bc(p.K[j * 3 + 1])));
     }
-    J0[3] = fmaf(J0[2], py, -J0[1] * pz);
-    J0[4] = fmaf(J0[0], pz, -J0[2] * px);
-    J0[5] = fmaf(J0[1], px, -J0[0] * py);
-    J1[3] = fmaf(J1[2], py, -J1[1] * pz);
-    J1[4] = fmaf(J1[0], pz, -J1[2] * px);
-    J1[5] = fmaf(J1[1], px, -J1[0] * py);
+    J0[3] = f2_fma(J0[2], py, f2_mul(J0[1], npz));
+    J0[4] = f2_fma(J0[0], pz, f2_mul(J0[2], npx));
+    J0[5] = f2_fma(J0[1], px, f2_mul(J0[0], npy));
+    J1[3] = f2_fma(J1[2], py, f2_mul(J1[1], npz));
+    J1[4] = f2_fma(J1[0], pz, f2_mul(J1[2], npx));
+    J1[5] = f2_fma(J1[1], px, f2_mul(J1[0], npy));
   }
-  const float chi = fmaf(e1, e1, e0 * e0);  // :75
-  const bool outlier = chi > p.thr;         // :78
-  float lambda = outlier ? 0.f : 1.f;       // dropped outliers weigh 0 (:90)
-  if (outlier && p.keep_outliers) lambda = sqrtf(p.thr / chi);  // :80
-  const float w = valid ? lambda : 0.f;
-  a.chi_out += (valid && outlier) ? chi : 0.f;   // :82
-  a.chi_in += (valid && !outlier) ? chi : 0.f;   // :86
-  a.n_in += (valid && !outlier) ? 1 : 0;         // :87
+  const f2_t chi = f2_fma(e1, e1, f2_mul(e0, e0));  // :75
+  float chi0, chi1;
+  f2_unpack(chi, chi0, chi1);
+  const bool out0 = chi0 > p.thr, out1 = chi1 > p.thr;  // :78
+  float l0 = out0 ? 0.f : 1.f, l1 = out1 ? 0.f : 1.f;    // dropped outliers weigh 0 (:90)
+  if (KEEP) {                                            // :80
+    l0 = out0 ? sqrtf(p.thr / chi0) : 1.f;
+    l1 = out1 ? sqrtf(p.thr / chi1) : 1.f;
+  }
+  const f2_t w = f2_pack(valid0 ? l0 : 0.f, valid1 ? l1 : 0.f);
+  a.chi_out = f2_add(a.chi_out, f2_sel(valid0 && out0, valid1 && out1, chi, 0ull));    // :82
+  a.chi_in = f2_add(a.chi_in, f2_sel(valid0 && !out0, valid1 && !out1, chi, 0ull));   // :86
+  a.n_in += ((valid0 && !out0) ? 1 : 0) + ((valid1 && !out1) ? 1 : 0);                 // :87
   // H += J^T J * lambda ; b += J^T e * lambda   (:92-93)
-  float L0[6], L1[6];
+  f2_t L0[6], L1[6];
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    L0[j] = J0[j] * w;
-    L1[j] = J1[j] * w;
+    L0[j] = (PINHOLE && j == 1) ? 0ull : f2_mul(J0[j], w);
+    L1[j] = (PINHOLE && j == 0) ? 0ull : f2_mul(J1[j], w);
   }
   int k = 0;
 #pragma unroll
   for (int r = 0; r < 6; ++r) {
 #pragma unroll
-    for (int c = r; c < 6; ++c) {
-      const bool z0 = PINHOLE && (r == 1 || c == 1);  // J0[1] == 0
-      const bool z1 = PINHOLE && (r == 0 || c == 0);  // J1[0] == 0
-      float hk = a.h[k];
-      if (!z1) hk = fmaf(L1[r], J1[c], hk);
-      if (!z0) hk = fmaf(L0[r], J0[c], hk);
+    for (int cc = r; cc < 6; ++cc) {
+      const bool z0 = PINHOLE && (r == 1 || cc == 1);  // J0[1] == 0
+      const bool z1 = PINHOLE && (r == 0 || cc == 0);  // J1[0] == 0
+      f2_t hk = a.h[k];
+      if (!z1) hk = f2_fma(L1[r], J1[cc], hk);
+      if (!z0) hk = f2_fma(L0[r], J0[cc], hk);
       a.h[k] = hk;
       ++k;
     }
-    float bk = a.b[r];
-    if (!(PINHOLE && r == 0)) bk = fmaf(L1[r], e1, bk);
-    if (!(PINHOLE && r == 1)) bk = fmaf(L0[r], e0, bk);
+    f2_t bk = a.b[r];
+    if (!(PINHOLE && r == 0)) bk = f2_fma(L1[r], e1, bk);
+    if (!(PINHOLE && r == 1)) bk = f2_fma(L0[r], e0, bk);
     a.b[r] = bk;
   }
 }
@@ -256,31 +298,32 @@ __device__ __forceinline__ void picp_gather(const PicpParams& p, const int2 (&pr
   }
 }
 
-template <bool PINHOLE>
-__global__ void __launch_bounds__(PICP_THREADS, 2) picp_round_kernel(const PicpParams p) {
+template <bool PINHOLE, bool KEEP>
+__global__ void __launch_bounds__(PICP_THREADS, 1) picp_round_kernel(const PicpParams p) {
   __shared__ float s_red[PICP_THREADS / 32][PICP_NACC];
   __shared__ bool s_last;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
 
-  float T[12];
+  PicpConsts c;
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int i = 0; i < 3; ++i) T[j * 3 + i] = p.st->s.T[j * 4 + i];
+    for (int i = 0; i < 3; ++i) c.T[j * 3 + i] = p.st->s.T[j * 4 + i];
 
   PicpAcc a;
 #pragma unroll
-  for (int i = 0; i < 21; ++i) a.h[i] = 0.f;
+  for (int i = 0; i < 21; ++i) a.h[i] = 0ull;
 #pragma unroll
-  for (int i = 0; i < 6; ++i) a.b[i] = 0.f;
-  a.chi_in = a.chi_out = 0.f;
+  for (int i = 0; i < 6; ++i) a.b[i] = 0ull;
+  a.chi_in = a.chi_out = 0ull;
   a.n_in = 0;
 
   // ---- software-pipelined stream over the correspondences --------------------------------------
   // thread t owns items t, t+stride, t+2*stride, ...; they are consumed in batches of PICP_UNROLL.
   // While batch k is being linearised, the point gathers of batch k+1 and the pair loads of batch
-  // k+2 are in flight, so every warp always has independent loads outstanding.
+  // k+2 are in flight, so every warp always has independent loads outstanding.  The two batch
+  // buffers swap roles every half-iteration (no register copies).
   const int n = (int)p.n_pairs;
   const int stride = (int)gridDim.x * PICP_THREADS;
   const int i0 = (int)blockIdx.x * PICP_THREADS + tid;
@@ -290,37 +333,51 @@ __global__ void __launch_bounds__(PICP_THREADS, 2) picp_round_kernel(const PicpP
   const int64_t bstep = (int64_t)stride * PICP_UNROLL;
   {
     int2 pr_next[PICP_UNROLL];
-    PicpBatch cur, nxt;
+    PicpBatch A, B;
     if (nb > 0) {
       picp_load_pairs(pp, stride, pr_next);
-      picp_gather(p, pr_next, cur);
+      picp_gather(p, pr_next, A);
     }
     if (nb > 1) picp_load_pairs(pp + bstep, stride, pr_next);
-    for (int bi = 0; bi < nb; ++bi) {
-      if (bi + 1 < nb) picp_gather(p, pr_next, nxt);                               // batch k+1 points
+    auto stage = [&](const PicpBatch& use, PicpBatch& fill, int bi) {
+      if (bi + 1 < nb) picp_gather(p, pr_next, fill);                                     // batch k+1 points
       if (bi + 2 < nb) picp_load_pairs(pp + (int64_t)(bi + 2) * bstep, stride, pr_next);  // k+2 pairs
 #pragma unroll
-      for (int u = 0; u < PICP_UNROLL; ++u)
-        picp_point<PINHOLE>(p, T, cur.w[u][0], cur.w[u][1], cur.w[u][2], cur.m[u].x, cur.m[u].y, a);
-      cur = nxt;
+      for (int u = 0; u < PICP_UNROLL; u += 2)
+        picp_point2<PINHOLE, KEEP>(p, c, f2_pack(use.w[u][0], use.w[u + 1][0]),
+                                   f2_pack(use.w[u][1], use.w[u + 1][1]),
+                                   f2_pack(use.w[u][2], use.w[u + 1][2]),
+                                   f2_pack(use.m[u].x, use.m[u + 1].x),
+                                   f2_pack(use.m[u].y, use.m[u + 1].y), true, a);
+    };
+    for (int bi = 0; bi < nb; bi += 2) {
+      stage(A, B, bi);
+      if (bi + 1 < nb) stage(B, A, bi + 1);
     }
-    // the (< PICP_UNROLL) leftover items of this thread
-    for (int m = nb * PICP_UNROLL; m < mine; ++m) {
-      const int2 pr = __ldg(pp + (int64_t)m * stride);
-      const float* wp = p.world + 3 * (int64_t)pr.y;
-      const float2 im = __ldg(reinterpret_cast<const float2*>(p.image) + pr.x);
-      picp_point<PINHOLE>(p, T, __ldg(wp), __ldg(wp + 1), __ldg(wp + 2), im.x, im.y, a);
+    // the (< PICP_UNROLL) leftover items of this thread, again two at a time
+    for (int m = nb * PICP_UNROLL; m < mine; m += 2) {
+      const bool have1 = m + 1 < mine;
+      const int2 pr0 = __ldg(pp + (int64_t)m * stride);
+      const int2 pr1 = have1 ? __ldg(pp + (int64_t)(m + 1) * stride) : pr0;
+      const float* w0 = p.world + 3 * (int64_t)pr0.y;
+      const float* w1 = p.world + 3 * (int64_t)pr1.y;
+      const float2 m0 = __ldg(reinterpret_cast<const float2*>(p.image) + pr0.x);
+      const float2 m1 = __ldg(reinterpret_cast<const float2*>(p.image) + pr1.x);
+      picp_point2<PINHOLE, KEEP>(p, c, f2_pack(__ldg(w0), __ldg(w1)),
+                                 f2_pack(__ldg(w0 + 1), __ldg(w1 + 1)),
+                                 f2_pack(__ldg(w0 + 2), __ldg(w1 + 2)), f2_pack(m0.x, m1.x),
+                                 f2_pack(m0.y, m1.y), have1, a);
     }
   }
 
   // ---- block reduction: shuffle within the warp, fixed-order sum across warps ----------------
   float v[PICP_NACC];
 #pragma unroll
-  for (int i = 0; i < 21; ++i) v[i] = a.h[i];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) v[21 + i] = a.b[i];
-  v[27] = a.chi_in;
-  v[28] = a.chi_out;
+  for (int i = 0; i < 29; ++i) {  // the two point slots
+    float lo, hi;
+    f2_unpack(i < 21 ? a.h[i] : (i < 27 ? a.b[i - 21] : (i == 27 ? a.chi_in : a.chi_out)), lo, hi);
+    v[i] = lo + hi;
+  }
   int n_in = a.n_in;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -479,7 +536,7 @@ static int picp_fill_params(vo_picp_s* h, int keep_outliers, PicpParams* p) {
 static int picp_pick_grid(vo_picp_s* h) {
   const int sms = num_sms(h->device);
   int per_sm = 2;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, picp_round_kernel<false>, PICP_THREADS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, picp_round_kernel<false, true>, PICP_THREADS, 0);
   if (per_sm < 1) per_sm = 1;
   const int64_t full = (int64_t)sms * per_sm;
   const int64_t need =
@@ -655,7 +712,8 @@ int vo_picp_compute(vo_picp_t h, int keep_outliers, int rounds) {
   const float* K = h->cam.K;
   const bool pinhole = !h->force_general && K[1] == 0.f && K[2] == 0.f && K[3] == 0.f &&
                        K[5] == 0.f && K[8] == 1.f;
-  auto kernel = pinhole ? picp_round_kernel<true> : picp_round_kernel<false>;
+  auto kernel = pinhole ? (p.keep_outliers ? picp_round_kernel<true, true> : picp_round_kernel<true, false>)
+                        : (p.keep_outliers ? picp_round_kernel<false, true> : picp_round_kernel<false, false>);
   if (rounds < 4) {
     for (int r = 0; r < rounds; ++r) {
       kernel<<<grid, PICP_THREADS, 0, h->stream>>>(p);
