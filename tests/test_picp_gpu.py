@@ -75,6 +75,57 @@ def test_compute_many_rounds_equals_one_round_loop(vo, synth):
     b.close()
 
 
+def test_compute_graph_path_equals_launch_loop_streaming(vo, synth, monkeypatch):
+    """The same check on the streaming kernel (CUDA-graph replay vs one launch per round)."""
+    monkeypatch.setenv("VO_PICP_FORCE_STREAM", "1")
+    pr = synth.picp_problem(30000, seed=23)
+    cam = vo.Camera(pr["rows"], pr["cols"], pr["z_near"], pr["z_far"], pr["K"], np.eye(4))
+    a, b = vo.PICPSolver(0), vo.PICPSolver(0)
+    for s in (a, b):
+        s.setKernelThreshold(10000.0)
+        s.init(cam, pr["world"], pr["image"])
+    for _ in range(6):
+        a.oneRound(pr["pairs"], False)
+    b.set_correspondences(pr["pairs"])
+    b.compute(False, 6)
+    sa, sb = a.state(), b.state()
+    assert list(sa.T) == list(sb.T) and list(sa.H) == list(sb.H)
+    a.close()
+    b.close()
+
+
+@pytest.mark.parametrize("n_corr", [1, 2, 3, 77, 1024, 1025, 2049, 4097, 8193, 30001, 65536])
+@pytest.mark.parametrize("keep", [False, True])
+def test_resident_kernel_matches_streaming_kernel(vo, synth, monkeypatch, n_corr, keep):
+    """n <= 65536 correspondences run every round inside one resident thread-block cluster of 1, 2,
+    4 or 8 CTAs (shared-memory copy of the points, DSMEM reduction); VO_PICP_FORCE_STREAM=1 sends
+    the same problem through the streaming kernel.  The two differ only in summation order."""
+    pr = synth.picp_problem(70000, seed=29, outlier_frac=0.05)
+    pairs = pr["pairs"][:n_corr]
+    assert len(pairs) == n_corr
+    cam = vo.Camera(pr["rows"], pr["cols"], pr["z_near"], pr["z_far"], pr["K"], np.eye(4))
+    res = []
+    for force in ("0", "1"):
+        monkeypatch.setenv("VO_PICP_FORCE_STREAM", force)
+        s = vo.PICPSolver(0)
+        s.setKernelThreshold(2000.0)
+        s.init(cam, pr["world"], pr["image"])
+        s.set_correspondences(pairs)
+        s.compute(keep, 1)
+        st1 = s.state()
+        s.compute(keep, 7)
+        st = s.state()
+        res.append((np.array(st1.H[:]), np.array(st1.b[:]), st1.num_inliers, st1.chi_inliers,
+                    st1.chi_outliers, np.array(st.T[:]), st.rounds_done))
+        s.close()
+    r, g = res
+    assert r[2] == g[2] and r[6] == g[6] == 8
+    assert rel(r[0], g[0]) <= 2e-6 and rel(r[1], g[1]) <= 1e-5
+    assert rel(r[3], g[3]) <= 1e-5 and abs(r[4] - g[4]) <= 1e-5 * max(abs(g[4]), 1.0)
+    if n_corr >= 77:  # with a handful of points the system is singular: poses are not comparable
+        assert rel(r[5], g[5]) <= 1e-4
+
+
 @pytest.mark.parametrize("keep", [False, True])
 def test_outliers_and_robust_kernel(vo, oracle, synth, keep):
     pr = synth.picp_problem(4000, seed=23, outlier_frac=0.25)

@@ -25,6 +25,8 @@
 #include <map>
 #include <tuple>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "linalg.cuh"
 
@@ -276,26 +278,52 @@ __device__ __forceinline__ void picp_point2(const PicpParams& p, const PicpConst
   }
 }
 
-struct PicpBatch {
-  float w[PICP_UNROLL][3];
-  float2 m[PICP_UNROLL];
-};
+// ---- per-thread asynchronous staging ring (cp.async, SASS LDGSTS) ---------------------------------
+// Registers cannot hold enough loads in flight: 6.5 TB/s x ~1.5 us of loaded HBM latency is ~10 MB,
+// i.e. ~70 KB per SM, while the accumulators already take 58 registers per thread.  So the
+// operands travel global -> shared memory asynchronously, PICP_DEPTH batches ahead of the
+// arithmetic, in a ring that is PRIVATE to each thread (a thread only ever reads back what it
+// copied itself: no block-wide barrier, only cp.async.wait_group).  Two dependent streams:
+//   P(b): the int2 pairs of batch b          (coalesced 8-byte copies)
+//   G(b): the 5 floats gathered through them (4-byte copies: a Vector3f is only 4-byte aligned)
+// In iteration b the thread waits for the group that carries G(b) and P(b+DEPTH), issues
+// G(b+DEPTH) (reading P(b+DEPTH) back from shared memory) and P(b+2*DEPTH), commits them as one
+// group, and then linearises batch b.  Slots are laid out so that every access of a warp is
+// conflict-free, and so that the two points a thread pairs up in packed-FP32 lanes sit in one
+// 8-byte word: one LDS.64 yields a ready-made packed operand.
+constexpr int PICP_DEPTH = 3;
+constexpr int PICP_SLOTS = PICP_DEPTH + 1;
+constexpr int PICP_PTS_WORDS = PICP_SLOTS * (PICP_UNROLL / 2) * 5;  // 8-byte words per thread
+constexpr int PICP_PRS_WORDS = PICP_SLOTS * PICP_UNROLL;
+constexpr size_t PICP_SMEM_BYTES = (size_t)(PICP_PTS_WORDS + PICP_PRS_WORDS) * PICP_THREADS * 8;
 
-__device__ __forceinline__ void picp_load_pairs(const int2* __restrict__ pp, int stride,
-                                                int2 (&pr)[PICP_UNROLL]) {
-#pragma unroll
-  for (int u = 0; u < PICP_UNROLL; ++u) pr[u] = __ldg(pp + (int64_t)u * stride);
+__device__ __forceinline__ void cp_async4(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void picp_gather(const PicpParams& p, const int2 (&pr)[PICP_UNROLL],
-                                            PicpBatch& b) {
-#pragma unroll
-  for (int u = 0; u < PICP_UNROLL; ++u) {
-    const float* wp = p.world + 3 * (int64_t)pr[u].y;  // .second -> world (:67)
-    b.w[u][0] = __ldg(wp);
-    b.w[u][1] = __ldg(wp + 1);
-    b.w[u][2] = __ldg(wp + 2);
-    b.m[u] = __ldg(reinterpret_cast<const float2*>(p.image) + pr[u].x);  // .first -> image (:66)
-  }
+__device__ __forceinline__ void cp_async8(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ f2_t lds_f2(uint32_t addr) {
+  f2_t v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ int2 lds_int2(uint32_t addr) {
+  int2 v;
+  asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+// byte offsets inside the ring, relative to the thread's own base (tid * 8)
+__device__ __forceinline__ constexpr uint32_t picp_pts_off(int slot, int pair, int comp) {
+  return (uint32_t)(((slot * (PICP_UNROLL / 2) + pair) * 5 + comp) * PICP_THREADS * 8);
+}
+__device__ __forceinline__ constexpr uint32_t picp_prs_off(int slot, int u) {
+  return (uint32_t)((PICP_PTS_WORDS + slot * PICP_UNROLL + u) * PICP_THREADS * 8);
 }
 
 template <bool PINHOLE, bool KEEP>
@@ -319,41 +347,71 @@ __global__ void __launch_bounds__(PICP_THREADS, 1) picp_round_kernel(const PicpP
   a.chi_in = a.chi_out = 0ull;
   a.n_in = 0;
 
-  // ---- software-pipelined stream over the correspondences --------------------------------------
+  // ---- asynchronous stream over the correspondences ------------------------------------------
   // thread t owns items t, t+stride, t+2*stride, ...; they are consumed in batches of PICP_UNROLL.
-  // While batch k is being linearised, the point gathers of batch k+1 and the pair loads of batch
-  // k+2 are in flight, so every warp always has independent loads outstanding.  The two batch
-  // buffers swap roles every half-iteration (no register copies).
   const int n = (int)p.n_pairs;
   const int stride = (int)gridDim.x * PICP_THREADS;
   const int i0 = (int)blockIdx.x * PICP_THREADS + tid;
   const int mine = i0 < n ? (n - i0 + stride - 1) / stride : 0;  // items of this thread
   const int nb = mine / PICP_UNROLL;                             // full batches
   const int2* pp = p.pairs + i0;
-  const int64_t bstep = (int64_t)stride * PICP_UNROLL;
   {
-    int2 pr_next[PICP_UNROLL];
-    PicpBatch A, B;
-    if (nb > 0) {
-      picp_load_pairs(pp, stride, pr_next);
-      picp_gather(p, pr_next, A);
-    }
-    if (nb > 1) picp_load_pairs(pp + bstep, stride, pr_next);
-    auto stage = [&](const PicpBatch& use, PicpBatch& fill, int bi) {
-      if (bi + 1 < nb) picp_gather(p, pr_next, fill);                                     // batch k+1 points
-      if (bi + 2 < nb) picp_load_pairs(pp + (int64_t)(bi + 2) * bstep, stride, pr_next);  // k+2 pairs
+    extern __shared__ __align__(16) unsigned char picp_ring[];
+    const uint32_t ring = smem_u32(picp_ring) + (uint32_t)tid * 8u;
+    auto issue_pairs = [&](int b, int slot) {  // P(b)
+      if (b < nb) {
 #pragma unroll
-      for (int u = 0; u < PICP_UNROLL; u += 2)
-        picp_point2<PINHOLE, KEEP>(p, c, f2_pack(use.w[u][0], use.w[u + 1][0]),
-                                   f2_pack(use.w[u][1], use.w[u + 1][1]),
-                                   f2_pack(use.w[u][2], use.w[u + 1][2]),
-                                   f2_pack(use.m[u].x, use.m[u + 1].x),
-                                   f2_pack(use.m[u].y, use.m[u + 1].y), true, a);
+        for (int u = 0; u < PICP_UNROLL; ++u)
+          cp_async8(ring + picp_prs_off(slot, u), pp + (int64_t)(b * PICP_UNROLL + u) * stride);
+      }
     };
-    for (int bi = 0; bi < nb; bi += 2) {
-      stage(A, B, bi);
-      if (bi + 1 < nb) stage(B, A, bi + 1);
+    auto issue_gathers = [&](int b, int slot) {  // G(b); P(b) has landed
+      if (b < nb) {
+#pragma unroll
+        for (int u = 0; u < PICP_UNROLL; ++u) {
+          const int2 pr = lds_int2(ring + picp_prs_off(slot, u));
+          const float* wp = p.world + 3 * (int64_t)pr.y;  // .second -> world (:67)
+          const float* ip = p.image + 2 * (int64_t)pr.x;  // .first -> image (:66)
+          const uint32_t lane = (uint32_t)(u & 1) * 4u;   // which half of the packed pair
+          cp_async4(ring + picp_pts_off(slot, u >> 1, 0) + lane, wp);
+          cp_async4(ring + picp_pts_off(slot, u >> 1, 1) + lane, wp + 1);
+          cp_async4(ring + picp_pts_off(slot, u >> 1, 2) + lane, wp + 2);
+          cp_async4(ring + picp_pts_off(slot, u >> 1, 3) + lane, ip);
+          cp_async4(ring + picp_pts_off(slot, u >> 1, 4) + lane, ip + 1);
+        }
+      }
+    };
+    // prologue: P(0..DEPTH-1); then G(j) + P(j+DEPTH) as the groups the main loop expects
+#pragma unroll
+    for (int j = 0; j < PICP_DEPTH; ++j) issue_pairs(j, j % PICP_SLOTS);
+    cp_async_commit();
+    cp_async_wait<0>();
+#pragma unroll
+    for (int j = 0; j < PICP_DEPTH; ++j) {
+      issue_gathers(j, j % PICP_SLOTS);
+      issue_pairs(j + PICP_DEPTH, (j + PICP_DEPTH) % PICP_SLOTS);
+      cp_async_commit();
     }
+    for (int b0 = 0; b0 < nb; b0 += PICP_SLOTS) {
+#pragma unroll
+      for (int sl = 0; sl < PICP_SLOTS; ++sl) {
+        const int b = b0 + sl;
+        if (b < nb) {
+          cp_async_wait<PICP_DEPTH - 1>();  // G(b) and P(b+DEPTH) have landed
+          issue_gathers(b + PICP_DEPTH, (sl + PICP_DEPTH) % PICP_SLOTS);
+          issue_pairs(b + 2 * PICP_DEPTH, (sl + 2 * PICP_DEPTH) % PICP_SLOTS);
+          cp_async_commit();
+#pragma unroll
+          for (int pi = 0; pi < PICP_UNROLL / 2; ++pi)
+            picp_point2<PINHOLE, KEEP>(p, c, lds_f2(ring + picp_pts_off(sl, pi, 0)),
+                                       lds_f2(ring + picp_pts_off(sl, pi, 1)),
+                                       lds_f2(ring + picp_pts_off(sl, pi, 2)),
+                                       lds_f2(ring + picp_pts_off(sl, pi, 3)),
+                                       lds_f2(ring + picp_pts_off(sl, pi, 4)), true, a);
+        }
+      }
+    }
+    cp_async_wait<0>();
     // the (< PICP_UNROLL) leftover items of this thread, again two at a time
     for (int m = nb * PICP_UNROLL; m < mine; m += 2) {
       const bool have1 = m + 1 < mine;
@@ -458,6 +516,212 @@ __global__ void __launch_bounds__(PICP_THREADS, 1) picp_round_kernel(const PicpP
   }
 }
 
+// ---- resident kernel: all rounds of a frame-sized problem in ONE launch ---------------------------
+// The streaming kernel pays a fixed ~7 us per round (launch, last-block hand-off, one-thread solve
+// with global round-trips), which dwarfs the arithmetic when a frame has a few thousand
+// correspondences — the size of every real VO frame (vo_complete.cpp:164-166 runs 100 rounds on
+// ~100 points; the synthetic sequences of config 5 on ~7e3).  Up to PICP_RES_MAX correspondences
+// are therefore gathered ONCE into the shared memory of a thread-block cluster (<= 8 CTAs, each
+// holding a contiguous slice already paired up for the packed-FP32 lanes), and the cluster
+// iterates all the rounds without leaving the SMs:
+//   linearise the slice from shared memory -> transposed warp reduction (31 shuffles for 32
+//   sums) -> per-CTA partial -> pushed into EVERY CTA's shared memory through DSMEM -> one
+//   cluster barrier -> every CTA adds the partials in rank order and its thread 0 solves the 6x6
+//   system and updates its own copy of the pose (identical instruction stream => identical bits in
+//   every CTA, so no second barrier and no broadcast).
+// Global memory is touched at the start (gather) and at the end (state write-back) only.
+constexpr int PICP_RES_THREADS = 512;
+constexpr int PICP_RES_CLUSTER = 8;                       // portable maximum
+constexpr int PICP_RES_SLOTS = 4096;                      // packed two-point slots per CTA
+constexpr int PICP_RES_MAX = PICP_RES_CLUSTER * PICP_RES_SLOTS * 2;  // 65536 correspondences
+constexpr size_t PICP_RES_SMEM = (size_t)5 * PICP_RES_SLOTS * 8;
+
+// lane l ends up with the sum over the warp of v[l] (v has 32 entries); 31 shuffles
+__device__ __forceinline__ float warp_reduce_transposed(float (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+// oneRound's tail (picp_solver.cpp:102-110) on register/shared state: tot = the 30 sums, T = the
+// 3x4 pose (column-major 3x3 then translation), updated in place.  Returns false when the round
+// is skipped (too few inliers).  Same operation sequence as picp_solve_and_update.
+__device__ __noinline__ bool picp_solve_local(const PicpParams& p, const float* tot, float* T,
+                                              float* H_out, float* b_out) {
+  float H[36], b[6];
+  {
+    int k = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = r; c < 6; ++c) {
+        H[c * 6 + r] = tot[k];
+        H[r * 6 + c] = tot[k];
+        ++k;
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) b[i] = tot[21 + i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) H[i * 6 + i] += p.damping;  // :102
+#pragma unroll
+  for (int i = 0; i < 36; ++i) H_out[i] = H[i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) b_out[i] = b[i];
+  if (__float_as_int(tot[29]) < p.min_inliers) return false;  // :103-107
+  float nb[6], dx[6];
+  float* A = H;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) nb[i] = -b[i];
+  ldlt_solve_dev<6>(A, nb, dx);  // :109
+  const float sx = sinf(dx[3]), cx = cosf(dx[3]);
+  const float sy = sinf(dx[4]), cy = cosf(dx[4]);
+  const float sz = sinf(dx[5]), cz = cosf(dx[5]);
+  const float Rx[9] = {1, 0, 0, 0, cx, sx, 0, -sx, cx};
+  const float Ry[9] = {cy, 0, -sy, 0, 1, 0, sy, 0, cy};
+  const float Rz[9] = {cz, sz, 0, -sz, cz, 0, 0, 0, 1};
+  float Rxy[9], R[9];
+  mat3_mul_dev(Rx, Ry, Rxy);
+  mat3_mul_dev(Rxy, Rz, R);
+  float Tn[12];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float acc = (R[i] * T[j * 3] + R[3 + i] * T[j * 3 + 1]) + R[6 + i] * T[j * 3 + 2];
+      if (j == 3) acc += dx[i];
+      Tn[j * 3 + i] = acc;
+    }
+#pragma unroll
+  for (int i = 0; i < 12; ++i) T[i] = Tn[i];
+  return true;
+}
+
+template <bool PINHOLE, bool KEEP>
+__global__ void __launch_bounds__(PICP_RES_THREADS, 1)
+picp_resident_kernel(const PicpParams p, const int rounds) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int csize = (int)cluster.num_blocks();
+  const int rank = (int)cluster.block_rank();
+  extern __shared__ __align__(16) unsigned char picp_ring[];
+  f2_t* pts = reinterpret_cast<f2_t*>(picp_ring);  // [5][PICP_RES_SLOTS]
+  constexpr int W = PICP_RES_THREADS / 32;
+  __shared__ float s_red[W][32];
+  __shared__ float s_part[2][PICP_RES_CLUSTER][32];  // [round parity][source CTA][sum]
+  __shared__ float s_T[12];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int n = (int)p.n_pairs;
+  const int nslots = (n + 1) >> 1;
+  const int per = (nslots + csize - 1) / csize;  // <= PICP_RES_SLOTS (host guarantees)
+  const int q0 = rank * per;
+  const int mine = max(0, min(per, nslots - q0));
+
+  // gather once: global slot q holds correspondences 2q (lane 0) and 2q+1 (lane 1)
+  for (int ql = tid; ql < mine; ql += PICP_RES_THREADS) {
+    const int q = q0 + ql;
+    const bool have1 = 2 * q + 1 < n;
+    const int2 pr0 = __ldg(p.pairs + 2 * q);
+    const int2 pr1 = have1 ? __ldg(p.pairs + 2 * q + 1) : pr0;
+    const float* w0 = p.world + 3 * (int64_t)pr0.y;  // .second -> world (:67)
+    const float* w1 = p.world + 3 * (int64_t)pr1.y;
+    const float2 m0 = __ldg(reinterpret_cast<const float2*>(p.image) + pr0.x);  // .first -> image
+    const float2 m1 = __ldg(reinterpret_cast<const float2*>(p.image) + pr1.x);
+    pts[0 * PICP_RES_SLOTS + ql] = f2_pack(__ldg(w0), __ldg(w1));
+    pts[1 * PICP_RES_SLOTS + ql] = f2_pack(__ldg(w0 + 1), __ldg(w1 + 1));
+    pts[2 * PICP_RES_SLOTS + ql] = f2_pack(__ldg(w0 + 2), __ldg(w1 + 2));
+    pts[3 * PICP_RES_SLOTS + ql] = f2_pack(m0.x, m1.x);
+    pts[4 * PICP_RES_SLOTS + ql] = f2_pack(m0.y, m1.y);
+  }
+  if (tid < 12) s_T[tid] = p.st->s.T[(tid / 3) * 4 + (tid % 3)];
+  // every CTA's shared memory must exist before anyone pushes into it
+  cluster.sync();
+
+  __shared__ float s_H[36], s_b[6], s_keep[4];  // last linearisation, written by thread 0
+  for (int round = 0; round < rounds; ++round) {
+    PicpConsts c;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) c.T[i] = s_T[i];
+    PicpAcc a;
+#pragma unroll
+    for (int i = 0; i < 21; ++i) a.h[i] = 0ull;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) a.b[i] = 0ull;
+    a.chi_in = a.chi_out = 0ull;
+    a.n_in = 0;
+    for (int ql = tid; ql < mine; ql += PICP_RES_THREADS)
+      picp_point2<PINHOLE, KEEP>(p, c, pts[ql], pts[PICP_RES_SLOTS + ql], pts[2 * PICP_RES_SLOTS + ql],
+                                 pts[3 * PICP_RES_SLOTS + ql], pts[4 * PICP_RES_SLOTS + ql],
+                                 2 * (q0 + ql) + 1 < n, a);
+    // the two point slots, then the warp (transposed: lane i gets sum i), then the CTA
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 29; ++i) {
+      float lo, hi;
+      f2_unpack(i < 21 ? a.h[i] : (i < 27 ? a.b[i - 21] : (i == 27 ? a.chi_in : a.chi_out)), lo, hi);
+      v[i] = lo + hi;
+    }
+    v[29] = (float)a.n_in;  // exact: at most 2^17 points per thread-block cluster
+    v[30] = v[31] = 0.f;
+    s_red[warp][lane] = warp_reduce_transposed(v);
+    __syncthreads();
+    if (warp == 0) {
+      float t = s_red[0][lane];
+#pragma unroll
+      for (int wv = 1; wv < W; ++wv) t += s_red[wv][lane];
+      // push this CTA's partial into every CTA of the cluster (DSMEM)
+      float* slot = &s_part[round & 1][rank][lane];
+      for (int r = 0; r < csize; ++r) *cluster.map_shared_rank(slot, r) = t;
+    }
+    cluster.sync();  // release/acquire: all partials of this round are visible everywhere
+    if (warp == 0) {
+      float t = s_part[round & 1][0][lane];
+      for (int r = 1; r < csize; ++r) t += s_part[round & 1][r][lane];
+      if (lane == 29) t = __int_as_float((int)t);  // the solve reads n_in as an integer
+      s_red[0][lane] = t;
+      __syncwarp();
+      if (lane == 0) {
+        s_keep[3] = picp_solve_local(p, s_red[0], s_T, s_H, s_b) ? 1.f : 0.f;
+        s_keep[0] = s_red[0][27];
+        s_keep[1] = s_red[0][28];
+        s_keep[2] = s_red[0][29];
+      }
+    }
+    __syncthreads();
+  }
+  // state write-back (CTA 0, thread 0): the pose and the LAST linearisation
+  if (rank == 0 && tid == 0 && rounds > 0) {
+    vo_picp_state& s = p.st->s;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) s.T[j * 4 + i] = s_T[j * 3 + i];
+    s.T[3] = s.T[7] = s.T[11] = 0.f;
+    s.T[15] = 1.f;
+#pragma unroll
+    for (int i = 0; i < 36; ++i) s.H[i] = s_H[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s.b[i] = s_b[i];
+    s.chi_inliers = s_keep[0];
+    s.chi_outliers = s_keep[1];
+    s.num_inliers = __float_as_int(s_keep[2]);
+    s.rounds_done += rounds;
+    s.last_ok = s_keep[3] != 0.f ? 1 : 0;
+  }
+  // no CTA may exit while a peer can still push into its shared memory
+  cluster.sync();
+}
+
 }  // namespace vo
 
 // =================================================================================================
@@ -473,6 +737,8 @@ struct vo_picp_s {
   vo_camera cam{};
   bool have_cam = false;
   float thr = 1000.f, damping = 1.f;  // picp_solver.cpp:10-13
+  bool smem_opted_in = false;
+  bool force_stream = false;          // VO_PICP_FORCE_STREAM=1: never use the resident kernel
   bool force_general = false;         // VO_PICP_FORCE_GENERAL=1: never use the pinhole kernel
   int32_t min_inliers = 0;
   DevBuf world_buf, image_buf, pairs_buf, state_buf, partials_buf;
@@ -536,7 +802,8 @@ static int picp_fill_params(vo_picp_s* h, int keep_outliers, PicpParams* p) {
 static int picp_pick_grid(vo_picp_s* h) {
   const int sms = num_sms(h->device);
   int per_sm = 2;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, picp_round_kernel<false, true>, PICP_THREADS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, picp_round_kernel<false, true>, PICP_THREADS,
+                                                PICP_SMEM_BYTES);
   if (per_sm < 1) per_sm = 1;
   const int64_t full = (int64_t)sms * per_sm;
   const int64_t need =
@@ -565,6 +832,8 @@ int vo_picp_create(vo_picp_t* out, int device) {
   h->own_stream = true;
   const char* fg = getenv("VO_PICP_FORCE_GENERAL");
   h->force_general = fg != nullptr && fg[0] == '1';
+  const char* fs = getenv("VO_PICP_FORCE_STREAM");
+  h->force_stream = fs != nullptr && fs[0] == '1';
   *out = h;
   return VO_OK;
 }
@@ -702,6 +971,17 @@ int vo_picp_compute(vo_picp_t h, int keep_outliers, int rounds) {
   VO_REQUIRE(rounds >= 0, VO_ERR_ARG, "negative rounds");
   if (rounds == 0) return VO_OK;
   DeviceGuard g(h->device);
+  if (!h->smem_opted_in) {  // the staging ring needs the opt-in shared-memory carve-out (per device)
+    VO_CUDA(cudaFuncSetAttribute(picp_round_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_SMEM_BYTES));
+    VO_CUDA(cudaFuncSetAttribute(picp_round_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_SMEM_BYTES));
+    VO_CUDA(cudaFuncSetAttribute(picp_round_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_SMEM_BYTES));
+    VO_CUDA(cudaFuncSetAttribute(picp_round_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_SMEM_BYTES));
+    VO_CUDA(cudaFuncSetAttribute(picp_resident_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_RES_SMEM));
+    VO_CUDA(cudaFuncSetAttribute(picp_resident_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_RES_SMEM));
+    VO_CUDA(cudaFuncSetAttribute(picp_resident_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_RES_SMEM));
+    VO_CUDA(cudaFuncSetAttribute(picp_resident_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_RES_SMEM));
+    h->smem_opted_in = true;
+  }
   const int grid = picp_pick_grid(h);
   int rc = h->partials_buf.reserve((size_t)grid * PICP_NACC * sizeof(float));
   if (rc) return rc;
@@ -714,9 +994,33 @@ int vo_picp_compute(vo_picp_t h, int keep_outliers, int rounds) {
                        K[5] == 0.f && K[8] == 1.f;
   auto kernel = pinhole ? (p.keep_outliers ? picp_round_kernel<true, true> : picp_round_kernel<true, false>)
                         : (p.keep_outliers ? picp_round_kernel<false, true> : picp_round_kernel<false, false>);
+  if (h->n_pairs <= PICP_RES_MAX && !h->force_stream) {
+    // a frame-sized problem: every round inside one resident thread-block cluster
+    auto rk = pinhole ? (p.keep_outliers ? picp_resident_kernel<true, true> : picp_resident_kernel<true, false>)
+                      : (p.keep_outliers ? picp_resident_kernel<false, true> : picp_resident_kernel<false, false>);
+    // one packed slot per thread where possible; cluster sizes 1, 2, 4, 8
+    const int64_t nslots = (h->n_pairs + 1) / 2;
+    int csize = 1;
+    while (csize < PICP_RES_CLUSTER && nslots > (int64_t)csize * PICP_RES_THREADS) csize *= 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)csize);
+    cfg.blockDim = dim3(PICP_RES_THREADS);
+    cfg.dynamicSmemBytes = PICP_RES_SMEM;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VO_CUDA(cudaLaunchKernelEx(&cfg, rk, p, rounds));
+    VO_LAUNCH_CHECK();
+    return VO_OK;
+  }
   if (rounds < 4) {
     for (int r = 0; r < rounds; ++r) {
-      kernel<<<grid, PICP_THREADS, 0, h->stream>>>(p);
+      kernel<<<grid, PICP_THREADS, PICP_SMEM_BYTES, h->stream>>>(p);
       VO_LAUNCH_CHECK();
     }
     return VO_OK;
@@ -735,7 +1039,7 @@ int vo_picp_compute(vo_picp_t h, int keep_outliers, int rounds) {
     if (!h->capture_stream)
       VO_CUDA(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
     VO_CUDA(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
-    for (int r = 0; r < rounds; ++r) kernel<<<grid, PICP_THREADS, 0, h->capture_stream>>>(p);
+    for (int r = 0; r < rounds; ++r) kernel<<<grid, PICP_THREADS, PICP_SMEM_BYTES, h->capture_stream>>>(p);
     cudaError_t e = cudaStreamEndCapture(h->capture_stream, &graph);
     if (e != cudaSuccess) {
       set_error("cudaStreamEndCapture -> %s", cudaGetErrorString(e));
