@@ -10,8 +10,9 @@ Primary line (BASELINE.json config 4, the only config that shards across GPUs):
           (it is the database, uploaded once like the reference builds its kd-tree once per map).
   roofline  FP32 CUDA-core bound: 30 algorithmic flop per (query,row) pair.
   cpu_baseline  the oracle port of bruteForceBestMatch on the host cores, on a query sample.
-Extra objects on the same line (N=1 only): "picp" (config 3 at 1e7 correspondences, HBM-bound)
-and "triangulate" (1e7 correspondences, HBM-bound), each with its own roofline and CPU sample.
+Extra objects on the same line: "picp" (config 3 at 1e7 correspondences, HBM-bound) and
+"triangulate" (1e7 correspondences, HBM-bound), each with its own roofline and CPU sample (N=1
+only), and "vo" (config 5: one synthetic 1000-frame x 1e5-landmark sequence per GPU, frames/s).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
   torchrun --nproc-per-node N bench.py --gpus N ...      (queries sharded, map replicated)
@@ -362,6 +363,56 @@ def bench_triangulate(torch, vo, synth, args, cores):
     }
 
 
+def bench_vo(torch, args, dist, rank, local, world):
+    """Config 5: the vo_complete frame loop on independent synthetic sequences, ONE PER GPU
+    (host/bin/vo_sequence, the reference-style C++ main running on the drop-in host layer over the
+    C ABI; seed 1000+rank).  frames/s counts the frame loop only (synthetic frame generation stands
+    for the sensor and is not timed); aggregate = all ranks' frames / the slowest rank's time.
+    CPU baseline (rank 0, N=1): the SAME driver source compiled against the reference's own
+    headers and sources (oracle/_ref/bin/vo_sequence) on a bounded, smaller sequence — the
+    reference's map update is O(frame x map) with a vector copy per comparison and does not finish
+    a single 1e5-landmark frame in minutes."""
+    import subprocess
+
+    exe = os.path.join(ROOT, "visual-odometry_b200", "host", "bin", "vo_sequence")
+    if not os.path.exists(exe):
+        return {"unavailable": "host/bin/vo_sequence not built (needs the reference checkout at build time)"}
+    env = dict(os.environ, VO_B200_DEVICE=str(local))
+    out = subprocess.run([exe, str(args.vo_landmarks), str(args.vo_frames), str(1000 + rank), "100"],
+                         env=env, capture_output=True, text=True, check=True).stdout
+    r = json.loads(out.strip().splitlines()[-1])
+    frames, sec = float(r["frames"]), r["loop_ms"] * 1e-3
+    if dist is not None:
+        t = torch.tensor([frames, sec], dtype=torch.float64, device="cuda")
+        tot = t.clone()
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        frames, sec = float(tot[0].item()), float(t[1].item())
+    res = {
+        "metric": "vo_frames_per_s", "value": frames / sec, "unit": "frames/s", "n_gpus": world,
+        "scaling": "weak",
+        "config": {"workload": f"batched vo_complete: {world} independent synthetic sequence(s) x "
+                               f"{args.vo_frames} frames x {args.vo_landmarks} landmarks, one per GPU, "
+                               "100 PICP rounds/frame"},
+        "rank0": {k: r[k] for k in ("frames_per_s", "stage_ms_per_frame", "mean_measurements",
+                                    "mean_correspondences", "map_points", "rot_err_mean_rad",
+                                    "scale_first_pair", "scale_median")},
+        "e2e": {"value": frames / sec, "unit": "frames/s",
+                "note": "host frames in, host poses out every frame (the driver IS the host API)"},
+    }
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "bin", "vo_sequence")
+    if rank == 0 and world == 1 and os.path.exists(ref_exe):
+        lm, fr = min(args.vo_landmarks, 10000), 6
+        c = json.loads(subprocess.run([ref_exe, str(lm), str(fr), "1000", "100"], capture_output=True,
+                                      text=True, check=True).stdout.strip().splitlines()[-1])
+        res["cpu_baseline"] = {"value": c["frames_per_s"], "unit": "frames/s", "cores": 1,
+                               "kind": "reference",
+                               "sample": f"{c['frames']} frames of a {lm}-landmark sequence "
+                                         f"({c['mean_measurements']:.0f} measurements/frame)",
+                               "stage_ms_per_frame": c["stage_ms_per_frame"]}
+    return res
+
+
 def ours_arm(args):
     import torch
 
@@ -506,6 +557,10 @@ def ours_arm(args):
     if rank == 0 and world == 1 and not args.nn_only:
         line["picp"] = bench_picp(torch, vo, synth, args, cores)
         line["triangulate"] = bench_triangulate(torch, vo, synth, args, cores)
+    if not args.nn_only and args.vo_frames > 0:
+        vo_res = bench_vo(torch, args, dist, rank, local, world)
+        if rank == 0:
+            line["vo"] = vo_res
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -523,6 +578,8 @@ def main():
     ap.add_argument("--queries", type=int, default=100_000)
     ap.add_argument("--picp-points", type=int, default=10_000_000)
     ap.add_argument("--tri-points", type=int, default=10_000_000)
+    ap.add_argument("--vo-landmarks", type=int, default=100_000)
+    ap.add_argument("--vo-frames", type=int, default=1000)
     ap.add_argument("--nn-only", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

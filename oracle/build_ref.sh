@@ -25,4 +25,8 @@ $CXX $FLAGS "$REF/src/apps/vo_complete.cpp" $OBJS -o "$OUT/bin/vo_complete"
 $CXX $FLAGS "$REF/src/tests/picp_solver_test.cpp" $OBJS -o "$OUT/bin/picp_test"
 $CXX $FLAGS "$REF/src/tests/essential_picp_test.cpp" $OBJS -o "$OUT/bin/whole_test"
 $CXX $FLAGS "$REF/src/apps/evaluate.cpp" "$REF/src/evaluation_utils.cpp" $OBJS -o "$OUT/bin/evaluation"
+# config 5 on the CPU: this repository's sequence driver compiled against the REFERENCE's headers and
+# objects (it only uses declarations both header sets share), i.e. the reference implementation of
+# every stage on the synthetic frames
+$CXX $FLAGS "$HERE/../visual-odometry_b200/host/apps/vo_sequence.cpp" $OBJS -o "$OUT/bin/vo_sequence"
 echo "built $OUT/libvo_ref.so and $OUT/bin/{vo_complete,picp_test,whole_test,evaluation}"

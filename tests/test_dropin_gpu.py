@@ -86,3 +86,29 @@ def test_vo_complete_on_bundled_data_matches_cpu_reference(tmp_path):
     bad = np.nonzero(gpu_dev > envelope)[0]
     assert bad.size == 0, (bad[:5], gpu_dev[bad[:5]], envelope[bad[:5]])
     assert gpu_dev[:10].max() <= 2e-3
+
+
+def test_synthetic_sequence_matches_cpu_reference(tmp_path):
+    """Config 5 at test size: the same driver source, built against the drop-in layer (GPU) and
+    against the reference's own sources (CPU), on the same synthetic frames.  Relative poses must
+    agree per frame to FP32 summation-order noise while the robot drives straight (the pipeline
+    is chaotic once it turns: see test_vo_complete_on_bundled_data)."""
+    gpu = _need("vo_sequence")
+    ref = os.path.join(ROOT, "oracle", "_ref", "bin", "vo_sequence")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/bin/vo_sequence not built")
+    import json
+
+    res = {}
+    for name, exe in (("ref", ref), ("gpu", gpu)):
+        out = subprocess.run([exe, "3000", "24", "1000", "100", str(tmp_path / f"{name}.txt")],
+                             capture_output=True, text=True, check=True).stdout
+        res[name] = json.loads(out.strip().splitlines()[-1])
+    a, b = np.loadtxt(tmp_path / "ref.txt"), np.loadtxt(tmp_path / "gpu.txt")
+    assert a.shape == b.shape == (22, 12)
+    assert res["gpu"]["impl"] == "b200"
+    # identical data association and map bookkeeping
+    for k in ("mean_measurements", "mean_correspondences", "map_points"):
+        assert res["gpu"][k] == res["ref"][k], k
+    assert np.abs(a - b).max() <= 5e-4, np.abs(a - b).max(1)
+    assert res["gpu"]["rot_err_mean_rad"] < 1e-3

@@ -22,4 +22,6 @@ LINK="-L $ROOT/visual-odometry_b200/lib -lvo_b200 -Wl,-rpath,\$ORIGIN/../../lib"
 $CXX $FLAGS "$REF/src/apps/vo_complete.cpp" $OBJS $LINK -o "$HERE/bin/vo_complete"
 $CXX $FLAGS "$REF/src/tests/picp_solver_test.cpp" $OBJS $LINK -o "$HERE/bin/picp_test"
 $CXX $FLAGS "$REF/src/tests/essential_picp_test.cpp" $OBJS $LINK -o "$HERE/bin/whole_test"
-echo "built $HERE/bin/{vo_complete,picp_test,whole_test} against libvo_b200.so"
+# the synthetic-sequence driver (config 5): our own source, the same file the CPU reference build uses
+$CXX $FLAGS "$HERE/apps/vo_sequence.cpp" $OBJS $LINK -o "$HERE/bin/vo_sequence"
+echo "built $HERE/bin/{vo_complete,picp_test,whole_test,vo_sequence} against libvo_b200.so"

@@ -2,6 +2,10 @@
 // appearance, and the structure-of-arrays container the pipeline passes around.  Host-side data
 // structure; the GPU entry points read points() / appearances() in place.
 #pragma once
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
 #include "defs.h"
 
 template <int dim>
@@ -33,10 +37,12 @@ class PointCloudVector {
   void clear() {
     _points.clear();
     _appearances.clear();
+    _index_valid = false;
   }
   void resize(size_t N) {
     _points.resize(N);
     _appearances.resize(N);
+    _index_valid = false;
   }
   void reserve(size_t N) {
     _points.reserve(N);
@@ -49,33 +55,85 @@ class PointCloudVector {
   // merge `cloud` into this one (reference PointCloud.h:52-66): a point whose appearance is
   // already present (exact float equality, first hit) replaces the stored position; every other
   // point is appended, in order.  Appended points take part in the matching of later ones.
+  // The reference scans the whole map for every new point (O(|cloud| x |map|), the dominant cost
+  // of a long sequence: SURVEY.md §8f.1); here the first index of every distinct appearance is
+  // kept in a hash index that stays valid across update()/push_back() calls and is rebuilt
+  // only after the containers were exposed for writing.  Same results, O(|cloud|) per call.
   void update(const PointCloudVector<dim>& cloud) {
+    if (!_index_valid || _indexed != _appearances.size()) rebuild_index();
     const PointsVec& new_points = cloud._points;
     const Vector10fVector& new_appearances = cloud._appearances;
     for (size_t i = 0; i < new_points.size(); ++i) {
-      size_t hit = _appearances.size();
-      for (size_t j = 0; j < _appearances.size(); ++j)
-        if (_appearances[j] == new_appearances[i]) {
-          hit = j;
-          break;
+      uint64_t h;
+      const bool comparable = hash_of(new_appearances[i], h);  // false: holds a NaN, equals nothing
+      if (comparable) {
+        if ((_appearances.size() + 1) * 2 > _slots.size()) rebuild_index();
+        const size_t slot = find_slot(new_appearances[i], h);
+        if (_slots[slot] != kEmpty) {
+          _points[_slots[slot]] = new_points[i];
+          continue;
         }
-      if (hit < _appearances.size()) {
-        _points[hit] = new_points[i];
-      } else {
-        _points.push_back(new_points[i]);
-        _appearances.push_back(new_appearances[i]);
+        _slots[slot] = (uint32_t)_appearances.size();
       }
+      _points.push_back(new_points[i]);
+      _appearances.push_back(new_appearances[i]);
+      _indexed = _appearances.size();
     }
   }
 
+  // non-const access may change appearances behind the index: it is rebuilt on the next update()
   inline PointsVec& points() { return _points; }
-  inline Vector10fVector& appearances() { return _appearances; }
+  inline Vector10fVector& appearances() {
+    _index_valid = false;
+    return _appearances;
+  }
   inline PointsVec points() const { return _points; }
   inline Vector10fVector appearances() const { return _appearances; }
 
  protected:
+  // Open-addressing table over the stored appearances: a slot holds the FIRST index whose
+  // appearance hashes there (float equality: -0.0 == +0.0 hash alike, a NaN equals nothing and is
+  // never indexed).  Linear probing; at most half full.
+  static constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+  static bool hash_of(const Vector10f& a, uint64_t& h) {
+    h = 0x9E3779B97F4A7C15ull;
+    for (int i = 0; i < 10; ++i) {
+      const float v = a(i);
+      if (v != v) return false;
+      const float z = (v == 0.f) ? 0.f : v;
+      uint32_t w;
+      std::memcpy(&w, &z, sizeof(float));
+      h = (h ^ w) * 0x100000001B3ull;
+      h ^= h >> 29;
+    }
+    return true;
+  }
+  // the slot holding an appearance equal to `a`, or the empty slot where it belongs
+  size_t find_slot(const Vector10f& a, uint64_t h) const {
+    const size_t mask = _slots.size() - 1;
+    size_t s = (size_t)h & mask;
+    while (_slots[s] != kEmpty && !(_appearances[_slots[s]] == a)) s = (s + 1) & mask;
+    return s;
+  }
+  void rebuild_index() {
+    size_t cap = 1024;
+    while (cap < 4 * (_appearances.size() + 1)) cap *= 2;
+    _slots.assign(cap, kEmpty);
+    for (size_t j = 0; j < _appearances.size(); ++j) {
+      uint64_t h;
+      if (!hash_of(_appearances[j], h)) continue;
+      const size_t s = find_slot(_appearances[j], h);
+      if (_slots[s] == kEmpty) _slots[s] = (uint32_t)j;  // keeps the first
+    }
+    _indexed = _appearances.size();
+    _index_valid = true;
+  }
+
   PointsVec _points;
   Vector10fVector _appearances;
+  std::vector<uint32_t> _slots;
+  size_t _indexed = 0;
+  bool _index_valid = false;
 };
 
 // every point of the cloud moved by X; appearances are carried over (PointCloud.h:77-82)

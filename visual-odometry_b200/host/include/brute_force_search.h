@@ -5,16 +5,20 @@
 // brute-force kernel (strict '<' against norm*norm, lowest address wins ties, nullptr if none).
 #pragma once
 #include <iterator>
+#include <mutex>
 #include <vector>
 
 #include "vo_b200_host.h"
 
 namespace vo_b200 {
-// RAII wrapper of one resident map
+// RAII wrapper of one resident map.  Handles (stream + grow-only device buffers) are recycled
+// through a small process-wide pool: the pipeline builds a search structure per frame
+// (vo_complete.cpp:35), and creating / destroying CUDA streams and allocations at that rate costs
+// more than the search itself.
 class NNMap {
  public:
-  NNMap() : _h(nullptr) { check(vo_nn_create(&_h, device()), "vo_nn_create"); }
-  ~NNMap() { vo_nn_destroy(_h); }
+  NNMap() : _h(acquire()) {}
+  ~NNMap() { release(_h); }
   NNMap(const NNMap&) = delete;
   NNMap& operator=(const NNMap&) = delete;
   void setRows(const float* rows, long n, int stride) {
@@ -39,6 +43,37 @@ class NNMap {
   }
 
  private:
+  struct Pool {
+    std::mutex mu;
+    std::vector<vo_nn_t> idle;
+    ~Pool() {
+      for (vo_nn_t h : idle) vo_nn_destroy(h);
+    }
+  };
+  static Pool& pool() {
+    static Pool p;
+    return p;
+  }
+  static vo_nn_t acquire() {
+    {
+      Pool& p = pool();
+      std::lock_guard<std::mutex> lock(p.mu);
+      if (!p.idle.empty()) {
+        vo_nn_t h = p.idle.back();
+        p.idle.pop_back();
+        return h;
+      }
+    }
+    vo_nn_t h = nullptr;
+    check(vo_nn_create(&h, device()), "vo_nn_create");
+    return h;
+  }
+  static void release(vo_nn_t h) {
+    Pool& p = pool();
+    std::lock_guard<std::mutex> lock(p.mu);
+    if (p.idle.size() < 8) p.idle.push_back(h);
+    else vo_nn_destroy(h);
+  }
   vo_nn_t _h;
 };
 

@@ -5,6 +5,10 @@
 
 #include "vo_b200.h"
 
+// lets a source file that compiles against both header sets (the reference's and this one) pick
+// the additive batched entry points when they exist
+#define VO_B200_DROPIN 1
+
 namespace vo_b200 {
 
 // There is no CPU fallback: a failing ABI call is fatal, with the library's message.
