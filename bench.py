@@ -142,6 +142,30 @@ def cpu_nn_queries_per_s(map_host, queries_host, threads):
     return len(queries_host) / dt, np.concatenate(res), dt
 
 
+def kdtree_agreement(vo, synth, local):
+    """GPU exact answers vs the reference's kd-tree (TreeNode_, leaf size 10, radius 0.1 as in
+    vo_complete.cpp:35-38) on a 1e6-row map: bestMatchFull is exact within the radius (up to
+    ties), bestMatchFast is approximate — the agreement rates north_star asks to report."""
+    import ref_lib
+
+    if not ref_lib.available():
+        return None
+    M, Q = 1_000_000, 4000
+    rows = synth.nn_map_rows_np(0, M)
+    q, _ = synth.nn_queries_np(Q, M)
+    nn = vo.NNIndex(local)
+    nn.set_map(rows)
+    gpu = nn.best_match(q, RADIUS)
+    nn.close()
+    t0 = time.perf_counter()
+    full = ref_lib.kdtree_best_match(rows, q, RADIUS, leaf=10, full=True)
+    t_full = time.perf_counter() - t0
+    fast = ref_lib.kdtree_best_match(rows, q, RADIUS, leaf=10, full=False)
+    return {"map_rows": M, "queries": Q, "bestMatchFull_agreement": float(np.mean(full == gpu)),
+            "bestMatchFast_agreement": float(np.mean(fast == gpu)),
+            "cpu_kdtree_build_plus_full_queries_s": t_full}
+
+
 def reference_arm(args):
     """--impl reference: the reference's CPU path for the metric — its bruteForceBestMatch
     template (oracle/_ref, prebuilt from the reference sources; the C port if that is absent) on
@@ -282,7 +306,31 @@ def bench_picp(torch, vo, synth, args, cores):
     peaks = measured_peaks()
     hbm = peaks.get("hbm_gbs", 6650.0)
     achieved = PICP_BYTES_PER_CORR * n_corr * rounds / (ms * 1e-3) / 1e9
+    # config 3's scale sweep: the same step at 1e4..1e6 generated points (<= 65536 correspondences
+    # run in the resident cluster kernel, above that in the streaming kernel; <~4e6 are L2-resident)
+    sweep = []
+    for ng in (10_000, 100_000, 1_000_000):
+        q = synth.picp_problem(ng, seed=42)
+        nq = len(q["pairs"])
+        w_, i_, p_ = (torch.from_numpy(q[k]).to(dev) for k in ("world", "image", "pairs"))
+        sv = vo.PICPSolver(0)
+        sv.set_stream(torch.cuda.current_stream().cuda_stream)
+        sv.setKernelThreshold(10000.0)
+
+        def sstep():
+            sv.init_device(cam, w_.data_ptr(), w_.shape[0], i_.data_ptr(), i_.shape[0])
+            sv.set_correspondences_device(p_.data_ptr(), nq)
+            sv.compute(False, rounds)
+
+        sms = timed_steps(torch, sstep, max(3, args.steps), args.warmup)
+        sweep.append({"n_corr": nq, "us_per_round": sms * 1e3 / rounds,
+                      "point_iters_per_s": nq * rounds / (sms * 1e-3),
+                      "pose_err_vs_gt": float(np.max(np.abs(sv.pose() - q["T_gt"])))})
+        sv.close()
+    sweep.append({"n_corr": n_corr, "us_per_round": ms * 1e3 / rounds,
+                  "point_iters_per_s": n_corr * rounds / (ms * 1e-3)})
     return {
+        "sweep": sweep,
         "metric": "picp_point_iters_per_s", "value": n_corr * rounds / (ms * 1e-3),
         "unit": "point-iters/s", "ms_per_step": ms,
         "config": {"workload": f"picp_test frustum-dist: {n_corr} correspondences "
@@ -551,7 +599,8 @@ def ours_arm(args):
                              "kind": cpu_kind(),
                              "sample": f"{sample_q} queries x full {M}-row map, {cores} threads"},
             "parity": {"planted_answers_equal": planted_ok, "oracle_sample_equal": oracle_equal,
-                       "oracle_sample": sample_q, "rule": "bit-exact indices"},
+                       "oracle_sample": sample_q, "rule": "bit-exact indices",
+                       "kdtree": None if args.nn_only else kdtree_agreement(vo, synth, local)},
         }
     nn.close()
     if rank == 0 and world == 1 and not args.nn_only:

@@ -154,6 +154,15 @@ __device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsig
   return d;
 }
 __device__ __forceinline__ unsigned long long f2_bc(float x) { return f2_pack(x, x); }
+// A product that is rounded ON ITS OWN.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one
+// FFMA2 even under --fmad=false (it does not for the scalar .rn forms), which would remove the
+// product's rounding.  fma(a, b, +0.0) is the same IEEE product (only a -0 result becomes +0) and
+// cannot be folded into a following add, so code that must match a non-FMA CPU uses this.
+__device__ __forceinline__ unsigned long long f2_prod(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("{\n.reg .b64 z;\nmov.b64 z, 0;\nfma.rn.f32x2 %0, %1, %2, z;\n}" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 #endif
 
 }  // namespace vo

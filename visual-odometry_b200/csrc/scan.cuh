@@ -133,6 +133,55 @@ __device__ __forceinline__ long long scan_tile_lookback(const ScanWorkspace& ws,
   return excl;
 }
 
+// Step 2, single-warp flavour: the same sum, gathered by WARP 0 ONLY (its lanes poll 32 words at a
+// time, every word of a chunk is requested before the first one is examined) and handed to the rest
+// of the block through shared memory.  The other warps sleep on the barrier instead of burning
+// issue slots in a spin loop.  Contains one __syncthreads(); every thread returns the same value.
+template <int THREADS>
+__device__ __forceinline__ long long scan_tile_lookback_warp0(const ScanWorkspace& ws, int tile) {
+  __shared__ long long s_excl;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    const int G = ws.group_tiles;
+    const int g = tile / G;
+    long long c = 0;
+    constexpr int B = 4;  // words in flight per lane
+    for (int base = lane; base < g; base += 32 * B) {
+      unsigned long long v[B];
+#pragma unroll
+      for (int k = 0; k < B; ++k) {
+        const int idx = base + 32 * k;
+        v[k] = idx < g ? scan_ld(ws.groups + idx) : ((unsigned long long)G << SCAN_GROUP_SHIFT);
+      }
+#pragma unroll
+      for (int k = 0; k < B; ++k) {
+        const int idx = base + 32 * k;
+        while ((int)(v[k] >> SCAN_GROUP_SHIFT) != G) v[k] = scan_ld(ws.groups + idx);
+        c += (long long)(v[k] & SCAN_VALUE_MASK);
+      }
+    }
+    for (int base = g * G + lane; base < tile; base += 32 * B) {
+      unsigned long long v[B];
+#pragma unroll
+      for (int k = 0; k < B; ++k) {
+        const int idx = base + 32 * k;
+        v[k] = idx < tile ? scan_ld(ws.status + idx) : SCAN_POSTED;
+      }
+#pragma unroll
+      for (int k = 0; k < B; ++k) {
+        const int idx = base + 32 * k;
+        while ((v[k] & SCAN_POSTED) == 0ull) v[k] = scan_ld(ws.status + idx);
+        c += (long long)(v[k] & SCAN_VALUE_MASK);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) s_excl = c;
+  }
+  __syncthreads();
+  return s_excl;
+}
+
 // Dynamic tile id (two __syncthreads()).
 __device__ __forceinline__ int scan_take_ticket(const ScanWorkspace& ws) {
   __shared__ int s_ticket;

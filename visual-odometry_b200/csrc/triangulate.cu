@@ -44,87 +44,228 @@ struct TriParams {
   int num_tiles;
 };
 
-// triangulate_point, utils.cpp:36-49
-__device__ __forceinline__ bool triangulate_point_dev(const float (&d1)[3], const float (&d2)[3],
-                                                      const float (&t)[3], float (&p)[3]) {
-  const float n0 = -d1[0], n1 = -d1[1], n2 = -d1[2];  // D.col(0) = -d1
-  float A[4], rhs[2], ss[2];
+// triangulate_point (utils.cpp:36-49) for TWO correspondences at once: the two lanes of sm_100a's
+// packed FP32 pairs (mul/add.rn.f32x2: one issue slot, two IEEE-rounded results) carry two
+// independent points.  No contraction anywhere on this path — every product (f2_prod) and every sum
+// is rounded separately, in the reference's order — so each lane equals the CPU oracle (IEEE ==;
+// the sign of an exact zero is the only thing that may differ, see f2_prod):
+//   D = [-d1 d2];  A = D^T D;  rhs = D^T t;  ss = ldlt(A).solve(rhs);  s = -ss;
+//   reject if s0 < 0 || s1 < 0;  p = 0.5 * (s0*d1 + (t + s1*d2)).
+// The 2x2 pivoted LDL^T is ldlt_solve_dev<2> written out (same operation sequence as Eigen's:
+// pivot on the larger |diagonal|, L = A10/D0, D1 = A11 - L*(D0*L), forward / diagonal / backward
+// substitution, un-permute); its three divisions stay scalar IEEE divisions per lane.
+typedef unsigned long long f2_t;
+
+__device__ __forceinline__ f2_t f2_dot3(const f2_t (&a)[3], const f2_t (&b)[3]) {
   // fixed-size Eigen products sum three terms as s0 + (s1 + s2) (see oracle/vo_oracle.c)
-  A[0] = n0 * n0 + (n1 * n1 + n2 * n2);  // D^T D
-  A[1] = d2[0] * n0 + (d2[1] * n1 + d2[2] * n2);
-  A[2] = A[1];
-  A[3] = d2[0] * d2[0] + (d2[1] * d2[1] + d2[2] * d2[2]);
-  rhs[0] = n0 * t[0] + (n1 * t[1] + n2 * t[2]);  // D^T p2
-  rhs[1] = d2[0] * t[0] + (d2[1] * t[1] + d2[2] * t[2]);
-  ldlt_solve_dev<2>(A, rhs, ss);  // :40
-  const float s0 = -ss[0], s1 = -ss[1];
-  if (s0 < 0.f || s1 < 0.f) return false;  // :41
-#pragma unroll
-  for (int i = 0; i < 3; ++i) p[i] = 0.5f * (s0 * d1[i] + (t[i] + s1 * d2[i]));  // :44-47
-  return true;
+  return f2_add(f2_prod(a[0], b[0]), f2_add(f2_prod(a[1], b[1]), f2_prod(a[2], b[2])));
+}
+__device__ __forceinline__ f2_t f2_select(bool c0, bool c1, f2_t a, f2_t b) {
+  float a0, a1, b0, b1;
+  f2_unpack(a, a0, a1);
+  f2_unpack(b, b0, b1);
+  return f2_pack(c0 ? a0 : b0, c1 ? a1 : b1);
 }
 
-// One tile of THREADS*ITEMS correspondences per block.  Item j of lane l of warp w sits at tile
-// position w*32*ITEMS + j*32 + l, so every load and store of a warp is a contiguous run.
+__device__ __forceinline__ void triangulate_pair_dev(const f2_t (&d1)[3], const f2_t (&d2)[3],
+                                                     const float (&t)[3], f2_t (&p)[3], bool& ok0,
+                                                     bool& ok1) {
+  const f2_t neg1 = f2_bc(-1.f);
+  const f2_t tt[3] = {f2_bc(t[0]), f2_bc(t[1]), f2_bc(t[2])};
+  // D.col(0) = -d1:  (-a)*(-b) == a*b and (-a)*b == -(a*b) exactly, so the sign is applied to the
+  // finished dot products
+  const f2_t A00 = f2_dot3(d1, d1);                 // n.n
+  const f2_t A10 = f2_mul(f2_dot3(d2, d1), neg1);   // d2.n
+  const f2_t A11 = f2_dot3(d2, d2);
+  const f2_t r0 = f2_mul(f2_dot3(d1, tt), neg1);    // n.t
+  const f2_t r1 = f2_dot3(d2, tt);
+  float a00[2], a10[2], a11[2];
+  f2_unpack(A00, a00[0], a00[1]);
+  f2_unpack(A10, a10[0], a10[1]);
+  f2_unpack(A11, a11[0], a11[1]);
+  // pivot: the larger |diagonal| first (strict >, as in the generic routine)
+  const bool sw0 = fabsf(a11[0]) > fabsf(a00[0]), sw1 = fabsf(a11[1]) > fabsf(a00[1]);
+  const f2_t D0 = f2_select(sw0, sw1, A11, A00);
+  f2_t D1 = f2_select(sw0, sw1, A00, A11);
+  f2_t y0 = f2_select(sw0, sw1, r1, r0);
+  f2_t y1 = f2_select(sw0, sw1, r0, r1);
+  float d0[2];
+  f2_unpack(D0, d0[0], d0[1]);
+  const f2_t L = f2_pack(fabsf(d0[0]) > 0.f ? a10[0] / d0[0] : a10[0],
+                         fabsf(d0[1]) > 0.f ? a10[1] / d0[1] : a10[1]);
+  D1 = f2_add(D1, f2_mul(f2_prod(L, f2_prod(D0, L)), neg1));  // A11 - L*(D0*L)
+  y1 = f2_add(y1, f2_mul(f2_prod(L, y0), neg1));              // forward substitution
+  float d1v[2], y0v[2], y1v[2];
+  f2_unpack(D1, d1v[0], d1v[1]);
+  f2_unpack(y0, y0v[0], y0v[1]);
+  f2_unpack(y1, y1v[0], y1v[1]);
+  constexpr float tiny = 1.17549435e-38f;
+  y0 = f2_pack(fabsf(d0[0]) > tiny ? y0v[0] / d0[0] : 0.f, fabsf(d0[1]) > tiny ? y0v[1] / d0[1] : 0.f);
+  y1 = f2_pack(fabsf(d1v[0]) > tiny ? y1v[0] / d1v[0] : 0.f, fabsf(d1v[1]) > tiny ? y1v[1] / d1v[1] : 0.f);
+  y0 = f2_add(y0, f2_mul(f2_prod(L, y1), neg1));              // backward substitution
+  const f2_t ss0 = f2_select(sw0, sw1, y1, y0), ss1 = f2_select(sw0, sw1, y0, y1);
+  const f2_t s0 = f2_mul(ss0, neg1), s1 = f2_mul(ss1, neg1);  // :40
+  float s0v[2], s1v[2];
+  f2_unpack(s0, s0v[0], s0v[1]);
+  f2_unpack(s1, s1v[0], s1v[1]);
+  ok0 = !(s0v[0] < 0.f || s1v[0] < 0.f);  // :41
+  ok1 = !(s0v[1] < 0.f || s1v[1] < 0.f);
+  const f2_t half = f2_bc(0.5f);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)  // :44-47
+    p[i] = f2_mul(half, f2_add(f2_prod(s0, d1[i]), f2_add(tt[i], f2_prod(s1, d2[i]))));
+}
+
+// Persistent blocks, deferred write-out.  An ordered compaction makes every tile depend on the
+// success counts of ALL earlier tiles; when a block waits for that prefix right after computing
+// its tile it idles for the slowest of several hundred in-flight predecessors (ncu: half of all
+// warp samples sat on that barrier).  Here a block therefore
+//   1. claims a tile (atomic ticket: it can only ever depend on tiles already claimed by running
+//      blocks), loads and solves it, ranks the successes with warp ballots,
+//   2. parks the compacted results (points + second index) in one of two shared-memory slots and
+//      publishes the tile's count,
+//   3. and only then RETIRES THE PREVIOUS tile: by now its predecessors have had a whole tile time
+//      to publish, so the look-back (warp 0 only) returns at once, and the parked results stream
+//      out as fully coalesced stores.
+// Item j of lane l of warp w sits at tile position w*32*ITEMS + j*32 + l, so every load of a warp
+// is a contiguous run.
 template <int THREADS, int ITEMS>
 __global__ void __launch_bounds__(THREADS) triangulate_kernel(const TriParams q) {
+  static_assert(ITEMS % 2 == 0, "items are processed in packed pairs");
   constexpr int TILE = THREADS * ITEMS;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tile = scan_take_ticket(q.ws);
-  const int64_t warp_base = (int64_t)tile * TILE + (int64_t)warp * (32 * ITEMS);
+  constexpr int WARPS = THREADS / 32;
+  __shared__ float s_pts[2][TILE * 3];
+  __shared__ int s_c2[2][TILE];
+  __shared__ int s_src[2][TILE];
+  __shared__ int s_next;
+  __shared__ int s_warp_tot[WARPS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float t[3] = {q.t[0], q.t[1], q.t[2]};
 
-  int2 c[ITEMS];
-  bool in[ITEMS];
+  // write-out of a parked tile: prefix of everything before it, then coalesced copies
+  auto retire = [&](int slot, int tile, int total) {
+    const long long excl = scan_tile_lookback_warp0<THREADS>(q.ws, tile);
+    float* dst = q.out_points + 3 * excl;
+    const int nf = 3 * total;
 #pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    const int64_t i = warp_base + j * 32 + lane;
-    in[j] = i < q.n_corr;
-    c[j] = in[j] ? __ldg(q.corr + i) : make_int2(0, 0);
-  }
-  float2 a[ITEMS], b[ITEMS];
+    for (int k = 0; k < 3 * ITEMS; ++k) {
+      const int j = k * THREADS + tid;
+      if (j < nf) dst[j] = s_pts[slot][j];
+    }
+    if (q.out_corr_new) {
 #pragma unroll
-  for (int j = 0; j < ITEMS; ++j)
-    if (in[j]) {
+      for (int k = 0; k < ITEMS; ++k) {
+        const int r = k * THREADS + tid;
+        if (r < total) q.out_corr_new[excl + r] = make_int2(s_c2[slot][r], (int)(excl + r));  // (idx_second, k) :97
+      }
+    }
+    if (q.out_src)
+      for (int r = tid; r < total; r += THREADS) q.out_src[excl + r] = s_src[slot][r];
+    if (q.out_app)  // :127 — the appearance travels with the point
+      for (int r = tid; r < total; r += THREADS) {
+        const float2* src = reinterpret_cast<const float2*>(q.app2 + 10 * (int64_t)s_c2[slot][r]);
+        float2* o = reinterpret_cast<float2*>(q.out_app + 10 * (excl + r));
+#pragma unroll
+        for (int i = 0; i < 5; ++i) o[i] = __ldg(src + i);
+      }
+    if (tile == q.num_tiles - 1 && tid == 0) *q.n_success = excl + total;
+  };
+
+  int pend_tile = -1, pend_total = 0, pend_slot = 0, slot = 0;
+  if (tid == 0) s_next = (int)atomicAdd(q.ws.ticket, 1u);
+  __syncthreads();
+  int tile = s_next;
+  while (tile < q.num_tiles) {
+    const int64_t warp_base = (int64_t)tile * TILE + (int64_t)warp * (32 * ITEMS);
+    // out-of-range slots of the last tile re-read the last correspondence and are masked out
+    int2 c[ITEMS];
+    bool in[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const int64_t i = warp_base + j * 32 + lane;
+      in[j] = i < q.n_corr;
+      c[j] = __ldg(q.corr + (in[j] ? i : q.n_corr - 1));
+    }
+    float2 a[ITEMS], b[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
       a[j] = __ldg(q.p1 + c[j].x);  // .first  -> image 1   (utils.cpp:87)
       b[j] = __ldg(q.p2 + c[j].y);  // .second -> image 2   (utils.cpp:88)
     }
-  float P[ITEMS][3];
-  bool ok[ITEMS];
-  const float t[3] = {q.t[0], q.t[1], q.t[2]};
+    f2_t P[ITEMS / 2][3];
+    bool ok[ITEMS];
 #pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    ok[j] = false;
-    if (in[j]) {
-      float d1[3], d2[3];
+    for (int jp = 0; jp < ITEMS / 2; ++jp) {
+      const f2_t ax = f2_pack(a[2 * jp].x, a[2 * jp + 1].x), ay = f2_pack(a[2 * jp].y, a[2 * jp + 1].y);
+      const f2_t bx = f2_pack(b[2 * jp].x, b[2 * jp + 1].x), by = f2_pack(b[2 * jp].y, b[2 * jp + 1].y);
+      f2_t d1[3], d2[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        d1[i] = q.iK[i] * a[j].x + (q.iK[3 + i] * a[j].y + q.iK[6 + i]);        // iK*[p1;1]   :91
-        d2[i] = q.iRiK[i] * b[j].x + (q.iRiK[3 + i] * b[j].y + q.iRiK[6 + i]);  // iRiK*[p2;1] :94
+        // iK*[p1;1] (:91) and iRiK*[p2;1] (:94):  m0*x + (m1*y + m2)
+        d1[i] = f2_add(f2_prod(f2_bc(q.iK[i]), ax), f2_add(f2_prod(f2_bc(q.iK[3 + i]), ay), f2_bc(q.iK[6 + i])));
+        d2[i] = f2_add(f2_prod(f2_bc(q.iRiK[i]), bx), f2_add(f2_prod(f2_bc(q.iRiK[3 + i]), by), f2_bc(q.iRiK[6 + i])));
       }
-      ok[j] = triangulate_point_dev(d1, d2, t, P[j]);
+      bool k0, k1;
+      triangulate_pair_dev(d1, d2, t, P[jp], k0, k1);
+      ok[2 * jp] = k0 && in[2 * jp];
+      ok[2 * jp + 1] = k1 && in[2 * jp + 1];
     }
+
+    // rank inside the tile: warp ballots, then the warp totals through shared memory
+    int local[ITEMS];
+    const unsigned lt = (1u << lane) - 1u;
+    int run = 0;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const unsigned bal = __ballot_sync(0xffffffffu, ok[j]);
+      local[j] = run + __popc(bal & lt);
+      run += __popc(bal);
+    }
+    if (lane == 0) s_warp_tot[warp] = run;
+    if (tid == 0) s_next = (int)atomicAdd(q.ws.ticket, 1u);  // the tile after this one
+    __syncthreads();
+    int warp_off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) {
+      const int x = s_warp_tot[w];
+      warp_off += (w < warp) ? x : 0;
+      total += x;
+    }
+    const int next = s_next;
+    if (tid == 0) {
+      scan_st(q.ws.status + tile, SCAN_POSTED | (unsigned long long)total);
+      atomicAdd(q.ws.groups + tile / q.ws.group_tiles,
+                (1ull << SCAN_GROUP_SHIFT) | (unsigned long long)total);
+    }
+    // park the compacted results of this tile
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+      if (ok[j]) {
+        const int r = warp_off + local[j];
+        float px, py, pz, ox, oy, oz;
+        f2_unpack(P[j >> 1][0], px, ox);
+        f2_unpack(P[j >> 1][1], py, oy);
+        f2_unpack(P[j >> 1][2], pz, oz);
+        s_pts[slot][3 * r + 0] = (j & 1) ? ox : px;
+        s_pts[slot][3 * r + 1] = (j & 1) ? oy : py;
+        s_pts[slot][3 * r + 2] = (j & 1) ? oz : pz;
+        s_c2[slot][r] = c[j].y;
+        s_src[slot][r] = (int)(warp_base + j * 32 + lane);
+      }
+    // retire the previous tile (contains a barrier, which also orders this tile's parking
+    // before its own retirement in the next iteration)
+    if (pend_tile >= 0) retire(pend_slot, pend_tile, pend_total);
+    else __syncthreads();
+    pend_tile = tile;
+    pend_total = total;
+    pend_slot = slot;
+    slot ^= 1;
+    tile = next;
   }
-  int local[ITEMS];
-  int total;
-  scan_tile_post<THREADS, ITEMS>(q.ws, tile, ok, local, &total);
-  const long long excl = scan_tile_lookback<THREADS>(q.ws, tile);
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j)
-    if (ok[j]) {
-      const long long k = excl + local[j];
-      q.out_points[3 * k + 0] = P[j][0];
-      q.out_points[3 * k + 1] = P[j][1];
-      q.out_points[3 * k + 2] = P[j][2];
-      if (q.out_corr_new) q.out_corr_new[k] = make_int2(c[j].y, (int)k);  // (idx_second, k) :97
-      if (q.out_src) q.out_src[k] = (int32_t)(warp_base + j * 32 + lane);
-      if (q.out_app) {  // :127 — the appearance travels with the point
-        const float2* src = reinterpret_cast<const float2*>(q.app2 + 10 * (int64_t)c[j].y);
-        float2* dst = reinterpret_cast<float2*>(q.out_app + 10 * k);
-#pragma unroll
-        for (int i = 0; i < 5; ++i) dst[i] = __ldg(src + i);
-      }
-    }
-  if (tile == q.num_tiles - 1 && threadIdx.x == 0) *q.n_success = excl + total;
+  if (pend_tile >= 0) {
+    __syncthreads();
+    retire(pend_slot, pend_tile, pend_total);
+  }
 }
 
 // ---- Camera::projectPoints -----------------------------------------------------------------------
@@ -256,7 +397,18 @@ static int tri_launch(cudaStream_t stream, const float K[9], const float X[16], 
   q.n_success = reinterpret_cast<long long*>(n_success);
   q.ws = scan_workspace_at(workspace, tiles);
   q.num_tiles = (int)tiles;
-  triangulate_kernel<TRI_THREADS, TRI_ITEMS><<<(unsigned)tiles, TRI_THREADS, 0, stream>>>(q);
+  // persistent blocks: as many as can be resident, each loops over dynamically claimed tiles
+  static int resident = 0;
+  if (resident == 0) {
+    int per_sm = 1, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, triangulate_kernel<TRI_THREADS, TRI_ITEMS>,
+                                                  TRI_THREADS, 0);
+    resident = (per_sm < 1 ? 1 : per_sm) * (sms < 1 ? 1 : sms);
+  }
+  const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
+  triangulate_kernel<TRI_THREADS, TRI_ITEMS><<<grid, TRI_THREADS, 0, stream>>>(q);
   VO_LAUNCH_CHECK();
   return VO_OK;
 }

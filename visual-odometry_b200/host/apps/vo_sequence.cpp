@@ -85,7 +85,9 @@ struct Robot {
   std::mt19937 rng;
   float target = 0.f;
   bool turning = false;
-  explicit Robot(unsigned seed) : rng(seed) {}
+  explicit Robot(unsigned seed) : rng(seed) {
+    if (const char* e = std::getenv("VO_SEQ_THETA0")) theta = (float)std::atof(e);
+  }
   static float wrap(float a) {
     while (a > 3.14159265f) a -= 6.2831853f;
     while (a < -3.14159265f) a += 6.2831853f;
