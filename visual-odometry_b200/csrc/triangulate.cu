@@ -125,8 +125,8 @@ __device__ __forceinline__ void triangulate_pair_dev(const f2_t (&d1)[3], const 
 //   2. parks the compacted results (points + second index) in one of two shared-memory slots and
 //      publishes the tile's count,
 //   3. and only then RETIRES THE PREVIOUS tile: by now its predecessors have had a whole tile time
-//      to publish, so the look-back (warp 0 only) returns at once, and the parked results stream
-//      out as fully coalesced stores.
+//      to publish, so the look-back (warp 0 only) rarely spins, and the parked results stream out
+//      as fully coalesced stores.
 // Item j of lane l of warp w sits at tile position w*32*ITEMS + j*32 + l, so every load of a warp
 // is a contiguous run.
 template <int THREADS, int ITEMS>
@@ -192,6 +192,8 @@ __global__ void __launch_bounds__(THREADS) triangulate_kernel(const TriParams q)
       a[j] = __ldg(q.p1 + c[j].x);  // .first  -> image 1   (utils.cpp:87)
       b[j] = __ldg(q.p2 + c[j].y);  // .second -> image 2   (utils.cpp:88)
     }
+    int claimed = 0;  // the tile after this one, claimed early so the atomic's latency is hidden too
+    if (tid == 0) claimed = (int)atomicAdd(q.ws.ticket, 1u);
     f2_t P[ITEMS / 2][3];
     bool ok[ITEMS];
 #pragma unroll
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(THREADS) triangulate_kernel(const TriParams q)
       run += __popc(bal);
     }
     if (lane == 0) s_warp_tot[warp] = run;
-    if (tid == 0) s_next = (int)atomicAdd(q.ws.ticket, 1u);  // the tile after this one
+    if (tid == 0) s_next = claimed;
     __syncthreads();
     int warp_off = 0, total = 0;
 #pragma unroll
@@ -252,8 +254,10 @@ __global__ void __launch_bounds__(THREADS) triangulate_kernel(const TriParams q)
         s_c2[slot][r] = c[j].y;
         s_src[slot][r] = (int)(warp_base + j * 32 + lane);
       }
-    // retire the previous tile (contains a barrier, which also orders this tile's parking
-    // before its own retirement in the next iteration)
+    // retire the previous tile now that this one is published: its predecessors have had a whole
+    // tile time to publish (measured: retiring it earlier, under this tile's load latency, brings
+    // the waiting back).  The barrier inside also orders this tile's parking before its own
+    // retirement in the next iteration.
     if (pend_tile >= 0) retire(pend_slot, pend_tile, pend_total);
     else __syncthreads();
     pend_tile = tile;
