@@ -411,6 +411,43 @@ def bench_triangulate(torch, vo, synth, args, cores):
     }
 
 
+def bench_vo_bundled(env):
+    """Config 1: the reference's vo_complete main, unchanged, on the bundled 121-frame sequence
+    (tests/golden/example_data.tar.gz): compiled against the drop-in host layer (GPU) and against
+    the reference's own sources (CPU).  Wall clock of the whole executable, text parsing included;
+    ~100 points per frame, so the GPU build is launch-latency-bound here by construction."""
+    import subprocess
+    import tarfile
+    import tempfile
+
+    gpu = os.path.join(ROOT, "visual-odometry_b200", "host", "bin", "vo_complete")
+    ref = os.path.join(ROOT, "oracle", "_ref", "bin", "vo_complete")
+    tar = os.path.join(ROOT, "tests", "golden", "example_data.tar.gz")
+    if not (os.path.exists(gpu) and os.path.exists(tar)):
+        return {"unavailable": "host/bin/vo_complete or the bundled fixture is missing"}
+    out = {"frames": 121}
+    with tempfile.TemporaryDirectory() as tmp:
+        with tarfile.open(tar) as tf:
+            tf.extractall(tmp)
+        data = None
+        for dirpath, _, files in os.walk(tmp):
+            if "camera.dat" in files:
+                data = dirpath
+        for name, exe in (("b200", gpu), ("reference_cpu", ref)):
+            if not os.path.exists(exe):
+                continue
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                subprocess.run([exe, data], cwd=tmp, env=env, stdout=subprocess.DEVNULL,
+                               stderr=subprocess.DEVNULL, check=True)
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            out[name + "_frames_per_s"] = 121 / best
+            out[name + "_wall_s"] = best
+    return out
+
+
 def bench_vo(torch, args, dist, rank, local, world):
     """Config 5: the vo_complete frame loop on independent synthetic sequences, ONE PER GPU
     (host/bin/vo_sequence, the reference-style C++ main running on the drop-in host layer over the
@@ -448,6 +485,8 @@ def bench_vo(torch, args, dist, rank, local, world):
         "e2e": {"value": frames / sec, "unit": "frames/s",
                 "note": "host frames in, host poses out every frame (the driver IS the host API)"},
     }
+    if rank == 0 and world == 1:
+        res["bundled"] = bench_vo_bundled(env)
     ref_exe = os.path.join(ROOT, "oracle", "_ref", "bin", "vo_sequence")
     if rank == 0 and world == 1 and os.path.exists(ref_exe):
         lm, fr = min(args.vo_landmarks, 10000), 6
