@@ -2,6 +2,7 @@
 // appearance, and the structure-of-arrays container the pipeline passes around.  Host-side data
 // structure; the GPU entry points read points() / appearances() in place.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -63,21 +64,43 @@ class PointCloudVector {
     if (!_index_valid || _indexed != _appearances.size()) rebuild_index();
     const PointsVec& new_points = cloud._points;
     const Vector10fVector& new_appearances = cloud._appearances;
-    for (size_t i = 0; i < new_points.size(); ++i) {
-      uint64_t h;
-      const bool comparable = hash_of(new_appearances[i], h);  // false: holds a NaN, equals nothing
-      if (comparable) {
-        if ((_appearances.size() + 1) * 2 > _slots.size()) rebuild_index();
-        const size_t slot = find_slot(new_appearances[i], h);
-        if (_slots[slot] != kEmpty) {
-          _points[_slots[slot]] = new_points[i];
-          continue;
-        }
-        _slots[slot] = (uint32_t)_appearances.size();
+    const size_t n = new_points.size();
+    // the table must not grow while slots are being prefetched: make room for the whole cloud
+    if ((_appearances.size() + n + 1) * 2 > _slots.size()) rebuild_index(n);
+    // Random probes into a multi-megabyte table are bound by memory latency, not by work: hash a
+    // block of new points first and prefetch their home slots, then prefetch the stored
+    // appearances those slots point at, and only then resolve the block in order.
+    constexpr size_t kBlock = 64;
+    uint64_t h[kBlock];
+    bool comparable[kBlock];
+    const size_t mask = _slots.size() - 1;
+    for (size_t b0 = 0; b0 < n; b0 += kBlock) {
+      const size_t bn = std::min(kBlock, n - b0);
+      for (size_t k = 0; k < bn; ++k) {
+        comparable[k] = hash_of(new_appearances[b0 + k], h[k]);  // false: holds a NaN, equals nothing
+        __builtin_prefetch(&_slots[(size_t)h[k] & mask]);
       }
-      _points.push_back(new_points[i]);
-      _appearances.push_back(new_appearances[i]);
-      _indexed = _appearances.size();
+      for (size_t k = 0; k < bn; ++k) {
+        const uint32_t j = _slots[(size_t)h[k] & mask];
+        if (comparable[k] && j != kEmpty) {
+          __builtin_prefetch(&_appearances[j]);
+          __builtin_prefetch(&_points[j], 1);
+        }
+      }
+      for (size_t k = 0; k < bn; ++k) {
+        const size_t i = b0 + k;
+        if (comparable[k]) {
+          const size_t slot = find_slot(new_appearances[i], h[k]);
+          if (_slots[slot] != kEmpty) {
+            _points[_slots[slot]] = new_points[i];
+            continue;
+          }
+          _slots[slot] = (uint32_t)_appearances.size();
+        }
+        _points.push_back(new_points[i]);
+        _appearances.push_back(new_appearances[i]);
+        _indexed = _appearances.size();
+      }
     }
   }
 
@@ -115,9 +138,9 @@ class PointCloudVector {
     while (_slots[s] != kEmpty && !(_appearances[_slots[s]] == a)) s = (s + 1) & mask;
     return s;
   }
-  void rebuild_index() {
+  void rebuild_index(size_t extra = 0) {
     size_t cap = 1024;
-    while (cap < 4 * (_appearances.size() + 1)) cap *= 2;
+    while (cap < 4 * (_appearances.size() + extra + 1)) cap *= 2;
     _slots.assign(cap, kEmpty);
     for (size_t j = 0; j < _appearances.size(); ++j) {
       uint64_t h;
