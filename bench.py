@@ -47,6 +47,33 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def measured_traffic(kernel, grid_prefix=None):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the latest
+    committed `ncu --set full` capture (profiles/*_traffic.json, written by tools/make_profiles.py
+    from the run recorded there); None when no capture of that kernel is committed."""
+    import glob
+
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+        try:
+            t = json.load(open(path)).get(kernel)
+        except Exception:
+            t = None
+        if t and (grid_prefix is None or str(t.get("grid", "")).startswith(grid_prefix)):
+            return {"bytes": t["dram_bytes"], "source": os.path.relpath(path, ROOT),
+                    "grid": t.get("grid")}
+    return None
+
+
+def traffic_fields(kernel, same_config):
+    """roofline.traffic (+ where it came from); null unless the committed capture was taken on the
+    configuration this run measures."""
+    t = measured_traffic(kernel) if same_config else None
+    if t is None:
+        return {"traffic": None}
+    return {"traffic": t["bytes"], "traffic_unit": "bytes/launch (ncu dram read+write)",
+            "traffic_source": t["source"]}
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -340,7 +367,8 @@ def bench_picp(torch, vo, synth, args, cores):
                 "h2d_bytes_per_step": int(28 * n_corr + 20 * (n_gen - n_corr)),
                 "d2h_bytes_per_step": 268},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                     "frac": achieved / hbm, "traffic": None,
+                     "frac": achieved / hbm, **traffic_fields("picp", n_gen == 10_000_000),
+                     "algorithmic_bytes_per_launch": PICP_BYTES_PER_CORR * n_corr,
                      "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         "cpu_baseline": {"value": len(sub) / cpu_dt, "unit": "point-iters/s", "cores": 1,
                          "kind": "port", "sample": f"1 round over {len(sub)} correspondences"},
@@ -403,7 +431,8 @@ def bench_triangulate(torch, vo, synth, args, cores):
                 "h2d_bytes_per_step": int(8 * nc + 16 * len(tv["p1"])),
                 "d2h_bytes_per_step": int(20 * ns + 8)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                     "frac": achieved / hbm, "traffic": None,
+                     "frac": achieved / hbm, **traffic_fields("tri", n == 10_000_000),
+                     "algorithmic_bytes_per_launch": TRI_BYTES_PER_CORR * nc,
                      "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         "cpu_baseline": {"value": len(sub) / cpu_dt, "unit": "correspondences/s", "cores": 1,
                          "kind": "port", "sample": f"{len(sub)} correspondences"},
@@ -628,7 +657,8 @@ def ours_arm(args):
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak,
-                         "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                         **traffic_fields("nn", M == 100_000_000 and Q == 100_000 and world == 1),
                          "peak_source": peak_src, "kernel": "nn_filter_kernel",
                          "algorithmic_flop_per_pair": NN_FLOP_PER_PAIR,
                          "nominal_fp32_tflops": NOMINAL_FP32_TFLOPS,

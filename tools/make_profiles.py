@@ -34,7 +34,21 @@ if os.path.exists(lc):
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:12]:
             f.write(f"| {n} | {t/1e6:.3f} | {100*t/tot:.1f} % | `{k}` |\n")
 
-for k in ("nn", "picp", "tri"):
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+traffic = {}
+for k in ("nn", "picp", "picpres", "tri"):
+    rep = os.path.join(G, f"{tag}_{k}.ncu-rep")
+    if not os.path.exists(rep): continue
+    raw = list(csv.reader(io.StringIO(run("ncu", "-i", rep, "--page", "raw", "--csv"))))
+    col = dict(zip(raw[0], zip(raw[1], raw[2])))
+    rd = float(col["dram__bytes_read.sum"][1]) * UNIT[col["dram__bytes_read.sum"][0]]
+    wr = float(col["dram__bytes_write.sum"][1]) * UNIT[col["dram__bytes_write.sum"][0]]
+    traffic[k] = {"kernel": col["Kernel Name"][1], "grid": col["Grid Size"][1],
+                  "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes": rd + wr,
+                  "gpu_time_ns_under_ncu": float(col["gpu__time_duration.sum"][1]) *
+                  {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}[col["gpu__time_duration.sum"][0]],
+                  "report": f"gpurun_out/{tag}_{k}.ncu-rep"}
+for k in ("nn", "picp", "picpres", "tri"):
     rep = os.path.join(G, f"{tag}_{k}.ncu-rep")
     if not os.path.exists(rep): continue
     out = [f"# {label}: `ncu --set full --clock-control none --import-source on` of the {k} kernel\n",
@@ -58,4 +72,7 @@ for k in ("nn", "picp", "tri"):
     out.append("## executed warp-instructions by opcode\n\n| opcode | warp-instructions | share |\n|---|---|---|\n" +
                "".join(f"| {o} | {v} | {100*v/tot:.1f} % |\n" for o, v in ops.most_common(14)))
     open(os.path.join(P, f"{label}_ncu_{k}.md"), "w").write("\n".join(out))
+if traffic:
+    import json
+    json.dump(traffic, open(os.path.join(P, f"{label}_traffic.json"), "w"), indent=1)
 print(sorted(os.listdir(P)))
