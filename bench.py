@@ -492,9 +492,17 @@ def bench_vo(torch, args, dist, rank, local, world):
     if not os.path.exists(exe):
         return {"unavailable": "host/bin/vo_sequence not built (needs the reference checkout at build time)"}
     env = dict(os.environ, VO_B200_DEVICE=str(local))
+    env.pop("VO_SEQ_MODE", None)  # default mode: the device-resident frame pipeline (vo_pipe_*)
     out = subprocess.run([exe, str(args.vo_landmarks), str(args.vo_frames), str(1000 + rank), "100"],
                          env=env, capture_output=True, text=True, check=True).stdout
     r = json.loads(out.strip().splitlines()[-1])
+    # the same frames through the drop-in classes (the reference's call surface, call by call)
+    rc = None
+    if rank == 0 and world == 1:
+        outc = subprocess.run([exe, str(args.vo_landmarks), str(min(args.vo_frames, 300)), "1000", "100"],
+                              env=dict(env, VO_SEQ_MODE="classes"), capture_output=True, text=True,
+                              check=True).stdout
+        rc = json.loads(outc.strip().splitlines()[-1])
     frames, sec = float(r["frames"]), r["loop_ms"] * 1e-3
     if dist is not None:
         t = torch.tensor([frames, sec], dtype=torch.float64, device="cuda")
@@ -508,12 +516,19 @@ def bench_vo(torch, args, dist, rank, local, world):
         "config": {"workload": f"batched vo_complete: {world} independent synthetic sequence(s) x "
                                f"{args.vo_frames} frames x {args.vo_landmarks} landmarks, one per GPU, "
                                "100 PICP rounds/frame"},
-        "rank0": {k: r[k] for k in ("frames_per_s", "stage_ms_per_frame", "mean_measurements",
+        "rank0": {k: r[k] for k in ("impl", "frames_per_s", "stage_ms_per_frame", "mean_measurements",
                                     "mean_correspondences", "map_points", "rot_err_mean_rad",
                                     "scale_first_pair", "scale_median")},
         "e2e": {"value": frames / sec, "unit": "frames/s",
-                "note": "host frames in, host poses out every frame (the driver IS the host API)"},
+                "h2d_bytes_per_step": int(44 * r["mean_measurements"]), "d2h_bytes_per_step": 64 + 268,
+                "note": "host frames in, host pose out every frame through vo_pipe_step (the "
+                        "driver IS the host API); one synchronisation per frame"},
     }
+    if rc is not None:
+        res["drop_in_classes"] = {"frames_per_s": rc["frames_per_s"], "frames": rc["frames"],
+                                  "stage_ms_per_frame": rc["stage_ms_per_frame"],
+                                  "note": "same frames through TreeNode_/PICPSolver/"
+                                          "triangulate_points/PointCloudVector, one call at a time"}
     if rank == 0 and world == 1:
         res["bundled"] = bench_vo_bundled(env)
     ref_exe = os.path.join(ROOT, "oracle", "_ref", "bin", "vo_sequence")

@@ -145,6 +145,13 @@ int vo_picp_set_correspondences_device(vo_picp_t h, const int32_t* pairs_dev, in
 /* `rounds` x oneRound on the uploaded correspondences, all on the device, no host
  * round-trip between rounds; asynchronous.                                                 */
 int vo_picp_compute(vo_picp_t h, int keep_outliers, int rounds);
+/* frame-pipeline variant of vo_picp_compute (<= 65536 correspondences, resident kernel only):
+ * n_pairs_dev (nullable) is a DEVICE int32 holding the actual number of uploaded pairs (the count
+ * passed to set_correspondences_device is then only an upper bound); pre_transform (nullable) is
+ * a column-major 4x4 isometry applied to every world point while it is gathered — the
+ * `X_curr * triangulated_pc` of vo_complete.cpp:154 without a pass over the cloud.              */
+int vo_picp_compute_ex(vo_picp_t h, int keep_outliers, int rounds, const int32_t* n_pairs_dev,
+                       const float* pre_transform);
 /* convenience == set_correspondences + compute                                             */
 int vo_picp_one_round(vo_picp_t h, const int32_t* pairs_host, int64_t n_pairs,
                       int keep_outliers);
@@ -177,6 +184,14 @@ int vo_triangulate_device(void* cuda_stream, const float K[9], const float X[16]
                           int32_t* out_corr_new_dev, float* out_app_dev, int32_t* out_src_dev,
                           int64_t* n_success_dev, void* workspace_dev);
 
+/* as vo_triangulate_device, with the number of correspondences read from DEVICE memory
+ * (n_corr_dev, int32); n_corr_max bounds it and sizes the workspace.                        */
+int vo_triangulate_device_ex(void* cuda_stream, const float K[9], const float X[16],
+                             const int32_t* corr_dev, int64_t n_corr_max, const int32_t* n_corr_dev,
+                             const float* p1_dev, const float* p2_dev, const float* app2_dev,
+                             float* out_points_dev, int32_t* out_corr_new_dev, float* out_app_dev,
+                             int64_t* n_success_dev, void* workspace_dev);
+
 /* ==== (4) batch projection =============================================================
  * replaces Camera::projectPoints   src/camera.cpp:16-37
  * keep_indices != 0: out_image has n_points entries, invalid ones are (-1,-1);
@@ -185,6 +200,52 @@ int vo_triangulate_device(void* cuda_stream, const float K[9], const float X[16]
 int vo_project_points(int device, const vo_camera* cam, const float* world_host,
                       int64_t n_points, int keep_indices, float* out_image_host,
                       int64_t* n_out, int64_t* n_inside);
+
+/* ==== (5) device-resident frame loop ====================================================
+ * replaces the loop body of src/apps/vo_complete.cpp:150-178 — compute_correspondences_images
+ * (:12-48), extract_correspondences_world (:51-66), operator*(Isometry3f, PointCloudVector)
+ * (PointCloud.h:77-82), PICPSolver::init + 100 x oneRound, triangulate_points (point-cloud
+ * overload) and PointCloudVector::update (PointCloud.h:52-66) — with the frames, the match
+ * lists, the triangulated cloud and the map resident on the device.  Per frame only the new
+ * measurements go up and the pose comes down.  Epipolar initialisation stays on the host:
+ *   vo_pipe_first_frame(f0); vo_pipe_second_frame(f1, corr, &n);   // appearance matches of (f0,f1)
+ *   X = estimate_transform(K, corr, ...)  (host);  vo_pipe_bootstrap(X);
+ *   for every further frame: vo_pipe_step(...)
+ * A frame is n measurements: points (2 floats each) and appearances (10 floats each).          */
+typedef struct vo_pipe_s* vo_pipe_t;
+
+typedef struct vo_pipe_result {
+  float T[16];               /* pose of the previous camera in the current one (column-major)  */
+  int64_t n_measurements;    /* of this frame                                                   */
+  int64_t n_matches;         /* appearance matches with the previous frame                      */
+  int64_t n_correspondences; /* matches that also have a triangulated point (PICP input)        */
+  int64_t map_points;        /* map size after the PREVIOUS frame's merge                       */
+  float chi_inliers;
+  int32_t n_inliers;
+  int32_t map_overflow;      /* != 0: max_map_points was reached, later points were dropped     */
+} vo_pipe_result;
+
+int vo_pipe_create(vo_pipe_t* out, int device, const vo_camera* cam, int64_t max_points_per_frame,
+                   int64_t max_map_points);
+int vo_pipe_destroy(vo_pipe_t h);
+int vo_pipe_first_frame(vo_pipe_t h, const float* points_host, const float* app_host, int64_t n);
+/* uploads the second frame and returns the (first, second) index pairs of the appearance
+ * matches (corr_host: int32 pairs, capacity >= min(n0, n1); nullable)                          */
+int vo_pipe_second_frame(vo_pipe_t h, const float* points_host, const float* app_host, int64_t n,
+                         int32_t* corr_host, int64_t* n_corr);
+/* X: pose of the first camera in the second (what estimate_transform returns); triangulates the
+ * first pair, starts the map                                                                   */
+int vo_pipe_bootstrap(vo_pipe_t h, const float X[16]);
+/* one frame of the loop; synchronises once, to return the pose                                 */
+int vo_pipe_step(vo_pipe_t h, const float* points_host, const float* app_host, int64_t n, int rounds,
+                 float kernel_threshold, vo_pipe_result* out);
+/* PointCloudVector::update (PointCloud.h:52-66) on the device map, for a host cloud moved by X:
+ * a point whose appearance is already stored (float ==, first hit) replaces that position, every
+ * other point is appended in order; appended points take part in the matching of later ones.   */
+int vo_pipe_merge_cloud(vo_pipe_t h, const float* points_host, const float* app_host, int64_t n,
+                        const float X[16]);
+/* the global map in `history` coordinates (vo_complete.cpp applies cam_transform afterwards)   */
+int vo_pipe_get_map(vo_pipe_t h, float* points_host, float* app_host, int64_t capacity, int64_t* n);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,108 @@
+"""GPU: the device-resident frame pipeline (include/vo_b200.h §5, csrc/pipeline.cu).
+ * vo_pipe_merge_cloud == PointCloudVector::update (reference include/PointCloud.h:52-66): first
+   equal appearance is overwritten, else append in order; appended points take part in later
+   matches; float equality (-0.0 == +0.0, NaN equals nothing).
+ * the whole loop against the CPU reference is in tests/test_dropin_gpu.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def reference_update(map_pts, map_app, pts, app):
+    """the reference's sequential semantics, restated"""
+    for p, a in zip(pts, app):
+        hit = None
+        for j, b in enumerate(map_app):
+            if np.all(b == a):  # float ==: NaN never equal, -0.0 == 0.0
+                hit = j
+                break
+        if hit is None:
+            map_pts.append(p.copy())
+            map_app.append(a.copy())
+        else:
+            map_pts[hit] = p.copy()
+
+
+def _pipe(vo, max_pts=4096, max_map=5000):
+    abi = vo._abi if hasattr(vo, "_abi") else __import__("importlib").import_module("visual-odometry_b200._abi")
+    lib = vo.lib()
+    cam = abi.vo_camera()
+    cam.rows, cam.cols, cam.z_near, cam.z_far = 480, 640, 0, 5
+    K = np.array([[180, 0, 320], [0, 180, 240], [0, 0, 1]], np.float32)
+    for j in range(3):
+        for i in range(3):
+            cam.K[j * 3 + i] = K[i, j]
+    for i in range(16):
+        cam.T[i] = 1.0 if i % 5 == 0 else 0.0
+    h = C.c_void_p()
+    assert lib.vo_pipe_create(C.byref(h), 0, C.byref(cam), max_pts, max_map) == 0, lib.vo_last_error()
+    return lib, h
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_map_merge_matches_sequential_semantics(vo):
+    lib, h = _pipe(vo)
+    rng = np.random.RandomState(3)
+    pool = rng.uniform(-1, 1, (300, 10)).astype(np.float32)
+    pool[10] = pool[3]                      # exact duplicate appearance
+    pool[20, 4], pool[21] = 0.0, pool[20]   # +0 / -0 twins
+    pool[21, 4] = -0.0
+    pool[30, 7] = np.nan                    # equals nothing, not even itself
+    ref_pts, ref_app = [], []
+    for call in range(25):
+        n = int(rng.randint(1, 400))
+        ids = rng.randint(0, 300, n)
+        if call % 5 == 0:
+            ids[: n // 2] = ids[n // 2: n // 2 + n // 2][: n // 2]  # many repeats inside one call
+        app = pool[ids].copy()
+        pts = rng.uniform(-5, 5, (n, 3)).astype(np.float32)
+        th = 0.1 * call
+        X = np.eye(4, dtype=np.float32)
+        X[:3, :3] = [[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]]
+        X[:3, 3] = [0.3 * call, -0.1, 0.05]
+        Xc = np.ascontiguousarray(X.T).reshape(-1)  # column-major
+        assert lib.vo_pipe_merge_cloud(h, _p(pts), _p(app), n, Xc.ctypes.data_as(C.POINTER(C.c_float))) == 0
+        moved = (pts.astype(np.float64) @ X[:3, :3].T.astype(np.float64) + X[:3, 3]).astype(np.float32)
+        reference_update(ref_pts, ref_app, moved, app)
+    cap = 6000
+    got_pts = np.zeros((cap, 3), np.float32)
+    got_app = np.zeros((cap, 10), np.float32)
+    n_map = C.c_int64(0)
+    assert lib.vo_pipe_get_map(h, _p(got_pts), _p(got_app), cap, C.byref(n_map)) == 0
+    lib.vo_pipe_destroy(h)
+    assert n_map.value == len(ref_app)
+    ra, rp = np.array(ref_app), np.array(ref_pts)
+    ga, gp = got_app[: n_map.value], got_pts[: n_map.value]
+    assert np.array_equal(np.isnan(ga), np.isnan(ra))
+    assert np.array_equal(np.nan_to_num(ga), np.nan_to_num(ra))  # same appearances in the same order
+    assert np.abs(gp - rp).max() <= 1e-5 * max(1.0, np.abs(rp).max())
+
+
+def test_map_overflow_is_reported_not_fatal(vo):
+    lib, h = _pipe(vo, max_pts=1024, max_map=100)
+    rng = np.random.RandomState(4)
+    app = rng.uniform(-1, 1, (300, 10)).astype(np.float32)
+    pts = rng.uniform(-1, 1, (300, 3)).astype(np.float32)
+    X = np.eye(4, dtype=np.float32).reshape(-1)
+    assert lib.vo_pipe_merge_cloud(h, _p(pts), _p(app), 300, X.ctypes.data_as(C.POINTER(C.c_float))) == 0
+    n_map = C.c_int64(0)
+    assert lib.vo_pipe_get_map(h, None, None, 0, C.byref(n_map)) == 0
+    assert n_map.value == 100
+    lib.vo_pipe_destroy(h)
+
+
+def test_call_order_is_enforced(vo):
+    lib, h = _pipe(vo)
+    res = (C.c_byte * 256)()
+    pts = np.zeros((4, 2), np.float32)
+    app = np.zeros((4, 10), np.float32)
+    assert lib.vo_pipe_step(h, _p(pts), _p(app), 4, 10, C.c_float(1e4), C.byref(res)) == -4  # VO_ERR_STATE
+    X = np.eye(4, dtype=np.float32).reshape(-1)
+    assert lib.vo_pipe_bootstrap(h, X.ctypes.data_as(C.POINTER(C.c_float))) == -4
+    lib.vo_pipe_destroy(h)

@@ -80,6 +80,7 @@ PROTOTYPES = {
     "vo_picp_set_correspondences": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "vo_picp_set_correspondences_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "vo_picp_compute": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "vo_picp_compute_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, c_f32p]),
     "vo_picp_one_round": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     "vo_picp_get_state": (C.c_int, [C.c_void_p, C.POINTER(vo_picp_state)]),
     "vo_triangulate": (
@@ -93,6 +94,22 @@ PROTOTYPES = {
         [C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     ),
+    "vo_triangulate_device_ex": (
+        C.c_int,
+        [C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "vo_pipe_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(vo_camera), C.c_int64,
+                                 C.c_int64]),
+    "vo_pipe_destroy": (C.c_int, [C.c_void_p]),
+    "vo_pipe_first_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "vo_pipe_second_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                       c_i64p]),
+    "vo_pipe_bootstrap": (C.c_int, [C.c_void_p, c_f32p]),
+    "vo_pipe_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float,
+                               C.c_void_p]),
+    "vo_pipe_merge_cloud": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, c_f32p]),
+    "vo_pipe_get_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, c_i64p]),
     "vo_project_points": (
         C.c_int,
         [C.c_int, C.POINTER(vo_camera), C.c_void_p, C.c_int64, C.c_int, C.c_void_p, c_i64p, c_i64p],

@@ -78,6 +78,18 @@ struct DevBuf {
 
 int num_sms(int device);
 
+// After cudaMemcpyAsync FROM `host_ptr`: may the caller reuse / free the buffer without a stream
+// synchronisation?  A copy from pageable memory has been staged by the runtime when the call
+// returns; only a copy from pinned (or managed) memory is still reading the caller's buffer.
+inline bool host_source_still_in_use(const void* host_ptr) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host_ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return true;  // unknown: be safe
+  }
+  return a.type != cudaMemoryTypeUnregistered;
+}
+
 // ---- device-side PTX wrappers (TMA bulk copy + mbarrier) ----------------------------------
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -712,7 +712,7 @@ int vo_nn_set_map(vo_nn_t h, const float* rows_host, int64_t n_rows, int row_str
   rc = nn_set_map_common(h, h->raw.as<float>(), n_rows, row_stride, skip_cols);
   if (rc) return rc;
   // the host buffer may be freed by the caller as soon as we return
-  VO_CUDA(cudaStreamSynchronize(h->stream));
+  if (bytes && host_source_still_in_use(rows_host)) VO_CUDA(cudaStreamSynchronize(h->stream));
   return VO_OK;
 }
 

@@ -54,6 +54,10 @@ struct PicpParams {
   int keep_outliers;
   PicpDeviceState* st;
   float* partials;                   // [gridDim.x][PICP_NACC]
+  // frame-pipeline extensions (resident kernel only)
+  const int* n_pairs_dev;            // if set: the correspondence count lives on the device
+  int has_pre;                       // if set: world points are moved by `pre` while gathered
+  float pre[12];                     //   3x3 linear (column-major) then translation
 };
 
 // oneRound's tail (picp_solver.cpp:102-110), executed by one thread of the last block.
@@ -621,7 +625,7 @@ picp_resident_kernel(const PicpParams p, const int rounds) {
   __shared__ float s_T[12];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int n = (int)p.n_pairs;
+  const int n = p.n_pairs_dev ? min(*p.n_pairs_dev, (int)p.n_pairs) : (int)p.n_pairs;
   const int nslots = (n + 1) >> 1;
   const int per = (nslots + csize - 1) / csize;  // <= PICP_RES_SLOTS (host guarantees)
   const int q0 = rank * per;
@@ -637,9 +641,21 @@ picp_resident_kernel(const PicpParams p, const int rounds) {
     const float* w1 = p.world + 3 * (int64_t)pr1.y;
     const float2 m0 = __ldg(reinterpret_cast<const float2*>(p.image) + pr0.x);  // .first -> image
     const float2 m1 = __ldg(reinterpret_cast<const float2*>(p.image) + pr1.x);
-    pts[0 * PICP_RES_SLOTS + ql] = f2_pack(__ldg(w0), __ldg(w1));
-    pts[1 * PICP_RES_SLOTS + ql] = f2_pack(__ldg(w0 + 1), __ldg(w1 + 1));
-    pts[2 * PICP_RES_SLOTS + ql] = f2_pack(__ldg(w0 + 2), __ldg(w1 + 2));
+    float x0 = __ldg(w0), y0 = __ldg(w0 + 1), z0 = __ldg(w0 + 2);
+    float x1 = __ldg(w1), y1 = __ldg(w1 + 1), z1 = __ldg(w1 + 2);
+    if (p.has_pre) {  // operator*(Isometry3f, PointCloudVector<3>) folded into the gather
+      const float* X = p.pre;
+      const float a0 = X[0] * x0 + (X[3] * y0 + X[6] * z0) + X[9];
+      const float b0 = X[1] * x0 + (X[4] * y0 + X[7] * z0) + X[10];
+      const float c0 = X[2] * x0 + (X[5] * y0 + X[8] * z0) + X[11];
+      const float a1 = X[0] * x1 + (X[3] * y1 + X[6] * z1) + X[9];
+      const float b1 = X[1] * x1 + (X[4] * y1 + X[7] * z1) + X[10];
+      const float c1 = X[2] * x1 + (X[5] * y1 + X[8] * z1) + X[11];
+      x0 = a0, y0 = b0, z0 = c0, x1 = a1, y1 = b1, z1 = c1;
+    }
+    pts[0 * PICP_RES_SLOTS + ql] = f2_pack(x0, x1);
+    pts[1 * PICP_RES_SLOTS + ql] = f2_pack(y0, y1);
+    pts[2 * PICP_RES_SLOTS + ql] = f2_pack(z0, z1);
     pts[3 * PICP_RES_SLOTS + ql] = f2_pack(m0.x, m1.x);
     pts[4 * PICP_RES_SLOTS + ql] = f2_pack(m0.y, m1.y);
   }
@@ -796,6 +812,9 @@ static int picp_fill_params(vo_picp_s* h, int keep_outliers, PicpParams* p) {
   p->keep_outliers = keep_outliers ? 1 : 0;
   p->st = h->state_buf.as<PicpDeviceState>();
   p->partials = h->partials_buf.as<float>();
+  p->n_pairs_dev = nullptr;
+  p->has_pre = 0;
+  memset(p->pre, 0, sizeof(p->pre));
   return VO_OK;
 }
 
@@ -912,7 +931,8 @@ int vo_picp_init(vo_picp_t h, const vo_camera* cam, const float* world_host, int
   rc = picp_init_common(h, cam, n_world, n_image);
   if (rc) return rc;
   // the reference borrows the vectors; we own a copy, so the caller may reuse them right away
-  VO_CUDA(cudaStreamSynchronize(h->stream));
+  if ((n_world && host_source_still_in_use(world_host)) || (n_image && host_source_still_in_use(image_host)))
+    VO_CUDA(cudaStreamSynchronize(h->stream));
   return VO_OK;
 }
 
@@ -948,7 +968,7 @@ int vo_picp_set_correspondences(vo_picp_t h, const int32_t* pairs_host, int64_t 
   if (n_pairs)
     VO_CUDA(cudaMemcpyAsync(h->pairs_buf.p, pairs_host, (size_t)n_pairs * 8,
                             cudaMemcpyHostToDevice, h->stream));
-  VO_CUDA(cudaStreamSynchronize(h->stream));
+  if (n_pairs && host_source_still_in_use(pairs_host)) VO_CUDA(cudaStreamSynchronize(h->stream));
   h->pairs = h->pairs_buf.as<int32_t>();
   h->n_pairs = n_pairs;
   return VO_OK;
@@ -965,10 +985,14 @@ int vo_picp_set_correspondences_device(vo_picp_t h, const int32_t* pairs_dev, in
   return VO_OK;
 }
 
-int vo_picp_compute(vo_picp_t h, int keep_outliers, int rounds) {
+static int picp_compute_common(vo_picp_t h, int keep_outliers, int rounds, const int32_t* n_pairs_dev,
+                               const float* pre_transform) {
   VO_REQUIRE(h != nullptr, VO_ERR_ARG, "null handle");
   VO_REQUIRE(h->have_cam, VO_ERR_STATE, "init not called");
   VO_REQUIRE(rounds >= 0, VO_ERR_ARG, "negative rounds");
+  const bool extended = n_pairs_dev != nullptr || pre_transform != nullptr;
+  VO_REQUIRE(!extended || (h->n_pairs <= PICP_RES_MAX && !h->force_stream), VO_ERR_UNSUPPORTED,
+             "device-side count / pre-transform need the resident kernel (<= 65536 correspondences)");
   if (rounds == 0) return VO_OK;
   DeviceGuard g(h->device);
   if (!h->smem_opted_in) {  // the staging ring needs the opt-in shared-memory carve-out (per device)
@@ -987,6 +1011,12 @@ int vo_picp_compute(vo_picp_t h, int keep_outliers, int rounds) {
   if (rc) return rc;
   PicpParams p;
   picp_fill_params(h, keep_outliers, &p);
+  p.n_pairs_dev = n_pairs_dev;
+  if (pre_transform) {
+    p.has_pre = 1;
+    for (int j = 0; j < 4; ++j)
+      for (int i = 0; i < 3; ++i) p.pre[j * 3 + i] = pre_transform[j * 4 + i];
+  }
 
   // K == [fx 0 cx; 0 fy cy; 0 0 1] exactly -> the structurally-sparse instantiation
   const float* K = h->cam.K;
@@ -1057,6 +1087,15 @@ int vo_picp_compute(vo_picp_t h, int keep_outliers, int rounds) {
   VO_CUDA(cudaGraphLaunch(it->second, h->stream));
   g_launches.fetch_add(rounds);
   return VO_OK;
+}
+
+int vo_picp_compute(vo_picp_t h, int keep_outliers, int rounds) {
+  return picp_compute_common(h, keep_outliers, rounds, nullptr, nullptr);
+}
+
+int vo_picp_compute_ex(vo_picp_t h, int keep_outliers, int rounds, const int32_t* n_pairs_dev,
+                       const float* pre_transform) {
+  return picp_compute_common(h, keep_outliers, rounds, n_pairs_dev, pre_transform);
 }
 
 int vo_picp_one_round(vo_picp_t h, const int32_t* pairs_host, int64_t n_pairs, int keep_outliers) {

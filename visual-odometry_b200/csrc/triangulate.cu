@@ -31,7 +31,8 @@ struct TriParams {
   float iRiK[9];  // X^-1.linear() * K^-1      (utils.cpp:55)
   float t[3];     // X^-1.translation()        (utils.cpp:56)
   const int2* __restrict__ corr;
-  int64_t n_corr;
+  int64_t n_corr;                  // count, or its upper bound when n_corr_dev is set
+  const int* n_corr_dev;           // frame pipeline: the count lives on the device
   const float2* __restrict__ p1;
   const float2* __restrict__ p2;
   const float* __restrict__ app2;  // nullable, 10 floats / point
@@ -141,6 +142,12 @@ __global__ void __launch_bounds__(THREADS) triangulate_kernel(const TriParams q)
   __shared__ int s_warp_tot[WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float t[3] = {q.t[0], q.t[1], q.t[2]};
+  const int64_t n_corr = q.n_corr_dev ? min((int64_t)*q.n_corr_dev, q.n_corr) : q.n_corr;
+  const int num_tiles = (int)((n_corr + TILE - 1) / TILE);
+  if (n_corr == 0) {
+    if (blockIdx.x == 0 && tid == 0) *q.n_success = 0;
+    return;
+  }
 
   // write-out of a parked tile: prefix of everything before it, then coalesced copies
   auto retire = [&](int slot, int tile, int total) {
@@ -168,14 +175,14 @@ __global__ void __launch_bounds__(THREADS) triangulate_kernel(const TriParams q)
 #pragma unroll
         for (int i = 0; i < 5; ++i) o[i] = __ldg(src + i);
       }
-    if (tile == q.num_tiles - 1 && tid == 0) *q.n_success = excl + total;
+    if (tile == num_tiles - 1 && tid == 0) *q.n_success = excl + total;
   };
 
   int pend_tile = -1, pend_total = 0, pend_slot = 0, slot = 0;
   if (tid == 0) s_next = (int)atomicAdd(q.ws.ticket, 1u);
   __syncthreads();
   int tile = s_next;
-  while (tile < q.num_tiles) {
+  while (tile < num_tiles) {
     const int64_t warp_base = (int64_t)tile * TILE + (int64_t)warp * (32 * ITEMS);
     // out-of-range slots of the last tile re-read the last correspondence and are masked out
     int2 c[ITEMS];
@@ -183,8 +190,8 @@ __global__ void __launch_bounds__(THREADS) triangulate_kernel(const TriParams q)
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
       const int64_t i = warp_base + j * 32 + lane;
-      in[j] = i < q.n_corr;
-      c[j] = __ldg(q.corr + (in[j] ? i : q.n_corr - 1));
+      in[j] = i < n_corr;
+      c[j] = __ldg(q.corr + (in[j] ? i : n_corr - 1));
     }
     float2 a[ITEMS], b[ITEMS];
 #pragma unroll
@@ -378,7 +385,7 @@ static void tri_precompute(const float K[9], const float X[16], TriParams* q) {
 static int tri_launch(cudaStream_t stream, const float K[9], const float X[16], const int32_t* corr,
                       int64_t n, const float* p1, const float* p2, const float* app2, float* out_pts,
                       int32_t* out_corr_new, float* out_app, int32_t* out_src, int64_t* n_success,
-                      void* workspace) {
+                      void* workspace, const int32_t* n_corr_dev = nullptr) {
   const int tile_items = TRI_TILE;
   const int64_t tiles = (n + tile_items - 1) / tile_items;
   VO_REQUIRE(tiles < (1LL << 31), VO_ERR_UNSUPPORTED, "too many correspondences");
@@ -391,6 +398,7 @@ static int tri_launch(cudaStream_t stream, const float K[9], const float X[16], 
   tri_precompute(K, X, &q);
   q.corr = reinterpret_cast<const int2*>(corr);
   q.n_corr = n;
+  q.n_corr_dev = n_corr_dev;
   q.p1 = reinterpret_cast<const float2*>(p1);
   q.p2 = reinterpret_cast<const float2*>(p2);
   q.app2 = app2;
@@ -452,6 +460,20 @@ int vo_triangulate_device(void* cuda_stream, const float K[9], const float X[16]
   return tri_launch(static_cast<cudaStream_t>(cuda_stream), K, X, corr_dev, n_corr, p1_dev, p2_dev,
                     app2_dev, out_points_dev, out_corr_new_dev, out_app_dev, out_src_dev,
                     n_success_dev, workspace_dev);
+}
+
+int vo_triangulate_device_ex(void* cuda_stream, const float K[9], const float X[16],
+                             const int32_t* corr_dev, int64_t n_corr_max, const int32_t* n_corr_dev,
+                             const float* p1_dev, const float* p2_dev, const float* app2_dev,
+                             float* out_points_dev, int32_t* out_corr_new_dev, float* out_app_dev,
+                             int64_t* n_success_dev, void* workspace_dev) {
+  VO_REQUIRE(K && X && n_success_dev && n_corr_dev, VO_ERR_ARG, "null pointer");
+  VO_REQUIRE(n_corr_max >= 0, VO_ERR_ARG, "negative size");
+  VO_REQUIRE(n_corr_max == 0 || (corr_dev && p1_dev && p2_dev && out_points_dev && workspace_dev),
+             VO_ERR_ARG, "null pointer");
+  return tri_launch(static_cast<cudaStream_t>(cuda_stream), K, X, corr_dev, n_corr_max, p1_dev, p2_dev,
+                    app2_dev, out_points_dev, out_corr_new_dev, out_app_dev, nullptr, n_success_dev,
+                    workspace_dev, n_corr_dev);
 }
 
 int vo_triangulate(int device, const float K[9], const float X[16], const int32_t* corr_host,

@@ -16,6 +16,8 @@
 // landmark's appearance copied verbatim.  Frames are generated on the fly, outside the timed region.
 //
 //   vo_sequence <n_landmarks> <n_frames> [seed=1000] [rounds=100] [pose_dump_file]
+//   env: VO_SEQ_MODE=classes (GPU build: use the drop-in classes instead of the resident pipeline),
+//        VO_SEQ_MAPDUMP=<file> (write the final map), VO_SEQ_LOG=1, VO_SEQ_THETA0=<rad>
 // prints one JSON line (frames/s over the frame loop, per-stage milliseconds, accuracy vs GT).
 #include <algorithm>
 #include <chrono>
@@ -185,6 +187,117 @@ float rotation_angle(const Eigen::Matrix3f& R) {
   return std::asin(std::min(1.f, s));
 }
 
+
+void dump_map(const char* path, const Vector3fVector& pts) {
+  FILE* f = std::fopen(path, "w");
+  if (!f) return;
+  for (const auto& p : pts) std::fprintf(f, "%.9g %.9g %.9g\n", p.x(), p.y(), p.z());
+  std::fclose(f);
+}
+
+#ifdef VO_B200_DROPIN
+// The same loop through the device-resident frame pipeline (vo_pipe_*, include/vo_b200.h §5):
+// only the measurements go up and the pose comes down; matches, join, cloud and map stay on the GPU.
+int run_pipeline(int n_landmarks, int n_frames, unsigned seed, int rounds, const std::string& dump) {
+  Eigen::Matrix3f k;
+  k << 180.f, 0.f, 320.f, 0.f, 180.f, 240.f, 0.f, 0.f, 1.f;
+  Camera synth_cam(480, 640, 0, 5, k);
+  const World world = make_world(n_landmarks, seed);
+  Robot robot(seed + 7u);
+  Frame reference = observe(world, synth_cam, robot);
+  robot.step();
+  Frame current = observe(world, synth_cam, robot);
+
+  vo_camera cam;
+  cam.rows = 480, cam.cols = 640, cam.z_near = 0, cam.z_far = 5;
+  vo_b200::pack3(k, cam.K);
+  vo_b200::pack_iso(Eigen::Isometry3f::Identity(), cam.T);
+  vo_pipe_t pipe = nullptr;
+  vo_b200::check(vo_pipe_create(&pipe, vo_b200::device(), &cam, 32768, (int64_t)n_landmarks + 4096),
+                 "vo_pipe_create");
+  auto pts = [](Frame& f) { return f.pc.size() ? f.pc.points()[0].data() : nullptr; };
+  auto app = [](Frame& f) { return f.pc.size() ? f.pc.appearances()[0].data() : nullptr; };
+
+  auto t0 = Clock::now();
+  vo_b200::check(vo_pipe_first_frame(pipe, pts(reference), app(reference), (int64_t)reference.pc.size()),
+                 "vo_pipe_first_frame");
+  IntPairVector corr(std::min(reference.pc.size(), current.pc.size()) + 1);
+  int64_t n_corr = 0;
+  vo_b200::check(vo_pipe_second_frame(pipe, pts(current), app(current), (int64_t)current.pc.size(),
+                                      &corr[0].first, &n_corr),
+                 "vo_pipe_second_frame");
+  corr.resize((size_t)n_corr);
+  const Eigen::Isometry3f X0 = estimate_transform(k, corr, reference.pc.points(), current.pc.points());
+  float Xf[16];
+  vo_b200::pack_iso(X0, Xf);
+  vo_b200::check(vo_pipe_bootstrap(pipe, Xf), "vo_pipe_bootstrap");
+  const Eigen::Isometry3f gt0 = current.world_in_camera * reference.world_in_camera.inverse();
+  const float scale = X0.translation().norm() / std::max(1e-12f, gt0.translation().norm());
+  Eigen::Isometry3f gt_prev = current.world_in_camera;
+  const double t_init = ms_since(t0);
+
+  std::vector<double> rot_err, ratio;
+  long long sum_corr = 0, sum_meas = 0;
+  FILE* fd = dump.empty() ? nullptr : std::fopen(dump.c_str(), "w");
+  double loop_ms = 0;
+  int frames_done = 0, overflow = 0;
+  for (int f = 2; f < n_frames; ++f) {
+    robot.step();
+    current = observe(world, synth_cam, robot);  // not timed: stands for the sensor
+    const auto tf = Clock::now();
+    vo_pipe_result res;
+    vo_b200::check(vo_pipe_step(pipe, pts(current), app(current), (int64_t)current.pc.size(), rounds,
+                                10000.f, &res),
+                   "vo_pipe_step");
+    loop_ms += ms_since(tf);
+    ++frames_done;
+    overflow |= res.map_overflow;
+    sum_corr += res.n_correspondences;
+    sum_meas += res.n_measurements;
+    Eigen::Isometry3f X_curr = Eigen::Isometry3f::Identity();
+    vo_b200::unpack_iso(res.T, X_curr);
+    const Eigen::Isometry3f gt = current.world_in_camera * gt_prev.inverse();
+    const Eigen::Matrix3f dR = X_curr.linear().transpose() * gt.linear();
+    rot_err.push_back(rotation_angle(dR));
+    ratio.push_back(X_curr.translation().norm() / std::max(1e-12f, gt.translation().norm()));
+    if (fd) {
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 4; ++c) std::fprintf(fd, "%.9g ", X_curr(r, c));
+      std::fprintf(fd, "\n");
+    }
+    gt_prev = current.world_in_camera;
+  }
+  if (fd) std::fclose(fd);
+  // the map (synchronises with the last frame's asynchronous merge; inside the timed total)
+  const auto tm = Clock::now();
+  Vector3fVector map_pts((size_t)n_landmarks + 4096);
+  int64_t n_map = 0;
+  vo_b200::check(vo_pipe_get_map(pipe, map_pts[0].data(), nullptr, (int64_t)map_pts.size(), &n_map),
+                 "vo_pipe_get_map");
+  loop_ms += ms_since(tm);
+  map_pts.resize((size_t)n_map);
+  if (const char* mp = std::getenv("VO_SEQ_MAPDUMP")) dump_map(mp, map_pts);
+  vo_pipe_destroy(pipe);
+
+  double rot_mean = 0;
+  for (double e : rot_err) rot_mean += e;
+  rot_mean /= std::max<size_t>(1, rot_err.size());
+  std::sort(ratio.begin(), ratio.end());
+  const double ratio_med = ratio.empty() ? 0 : ratio[ratio.size() / 2];
+  std::printf(
+      "{\"impl\": \"b200-pipeline\", \"landmarks\": %d, \"frames\": %d, \"rounds\": %d, \"seed\": %u, "
+      "\"loop_ms\": %.3f, \"frames_per_s\": %.3f, \"init_ms\": %.3f, "
+      "\"stage_ms_per_frame\": {\"step\": %.4f}, "
+      "\"mean_measurements\": %.1f, \"mean_correspondences\": %.1f, \"map_points\": %lld, "
+      "\"map_overflow\": %d, "
+      "\"rot_err_mean_rad\": %.3e, \"scale_first_pair\": %.6f, \"scale_median\": %.6f}\n",
+      n_landmarks, frames_done, rounds, seed, loop_ms, frames_done / (loop_ms * 1e-3), t_init,
+      loop_ms / frames_done, double(sum_meas) / frames_done, double(sum_corr) / frames_done,
+      (long long)n_map, overflow, rot_mean, (double)scale, ratio_med);
+  return 0;
+}
+#endif
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -200,6 +313,12 @@ int main(int argc, char** argv) {
     std::fprintf(stderr, "need at least 3 frames\n");
     return 2;
   }
+#ifdef VO_B200_DROPIN
+  // VO_SEQ_MODE=classes: through the drop-in classes (the reference's call surface, one call at a
+  // time); default: the device-resident frame pipeline
+  const char* mode = std::getenv("VO_SEQ_MODE");
+  if (!(mode && std::string(mode) == "classes")) return run_pipeline(n_landmarks, n_frames, seed, rounds, dump);
+#endif
 
   Eigen::Matrix3f k;
   k << 180.f, 0.f, 320.f, 0.f, 180.f, 240.f, 0.f, 0.f, 1.f;
@@ -254,6 +373,7 @@ int main(int argc, char** argv) {
     const PointCloudVector<3> moved = X_curr * triangulated;
     t_join += ms_since(t);
 
+    sum_corr += (long long)corr_world.size();  // the solver's input
     t = Clock::now();
     cam.setWorldInCameraPose(Eigen::Isometry3f::Identity());
     solver.init(cam, moved.points(), current.pc.points());
@@ -281,7 +401,6 @@ int main(int argc, char** argv) {
       std::fprintf(stderr, "frame %d: meas %zu corr %zu map %zu |t| %.4f cum ms: assoc %.1f join %.1f picp %.1f tri %.1f map %.1f\n",
                    f, current.pc.size(), corr_world.size(), map.size(), X_curr.translation().norm(),
                    t_assoc, t_join, t_picp, t_tri, t_map);
-    sum_corr += (long long)corr_world.size();
     sum_meas += (long long)current.pc.size();
 
     // accuracy of the relative pose against the generator's ground truth
@@ -298,6 +417,10 @@ int main(int argc, char** argv) {
     reference = current;
   }
   if (fd) std::fclose(fd);
+  if (const char* mp = std::getenv("VO_SEQ_MAPDUMP")) {
+    const PointCloudVector<3>& cm = map;
+    dump_map(mp, cm.points());
+  }
 
   double rot_mean = 0;
   for (double e : rot_err) rot_mean += e;
