@@ -97,11 +97,12 @@ __device__ void picp_solve_and_update(const PicpParams& p, const float* tot) {
   float nb[6], dx[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) nb[i] = -b[i];
-  ldlt_solve_dev<6>(H, nb, dx);  // :109
+  ldlt_solve_recip_dev<6>(H, nb, dx);  // :109
   // v2tEuler(dx): R = Rx(dx3)*Ry(dx4)*Rz(dx5), t = dx0..2   (utils.h:64-78)
-  const float sx = sinf(dx[3]), cx = cosf(dx[3]);
-  const float sy = sinf(dx[4]), cy = cosf(dx[4]);
-  const float sz = sinf(dx[5]), cz = cosf(dx[5]);
+  float sx, cx, sy, cy, sz, cz;
+  sincosf(dx[3], &sx, &cx);
+  sincosf(dx[4], &sy, &cy);
+  sincosf(dx[5], &sz, &cz);
   const float Rx[9] = {1, 0, 0, 0, cx, sx, 0, -sx, cx};
   const float Ry[9] = {cy, 0, -sy, 0, 1, 0, sy, 0, cy};
   const float Rz[9] = {cz, sz, 0, -sz, cz, 0, 0, 0, 1};
@@ -586,10 +587,11 @@ __device__ __noinline__ bool picp_solve_local(const PicpParams& p, const float* 
   float* A = H;
 #pragma unroll
   for (int i = 0; i < 6; ++i) nb[i] = -b[i];
-  ldlt_solve_dev<6>(A, nb, dx);  // :109
-  const float sx = sinf(dx[3]), cx = cosf(dx[3]);
-  const float sy = sinf(dx[4]), cy = cosf(dx[4]);
-  const float sz = sinf(dx[5]), cz = cosf(dx[5]);
+  ldlt_solve_recip_dev<6>(A, nb, dx);  // :109
+  float sx, cx, sy, cy, sz, cz;
+  sincosf(dx[3], &sx, &cx);
+  sincosf(dx[4], &sy, &cy);
+  sincosf(dx[5], &sz, &cz);
   const float Rx[9] = {1, 0, 0, 0, cx, sx, 0, -sx, cx};
   const float Ry[9] = {cy, 0, -sy, 0, 1, 0, sy, 0, cy};
   const float Rz[9] = {cz, sz, 0, -sz, cz, 0, 0, 0, 1};

@@ -273,6 +273,10 @@ using namespace vo;
 struct vo_pipe_s {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // the map merge of frame k only feeds the map: it runs on a side stream, concurrently with the
+  // association and the PICP rounds of frame k+1
+  cudaStream_t map_stream = nullptr;
+  cudaEvent_t tri_done = nullptr, map_done = nullptr;
   vo_camera cam{};
   int64_t max_pts = 0, max_map = 0;
   vo_nn_t nn = nullptr;
@@ -329,13 +333,16 @@ static int pipe_associate(vo_pipe_s* h, bool with_join) {
   return VO_OK;
 }
 
-static int pipe_merge(vo_pipe_s* h, const float* pts_dev, const float* app_dev,
+static int pipe_merge(vo_pipe_s* h, cudaStream_t stream, const float* pts_dev, const float* app_dev,
                       const long long* n_new_dev, const float* X);
 
 // triangulate (ref, cur) with pose X into the other tri slot and merge into the map with `history`
 static int pipe_triangulate_and_merge(vo_pipe_s* h, const float* X) {
   const int ref = h->ref, cur = 1 - h->ref, nt = 1 - h->tri_slot;
   long long* counts = h->counts.as<long long>();
+  // the slot about to be overwritten was read by the merge of two frames ago; the merges are
+  // ordered on their stream, so waiting for the latest one is enough
+  VO_CUDA(cudaStreamWaitEvent(h->stream, h->map_done, 0));
   int rc = vo_triangulate_device_ex(
       h->stream, h->cam.K, X, h->corr_imgs.as<int32_t>(), h->n_q_last,
       reinterpret_cast<const int32_t*>(counts + C_CI), h->pts2d[ref].as<float>(),
@@ -343,14 +350,17 @@ static int pipe_triangulate_and_merge(vo_pipe_s* h, const float* X) {
       h->corr_world[nt].as<int32_t>(), h->tri_app[nt].as<float>(),
       reinterpret_cast<int64_t*>(counts + C_TRI0 + nt), h->tri_ws.p);
   if (rc) return rc;
-  rc = pipe_merge(h, h->tri_pts[nt].as<float>(), h->tri_app[nt].as<float>(), counts + C_TRI0 + nt,
-                  h->history);
+  VO_CUDA(cudaEventRecord(h->tri_done, h->stream));
+  VO_CUDA(cudaStreamWaitEvent(h->map_stream, h->tri_done, 0));
+  rc = pipe_merge(h, h->map_stream, h->tri_pts[nt].as<float>(), h->tri_app[nt].as<float>(),
+                  counts + C_TRI0 + nt, h->history);
   if (rc) return rc;
+  VO_CUDA(cudaEventRecord(h->map_done, h->map_stream));
   h->tri_slot = nt;
   return VO_OK;
 }
 
-static int pipe_merge(vo_pipe_s* h, const float* pts_dev, const float* app_dev,
+static int pipe_merge(vo_pipe_s* h, cudaStream_t stream, const float* pts_dev, const float* app_dev,
                       const long long* n_new_dev, const float* X) {
   long long* counts = h->counts.as<long long>();
   MapParams p;
@@ -368,7 +378,7 @@ static int pipe_merge(vo_pipe_s* h, const float* pts_dev, const float* app_dev,
   p.max_map = h->max_map;
   p.n_map_dev = counts + C_MAP;
   p.overflow_dev = counts + C_OVF;
-  map_update_kernel<<<1, PIPE_THREADS, 0, h->stream>>>(p);
+  map_update_kernel<<<1, PIPE_THREADS, 0, stream>>>(p);
   VO_LAUNCH_CHECK();
   return VO_OK;
 }
@@ -397,6 +407,13 @@ int vo_pipe_create(vo_pipe_t* out, int device, const vo_camera* cam, int64_t max
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
     set_error("cudaStreamCreate failed");
     delete h;
+    return VO_ERR_CUDA;
+  }
+  if (cudaStreamCreateWithFlags(&h->map_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->tri_done, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->map_done, cudaEventDisableTiming) != cudaSuccess) {
+    set_error("stream/event creation failed");
+    vo_pipe_destroy(h);
     return VO_ERR_CUDA;
   }
   int rc;
@@ -430,6 +447,7 @@ int vo_pipe_create(vo_pipe_t* out, int device, const vo_camera* cam, int64_t max
   iso_identity(h->X_curr);
   iso_identity(h->history);
   VO_CUDA(cudaStreamSynchronize(h->stream));
+  VO_CUDA(cudaEventRecord(h->map_done, h->map_stream));  // "no merge pending"
   *out = h;
   return VO_OK;
 }
@@ -438,6 +456,10 @@ int vo_pipe_destroy(vo_pipe_t h) {
   if (!h) return VO_OK;
   DeviceGuard g(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->map_stream) cudaStreamSynchronize(h->map_stream);
+  if (h->tri_done) cudaEventDestroy(h->tri_done);
+  if (h->map_done) cudaEventDestroy(h->map_done);
+  if (h->map_stream) cudaStreamDestroy(h->map_stream);
   if (h->nn) vo_nn_destroy(h->nn);
   if (h->picp) vo_picp_destroy(h->picp);
   for (int s = 0; s < 2; ++s) {
@@ -562,6 +584,7 @@ int vo_pipe_merge_cloud(vo_pipe_t h, const float* points_host, const float* app_
   VO_REQUIRE((points_host && app_host) || n == 0, VO_ERR_ARG, "null cloud");
   if (n == 0) return VO_OK;
   DeviceGuard g(h->device);
+  VO_CUDA(cudaStreamSynchronize(h->map_stream));
   // staged through the buffers of the NEXT triangulation (free between frames)
   const int nt = 1 - h->tri_slot;
   long long* counts = h->counts.as<long long>();
@@ -569,7 +592,8 @@ int vo_pipe_merge_cloud(vo_pipe_t h, const float* points_host, const float* app_
   VO_CUDA(cudaMemcpyAsync(h->tri_pts[nt].p, points_host, (size_t)n * 12, cudaMemcpyHostToDevice, h->stream));
   VO_CUDA(cudaMemcpyAsync(h->tri_app[nt].p, app_host, (size_t)n * 40, cudaMemcpyHostToDevice, h->stream));
   VO_CUDA(cudaMemcpyAsync(counts + C_TRI0 + nt, &cnt, 8, cudaMemcpyHostToDevice, h->stream));
-  int rc = pipe_merge(h, h->tri_pts[nt].as<float>(), h->tri_app[nt].as<float>(), counts + C_TRI0 + nt, X);
+  int rc = pipe_merge(h, h->stream, h->tri_pts[nt].as<float>(), h->tri_app[nt].as<float>(),
+                      counts + C_TRI0 + nt, X);
   if (rc) return rc;
   VO_CUDA(cudaStreamSynchronize(h->stream));
   return VO_OK;
@@ -578,6 +602,7 @@ int vo_pipe_merge_cloud(vo_pipe_t h, const float* points_host, const float* app_
 int vo_pipe_get_map(vo_pipe_t h, float* points_host, float* app_host, int64_t capacity, int64_t* n) {
   VO_REQUIRE(h != nullptr && n != nullptr, VO_ERR_ARG, "null pointer");
   DeviceGuard g(h->device);
+  VO_CUDA(cudaStreamSynchronize(h->map_stream));  // the last frame's merge
   long long cnt = 0;
   VO_CUDA(cudaMemcpyAsync(&cnt, h->counts.as<long long>() + C_MAP, 8, cudaMemcpyDeviceToHost, h->stream));
   VO_CUDA(cudaStreamSynchronize(h->stream));
