@@ -191,44 +191,53 @@ __device__ __forceinline__ float nn_filter_threshold(const float (&qn)[NN_DIM], 
   return (bound - qq) + eps;
 }
 
-// Slow path (rare): re-scan one tile for one query, exact arithmetic for the candidates.
-// The running exact bound is NOT kept in registers: it is the d2 stored in the query's global key
-// (possibly improved by another map split in the meantime).  A candidate is merged when
-// d2 < norm^2 (strict, brute_force_search.h:35) and d2 <= best-so-far; among equal d2 the packed
-// atomicMin keeps the lowest row (the reference's first-match-wins order).  Returns the new bound.
-__device__ __noinline__ float nn_rescan_tile(const float4* __restrict__ tile, int64_t row0,
-                                             int64_t n_rows, float qn0, float qn1, float qn2,
-                                             float qn3, float qn4, float qn5, float qn6, float qn7,
-                                             float qn8, float qn9, float tq, float radius2,
-                                             unsigned long long* key) {
-  const float q[NN_DIM] = {-0.5f * qn0, -0.5f * qn1, -0.5f * qn2, -0.5f * qn3, -0.5f * qn4,
-                           -0.5f * qn5, -0.5f * qn6, -0.5f * qn7, -0.5f * qn8, -0.5f * qn9};
+// Slow path: re-scan one tile for ONE query, exact arithmetic for the candidates — executed by the
+// whole warp (lane l takes rows l, l+32, ...), because in frame-to-frame association nearly every
+// query has a match, and a single lane walking 128 rows while 31 idle made the re-scans cost
+// several times the filter on frame-sized maps.  `qn` (the query, pre-scaled by -2), `tq` (its
+// filter threshold) and `key` are warp-uniform.  The running exact bound is NOT kept in
+// registers: it is the d2 stored in the query's global key (possibly improved by another map split
+// in the meantime).  A candidate is merged when d2 < norm^2 (strict, brute_force_search.h:35) and
+// d2 <= best-so-far; among equal d2 the packed atomicMin keeps the lowest row (the reference's
+// first-match-wins order).  Returns the new bound (warp-uniform).
+__device__ __forceinline__ float nn_rescan_tile_warp(const float4* __restrict__ tile, int64_t row0,
+                                                     int64_t n_rows, const float (&qn)[NN_DIM],
+                                                     float tq, float radius2,
+                                                     unsigned long long* key) {
+  const int lane = threadIdx.x & 31;
+  float q[NN_DIM];
+#pragma unroll
+  for (int k = 0; k < NN_DIM; ++k) q[k] = -0.5f * qn[k];
   const unsigned long long k0 = *reinterpret_cast<volatile unsigned long long*>(key);
   float best = (k0 == NN_KEY_NONE) ? radius2 : __uint_as_float(static_cast<unsigned int>(k0 >> 32));
-  for (int r = 0; r < NN_TM; ++r) {
+  float found = best;
+#pragma unroll
+  for (int r = lane; r < NN_TM; r += 32) {
     const float4 a = tile[r * 3 + 0], b = tile[r * 3 + 1], c = tile[r * 3 + 2];
     float acc = c.z;
-    acc = fmaf(qn0, a.x, acc);
-    acc = fmaf(qn1, a.y, acc);
-    acc = fmaf(qn2, a.z, acc);
-    acc = fmaf(qn3, a.w, acc);
-    acc = fmaf(qn4, b.x, acc);
-    acc = fmaf(qn5, b.y, acc);
-    acc = fmaf(qn6, b.z, acc);
-    acc = fmaf(qn7, b.w, acc);
-    acc = fmaf(qn8, c.x, acc);
-    acc = fmaf(qn9, c.y, acc);
+    acc = fmaf(qn[0], a.x, acc);
+    acc = fmaf(qn[1], a.y, acc);
+    acc = fmaf(qn[2], a.z, acc);
+    acc = fmaf(qn[3], a.w, acc);
+    acc = fmaf(qn[4], b.x, acc);
+    acc = fmaf(qn[5], b.y, acc);
+    acc = fmaf(qn[6], b.z, acc);
+    acc = fmaf(qn[7], b.w, acc);
+    acc = fmaf(qn[8], c.x, acc);
+    acc = fmaf(qn[9], c.y, acc);
     if (acc < tq) {
       const int64_t row = row0 + r;
       const float m[NN_DIM] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y};
       const float d2 = ref_sqdist<NN_DIM>(m, q);
       if (row < n_rows && d2 < radius2 && d2 <= best) {
-        best = d2;
+        found = fminf(found, d2);
         atomicMin(key, nn_pack_key(d2, static_cast<uint32_t>(row)));
       }
     }
   }
-  return best;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) found = fminf(found, __shfl_xor_sync(0xffffffffu, found, o));
+  return found;
 }
 
 __device__ __forceinline__ float f_min3(float a, float b, float c) {
@@ -353,24 +362,30 @@ nn_filter_kernel(const NNParams p) {
       }
     }
 
-    // rare: some row of this tile may be within the bound for some query of this thread
+    // some row of this tile may be within the bound for some query of this warp: the warp takes
+    // the flagged (lane, query) pairs one by one and re-scans the tile together
 #pragma unroll
     for (int j = 0; j < TQ; ++j) {
       const float tqj = tq_s[j * THREADS + tid];
-      if (mn[j] < tqj) {
-        const int64_t qi = qbase + (int64_t)j * THREADS + tid;
+      float own[NN_DIM];
+#pragma unroll
+      for (int k = 0; k < NN_DIM; ++k) {
+        float lo, hi;
+        f2_unpack(q2[j >> 1][k], lo, hi);
+        own[k] = (j & 1) ? hi : lo;
+      }
+      unsigned pending = __ballot_sync(0xffffffffu, mn[j] < tqj);
+      while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
         float qn[NN_DIM];
 #pragma unroll
-        for (int k = 0; k < NN_DIM; ++k) {
-          float lo, hi;
-          f2_unpack(q2[j >> 1][k], lo, hi);
-          qn[k] = (j & 1) ? hi : lo;
-        }
-        const float nb = nn_rescan_tile(tile, t * NN_TM, p.n_rows, qn[0], qn[1], qn[2], qn[3], qn[4],
-                                        qn[5], qn[6], qn[7], qn[8], qn[9], tqj, p.bound,
-                                        p.keys + qi);
+        for (int k = 0; k < NN_DIM; ++k) qn[k] = __shfl_sync(0xffffffffu, own[k], src);
+        const float tqs = __shfl_sync(0xffffffffu, tqj, src);
+        const int64_t qi = qbase + (int64_t)j * THREADS + (tid & ~31) + src;
+        const float nb = nn_rescan_tile_warp(tile, t * NN_TM, p.n_rows, qn, tqs, p.bound, p.keys + qi);
         // tighten: later rows only matter if they can reach d2 <= nb
-        tq_s[j * THREADS + tid] = fminf(tqj, nn_filter_threshold(qn, nb, mm_max));
+        if ((tid & 31) == src) tq_s[j * THREADS + tid] = fminf(tqj, nn_filter_threshold(own, nb, mm_max));
       }
       mn[j] = INFINITY;
     }
