@@ -106,3 +106,44 @@ def test_call_order_is_enforced(vo):
     X = np.eye(4, dtype=np.float32).reshape(-1)
     assert lib.vo_pipe_bootstrap(h, X.ctypes.data_as(C.POINTER(C.c_float))) == -4
     lib.vo_pipe_destroy(h)
+
+
+def test_degenerate_frames_do_not_break_the_loop(vo):
+    """empty and unmatched frames: no matches -> no correspondences -> the pose stays the identity
+    and nothing is triangulated; the loop keeps running"""
+    lib, h = _pipe(vo, max_pts=2048, max_map=4000)
+    abi = __import__("importlib").import_module("visual-odometry_b200._abi")
+    rng = np.random.RandomState(9)
+
+    def frame(n):
+        return (rng.uniform(0, 600, (n, 2)).astype(np.float32), rng.uniform(-1, 1, (n, 10)).astype(np.float32))
+
+    class Result(C.Structure):
+        _fields_ = [("T", C.c_float * 16), ("n_measurements", C.c_int64), ("n_matches", C.c_int64),
+                    ("n_correspondences", C.c_int64), ("map_points", C.c_int64),
+                    ("chi_inliers", C.c_float), ("n_inliers", C.c_int32), ("map_overflow", C.c_int32)]
+
+    p0, a0 = frame(50)
+    assert lib.vo_pipe_first_frame(h, _p(p0), _p(a0), 50) == 0
+    p1, a1 = frame(40)  # unrelated appearances: no match
+    corr = np.zeros((64, 2), np.int32)
+    n = C.c_int64(-1)
+    assert lib.vo_pipe_second_frame(h, _p(p1), _p(a1), 40, _p(corr), C.byref(n)) == 0
+    assert n.value == 0
+    X = np.eye(4, dtype=np.float32).reshape(-1)
+    assert lib.vo_pipe_bootstrap(h, X.ctypes.data_as(C.POINTER(C.c_float))) == 0
+    res = Result()
+    for size in (30, 0, 0, 25, 1):
+        pts, app = frame(max(size, 1))
+        assert lib.vo_pipe_step(h, _p(pts), _p(app), size, 5, C.c_float(1e4), C.byref(res)) == 0, lib.vo_last_error()
+        assert res.n_measurements == size and res.n_matches == 0 and res.n_correspondences == 0
+        assert np.allclose(np.array(res.T[:]).reshape(4, 4), np.eye(4), atol=1e-6)
+    # a frame that repeats the previous one exactly: every point matches itself
+    pts, app = frame(64)
+    assert lib.vo_pipe_step(h, _p(pts), _p(app), 64, 5, C.c_float(1e4), C.byref(res)) == 0
+    assert lib.vo_pipe_step(h, _p(pts), _p(app), 64, 5, C.c_float(1e4), C.byref(res)) == 0
+    assert res.n_matches == 64
+    n_map = C.c_int64(-1)
+    assert lib.vo_pipe_get_map(h, None, None, 0, C.byref(n_map)) == 0
+    assert n_map.value >= 0
+    lib.vo_pipe_destroy(h)
