@@ -562,6 +562,7 @@ static int nn_launch_filter(vo_nn_s* h, const float* queries_dev, int64_t nq, in
   };
   // a batch too small for the wide register tile
   auto launch_small = [&](int64_t q0, int64_t cnt) -> int {
+    if (cnt > 4096) return launch(nn_filter_kernel<4, 256>, 4, 256, q0, cnt);
     if (cnt > 1024) return launch(nn_filter_kernel<2, 256>, 2, 256, q0, cnt);
     return launch(nn_filter_kernel<2, 64>, 2, 64, q0, cnt);
   };
@@ -572,7 +573,9 @@ static int nn_launch_filter(vo_nn_s* h, const float* queries_dev, int64_t nq, in
   // it: a sharded batch (Q/8 = 12500 queries = 4.07 tiles) then costs 4 waves plus a thin one
   // instead of 5 (what near-linear scaling of the query-sharded sweep hinges on).
   constexpr int64_t WIDE = 8 * 384;
-  if (nq <= 8192) return launch_small(0, nq);
+  // a map of only a few tiles cannot feed 148 wide CTAs with work: frame-sized problems take the
+  // narrow register tile whatever the query count
+  if (nq <= 8192 || h->n_tiles < 2 * (int64_t)sms) return launch_small(0, nq);
   const int64_t full = nq / WIDE * WIDE, rem = nq - full;
   int rc = launch(nn_filter_kernel<8, 384>, 8, 384, 0, full);
   if (rc || rem == 0) return rc;
