@@ -526,7 +526,7 @@ def bench_vo(torch, args, dist, rank, local, world):
         "scaling": "weak",
         "config": {"workload": f"batched vo_complete: {world} independent synthetic sequence(s) x "
                                f"{args.vo_frames} frames x {args.vo_landmarks} landmarks, one per GPU, "
-                               "100 PICP rounds/frame"},
+                               "100 PICP rounds/frame; the first 20 loop frames are untimed warm-up"},
         "rank0": {k: r[k] for k in ("impl", "frames_per_s", "stage_ms_per_frame", "mean_measurements",
                                     "mean_correspondences", "map_points", "rot_err_mean_rad",
                                     "scale_first_pair", "scale_median")},

@@ -77,6 +77,9 @@ struct DevBuf {
 };
 
 int num_sms(int device);
+// internal (not part of the C ABI): device address of a solver's vo_picp_state, for callers inside
+// the library that fetch it together with other results in one synchronisation
+const void* picp_state_device_ptr(vo_picp_t h);
 
 // After cudaMemcpyAsync FROM `host_ptr`: may the caller reuse / free the buffer without a stream
 // synchronisation?  A copy from pageable memory has been staged by the runtime when the call

@@ -25,6 +25,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <map>
 
 #include "common.cuh"
 
@@ -510,6 +511,7 @@ struct vo_nn_s {
   DevBuf scalars;             // [0] = mm_max
   DevBuf keys;
   DevBuf q_stage, idx_stage, d2_stage, cnt_stage, list_stage;
+  std::map<int, int> occupancy;  // (TQ, THREADS) -> resident CTAs per SM of that filter variant
 };
 
 static int nn_launch_filter(vo_nn_s* h, const float* queries_dev, int64_t nq, int qstride,
@@ -548,9 +550,15 @@ static int nn_launch_filter(vo_nn_s* h, const float* queries_dev, int64_t nq, in
     r.n_queries = cnt;
     const int64_t qtiles = (cnt + (int64_t)tq * threads - 1) / ((int64_t)tq * threads);
     const size_t smem = smem_for(tq, threads);
-    VO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 1;
-    VO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    // per handle (= per device) and per variant: opt in to the shared-memory size and ask for the
+    // occupancy once, not on every launch (two driver calls on the per-frame critical path)
+    int& per_sm = h->occupancy[tq * 1024 + threads];
+    if (per_sm == 0) {
+      VO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int v = 1;
+      VO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, threads, smem));
+      per_sm = v < 1 ? 1 : v;
+    }
     const int64_t splits = splits_for(qtiles, (int64_t)sms * std::max(per_sm, 1));
     r.tiles_per_split = (h->n_tiles + splits - 1) / splits;
     const int64_t nsplit = (h->n_tiles + r.tiles_per_split - 1) / r.tiles_per_split;

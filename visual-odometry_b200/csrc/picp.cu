@@ -834,6 +834,10 @@ static int picp_pick_grid(vo_picp_s* h) {
   return (int)g;
 }
 
+namespace vo {
+const void* picp_state_device_ptr(vo_picp_t h) { return h ? h->state_buf.p : nullptr; }
+}  // namespace vo
+
 extern "C" {
 
 int vo_picp_create(vo_picp_t* out, int device) {

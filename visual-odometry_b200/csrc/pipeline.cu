@@ -290,6 +290,7 @@ struct vo_pipe_s {
   DevBuf map_pts, map_app, map_slots, map_last, key_slot;
   unsigned int cap = 0;
   float X_curr[16], history[16];
+  unsigned char* pinned = nullptr;  // host staging for the per-frame read-back
   int64_t n_q_last = 0;   // upper bound of |corr_imgs| of the last association
 };
 
@@ -446,6 +447,8 @@ int vo_pipe_create(vo_pipe_t* out, int device, const vo_camera* cam, int64_t max
                                PIPE_MAX_POINTS * (int)sizeof(int)));
   iso_identity(h->X_curr);
   iso_identity(h->history);
+  VO_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->pinned), C_N * 8 + sizeof(vo_picp_state) + 64,
+                        cudaHostAllocDefault));
   VO_CUDA(cudaStreamSynchronize(h->stream));
   VO_CUDA(cudaEventRecord(h->map_done, h->map_stream));  // "no merge pending"
   *out = h;
@@ -457,6 +460,7 @@ int vo_pipe_destroy(vo_pipe_t h) {
   DeviceGuard g(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->map_stream) cudaStreamSynchronize(h->map_stream);
+  if (h->pinned) cudaFreeHost(h->pinned);
   if (h->tri_done) cudaEventDestroy(h->tri_done);
   if (h->map_done) cudaEventDestroy(h->map_done);
   if (h->map_stream) cudaStreamDestroy(h->map_stream);
@@ -555,10 +559,13 @@ int vo_pipe_step(vo_pipe_t h, const float* points_host, const float* app_host, i
                                reinterpret_cast<const int32_t*>(h->counts.as<long long>() + C_PP),
                                h->X_curr)))
     return rc;
-  long long counts[C_N];
-  VO_CUDA(cudaMemcpyAsync(counts, h->counts.p, sizeof(counts), cudaMemcpyDeviceToHost, h->stream));
-  vo_picp_state st;
-  if ((rc = vo_picp_get_state(h->picp, &st))) return rc;                   // the frame's one sync
+  // the frame's one synchronisation: counts and solver state land in pinned memory together
+  long long* counts = reinterpret_cast<long long*>(h->pinned);
+  vo_picp_state& st = *reinterpret_cast<vo_picp_state*>(h->pinned + C_N * 8);
+  VO_CUDA(cudaMemcpyAsync(counts, h->counts.p, C_N * 8, cudaMemcpyDeviceToHost, h->stream));
+  VO_CUDA(cudaMemcpyAsync(&st, picp_state_device_ptr(h->picp), sizeof(vo_picp_state),
+                          cudaMemcpyDeviceToHost, h->stream));
+  VO_CUDA(cudaStreamSynchronize(h->stream));
   memcpy(h->X_curr, st.T, sizeof(st.T));                                   // :161-163
   memcpy(out->T, st.T, sizeof(st.T));
   out->n_measurements = n;
