@@ -193,6 +193,13 @@ def kdtree_agreement(vo, synth, local):
             "cpu_kdtree_build_plus_full_queries_s": t_full}
 
 
+def kdtree_guard(vo, synth, local):
+    try:
+        return kdtree_agreement(vo, synth, local)
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def reference_arm(args):
     """--impl reference: the reference's CPU path for the metric — its bruteForceBestMatch
     template (oracle/_ref, prebuilt from the reference sources; the C port if that is absent) on
@@ -504,17 +511,27 @@ def bench_vo(torch, args, dist, rank, local, world):
         return {"unavailable": "host/bin/vo_sequence not built (needs the reference checkout at build time)"}
     env = dict(os.environ, VO_B200_DEVICE=str(local))
     env.pop("VO_SEQ_MODE", None)  # default mode: the device-resident frame pipeline (vo_pipe_*)
-    out = subprocess.run([exe, str(args.vo_landmarks), str(args.vo_frames), str(1000 + rank), "100"],
-                         env=env, capture_output=True, text=True, check=True).stdout
-    r = json.loads(out.strip().splitlines()[-1])
+    r, err = None, None
+    try:
+        out = subprocess.run([exe, str(args.vo_landmarks), str(args.vo_frames), str(1000 + rank), "100"],
+                             env=env, capture_output=True, text=True, check=True, timeout=900).stdout
+        r = json.loads(out.strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001 — every rank must still reach the collectives below
+        err = f"{type(e).__name__}: {e}"[:300]
+        r = {"frames": 0, "loop_ms": 0.0, "frames_per_s": 0.0, "stage_ms_per_frame": {},
+             "mean_measurements": 0.0, "mean_correspondences": 0.0, "map_points": 0,
+             "rot_err_mean_rad": None, "scale_first_pair": None, "scale_median": None, "impl": "failed"}
     # the same frames through the drop-in classes (the reference's call surface, call by call)
     rc = None
     if rank == 0 and world == 1:
-        outc = subprocess.run([exe, str(args.vo_landmarks), str(min(args.vo_frames, 300)), "1000", "100"],
-                              env=dict(env, VO_SEQ_MODE="classes"), capture_output=True, text=True,
-                              check=True).stdout
-        rc = json.loads(outc.strip().splitlines()[-1])
-    frames, sec = float(r["frames"]), r["loop_ms"] * 1e-3
+        try:
+            outc = subprocess.run([exe, str(args.vo_landmarks), str(min(args.vo_frames, 300)), "1000", "100"],
+                                  env=dict(env, VO_SEQ_MODE="classes"), capture_output=True, text=True,
+                                  check=True, timeout=900).stdout
+            rc = json.loads(outc.strip().splitlines()[-1])
+        except Exception:  # noqa: BLE001
+            rc = None
+    frames, sec = float(r["frames"]), max(r["loop_ms"] * 1e-3, 1e-9)
     if dist is not None:
         t = torch.tensor([frames, sec], dtype=torch.float64, device="cuda")
         tot = t.clone()
@@ -535,23 +552,31 @@ def bench_vo(torch, args, dist, rank, local, world):
                 "note": "host frames in, host pose out every frame through vo_pipe_step (the "
                         "driver IS the host API); one synchronisation per frame"},
     }
+    if err is not None:
+        res["error_rank0"] = err
     if rc is not None:
         res["drop_in_classes"] = {"frames_per_s": rc["frames_per_s"], "frames": rc["frames"],
                                   "stage_ms_per_frame": rc["stage_ms_per_frame"],
                                   "note": "same frames through TreeNode_/PICPSolver/"
                                           "triangulate_points/PointCloudVector, one call at a time"}
     if rank == 0 and world == 1:
-        res["bundled"] = bench_vo_bundled(env)
+        try:
+            res["bundled"] = bench_vo_bundled(env)
+        except Exception as e:  # noqa: BLE001
+            res["bundled"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     ref_exe = os.path.join(ROOT, "oracle", "_ref", "bin", "vo_sequence")
     if rank == 0 and world == 1 and os.path.exists(ref_exe):
         lm, fr = min(args.vo_landmarks, 10000), 6
-        c = json.loads(subprocess.run([ref_exe, str(lm), str(fr), "1000", "100"], capture_output=True,
-                                      text=True, check=True).stdout.strip().splitlines()[-1])
-        res["cpu_baseline"] = {"value": c["frames_per_s"], "unit": "frames/s", "cores": 1,
-                               "kind": "reference",
-                               "sample": f"{c['frames']} frames of a {lm}-landmark sequence "
-                                         f"({c['mean_measurements']:.0f} measurements/frame)",
-                               "stage_ms_per_frame": c["stage_ms_per_frame"]}
+        try:
+            c = json.loads(subprocess.run([ref_exe, str(lm), str(fr), "1000", "100"], capture_output=True,
+                                          text=True, check=True, timeout=600).stdout.strip().splitlines()[-1])
+            res["cpu_baseline"] = {"value": c["frames_per_s"], "unit": "frames/s", "cores": 1,
+                                   "kind": "reference",
+                                   "sample": f"{c['frames']} frames of a {lm}-landmark sequence "
+                                             f"({c['mean_measurements']:.0f} measurements/frame)",
+                                   "stage_ms_per_frame": c["stage_ms_per_frame"]}
+        except Exception as e:  # noqa: BLE001
+            res["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     return res
 
 
@@ -695,14 +720,24 @@ def ours_arm(args):
                              "sample": f"{sample_q} queries x full {M}-row map, {cores} threads"},
             "parity": {"planted_answers_equal": planted_ok, "oracle_sample_equal": oracle_equal,
                        "oracle_sample": sample_q, "rule": "bit-exact indices",
-                       "kdtree": None if args.nn_only else kdtree_agreement(vo, synth, local)},
+                       "kdtree": None if args.nn_only else kdtree_guard(vo, synth, local)},
         }
     nn.close()
+    # the secondary objects must never cost the primary line: a failure is recorded, not raised
+    def guarded(fn, *a):
+        try:
+            return fn(*a)
+        except Exception as e:  # noqa: BLE001
+            import traceback
+
+            traceback.print_exc(file=sys.stderr)
+            return {"error": f"{type(e).__name__}: {e}"[:400]}
+
     if rank == 0 and world == 1 and not args.nn_only:
-        line["picp"] = bench_picp(torch, vo, synth, args, cores)
-        line["triangulate"] = bench_triangulate(torch, vo, synth, args, cores)
+        line["picp"] = guarded(bench_picp, torch, vo, synth, args, cores)
+        line["triangulate"] = guarded(bench_triangulate, torch, vo, synth, args, cores)
     if not args.nn_only and args.vo_frames > 0:
-        vo_res = bench_vo(torch, args, dist, rank, local, world)
+        vo_res = guarded(bench_vo, torch, args, dist, rank, local, world)
         if rank == 0:
             line["vo"] = vo_res
     if rank == 0:
