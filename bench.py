@@ -488,10 +488,9 @@ def bench_vo_bundled(env):
         # what a GPU executable pays before its first frame (CUDA context + module load)
         seq = os.path.join(ROOT, "visual-odometry_b200", "host", "bin", "vo_sequence")
         if os.path.exists(seq):
-            init = best_of([seq, "init"])
-            out["b200_cuda_init_s"] = init
-            if out.get("b200_wall_s", 0) > init:
-                out["b200_frames_per_s_excluding_init"] = 121 / (out["b200_wall_s"] - init)
+            # informational only: context creation varies by several 100 ms from process to process,
+            # so it cannot be subtracted from the wall clock above
+            out["b200_cuda_init_s"] = best_of([seq, "init"])
     return out
 
 

@@ -65,18 +65,18 @@ def test_compute_many_rounds_equals_one_round_loop(vo, synth):
     for _ in range(12):
         a.oneRound(pr["pairs"], False)
     b.set_correspondences(pr["pairs"])
-    b.compute(False, 12)  # CUDA-graph path
+    b.compute(False, 12)  # all rounds in one launch
     sa, sb = a.state(), b.state()
     assert list(sa.T) == list(sb.T) and list(sa.H) == list(sb.H)  # deterministic, bit-equal
     assert sb.rounds_done == 12
-    b.compute(False, 12)  # graph replay
+    b.compute(False, 12)  # again
     assert b.state().rounds_done == 24
     a.close()
     b.close()
 
 
 def test_compute_graph_path_equals_launch_loop_streaming(vo, synth, monkeypatch):
-    """The same check on the streaming kernel (CUDA-graph replay vs one launch per round)."""
+    """The same check on the streaming kernel (one cooperative launch for 6 rounds vs 6 launches)."""
     monkeypatch.setenv("VO_PICP_FORCE_STREAM", "1")
     pr = synth.picp_problem(30000, seed=23)
     cam = vo.Camera(pr["rows"], pr["cols"], pr["z_near"], pr["z_far"], pr["K"], np.eye(4))

@@ -60,72 +60,6 @@ struct PicpParams {
   float pre[12];                     //   3x3 linear (column-major) then translation
 };
 
-// oneRound's tail (picp_solver.cpp:102-110), executed by one thread of the last block.
-__device__ void picp_solve_and_update(const PicpParams& p, const float* tot) {
-  vo_picp_state& s = p.st->s;
-  // upper triangle -> full symmetric H, column-major
-  float H[36];
-  {
-    int k = 0;
-#pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-      for (int c = r; c < 6; ++c) {
-        H[c * 6 + r] = tot[k];
-        H[r * 6 + c] = tot[k];
-        ++k;
-      }
-  }
-  float b[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) b[i] = tot[21 + i];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) H[i * 6 + i] += p.damping;  // :102
-#pragma unroll
-  for (int i = 0; i < 36; ++i) s.H[i] = H[i];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) s.b[i] = b[i];
-  s.chi_inliers = tot[27];
-  s.chi_outliers = tot[28];
-  const int n_in = __float_as_int(tot[29]);
-  s.num_inliers = n_in;
-  s.rounds_done += 1;
-  if (n_in < p.min_inliers) {  // :103-107
-    s.last_ok = 0;
-    return;
-  }
-  float nb[6], dx[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) nb[i] = -b[i];
-  ldlt_solve_recip_dev<6>(H, nb, dx);  // :109
-  // v2tEuler(dx): R = Rx(dx3)*Ry(dx4)*Rz(dx5), t = dx0..2   (utils.h:64-78)
-  float sx, cx, sy, cy, sz, cz;
-  sincosf(dx[3], &sx, &cx);
-  sincosf(dx[4], &sy, &cy);
-  sincosf(dx[5], &sz, &cz);
-  const float Rx[9] = {1, 0, 0, 0, cx, sx, 0, -sx, cx};
-  const float Ry[9] = {cy, 0, -sy, 0, 1, 0, sy, 0, cy};
-  const float Rz[9] = {cz, sz, 0, -sz, cz, 0, 0, 0, 1};
-  float Rxy[9], R[9];
-  mat3_mul_dev(Rx, Ry, Rxy);
-  mat3_mul_dev(Rxy, Rz, R);
-  // pose <- D * pose   (:110)
-  float Tn[16];
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      float acc = (R[i] * s.T[j * 4] + R[3 + i] * s.T[j * 4 + 1]) + R[6 + i] * s.T[j * 4 + 2];
-      if (j == 3) acc += dx[i];
-      Tn[j * 4 + i] = acc;
-    }
-  Tn[3] = Tn[7] = Tn[11] = 0.f;
-  Tn[15] = 1.f;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) s.T[i] = Tn[i];
-  s.last_ok = 1;
-}
-
 // Two correspondences at a time: errorAndJacobian (:25-53) + the body of linearize's loop (:62-95).
 // Branch-free: a rejected point runs the same instructions with weight 0, so a warp never
 // diverges on the data.
@@ -331,196 +265,6 @@ __device__ __forceinline__ constexpr uint32_t picp_prs_off(int slot, int u) {
   return (uint32_t)((PICP_PTS_WORDS + slot * PICP_UNROLL + u) * PICP_THREADS * 8);
 }
 
-template <bool PINHOLE, bool KEEP>
-__global__ void __launch_bounds__(PICP_THREADS, 1) picp_round_kernel(const PicpParams p) {
-  __shared__ float s_red[PICP_THREADS / 32][PICP_NACC];
-  __shared__ bool s_last;
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-
-  PicpConsts c;
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int i = 0; i < 3; ++i) c.T[j * 3 + i] = p.st->s.T[j * 4 + i];
-
-  PicpAcc a;
-#pragma unroll
-  for (int i = 0; i < 21; ++i) a.h[i] = 0ull;
-#pragma unroll
-  for (int i = 0; i < 6; ++i) a.b[i] = 0ull;
-  a.chi_in = a.chi_out = 0ull;
-  a.n_in = 0;
-
-  // ---- asynchronous stream over the correspondences ------------------------------------------
-  // thread t owns items t, t+stride, t+2*stride, ...; they are consumed in batches of PICP_UNROLL.
-  const int n = (int)p.n_pairs;
-  const int stride = (int)gridDim.x * PICP_THREADS;
-  const int i0 = (int)blockIdx.x * PICP_THREADS + tid;
-  const int mine = i0 < n ? (n - i0 + stride - 1) / stride : 0;  // items of this thread
-  const int nb = mine / PICP_UNROLL;                             // full batches
-  const int2* pp = p.pairs + i0;
-  {
-    extern __shared__ __align__(16) unsigned char picp_ring[];
-    const uint32_t ring = smem_u32(picp_ring) + (uint32_t)tid * 8u;
-    auto issue_pairs = [&](int b, int slot) {  // P(b)
-      if (b < nb) {
-#pragma unroll
-        for (int u = 0; u < PICP_UNROLL; ++u)
-          cp_async8(ring + picp_prs_off(slot, u), pp + (int64_t)(b * PICP_UNROLL + u) * stride);
-      }
-    };
-    auto issue_gathers = [&](int b, int slot) {  // G(b); P(b) has landed
-      if (b < nb) {
-#pragma unroll
-        for (int u = 0; u < PICP_UNROLL; ++u) {
-          const int2 pr = lds_int2(ring + picp_prs_off(slot, u));
-          const float* wp = p.world + 3 * (int64_t)pr.y;  // .second -> world (:67)
-          const float* ip = p.image + 2 * (int64_t)pr.x;  // .first -> image (:66)
-          const uint32_t lane = (uint32_t)(u & 1) * 4u;   // which half of the packed pair
-          cp_async4(ring + picp_pts_off(slot, u >> 1, 0) + lane, wp);
-          cp_async4(ring + picp_pts_off(slot, u >> 1, 1) + lane, wp + 1);
-          cp_async4(ring + picp_pts_off(slot, u >> 1, 2) + lane, wp + 2);
-          cp_async4(ring + picp_pts_off(slot, u >> 1, 3) + lane, ip);
-          cp_async4(ring + picp_pts_off(slot, u >> 1, 4) + lane, ip + 1);
-        }
-      }
-    };
-    // prologue: P(0..DEPTH-1); then G(j) + P(j+DEPTH) as the groups the main loop expects
-#pragma unroll
-    for (int j = 0; j < PICP_DEPTH; ++j) issue_pairs(j, j % PICP_SLOTS);
-    cp_async_commit();
-    cp_async_wait<0>();
-#pragma unroll
-    for (int j = 0; j < PICP_DEPTH; ++j) {
-      issue_gathers(j, j % PICP_SLOTS);
-      issue_pairs(j + PICP_DEPTH, (j + PICP_DEPTH) % PICP_SLOTS);
-      cp_async_commit();
-    }
-    for (int b0 = 0; b0 < nb; b0 += PICP_SLOTS) {
-#pragma unroll
-      for (int sl = 0; sl < PICP_SLOTS; ++sl) {
-        const int b = b0 + sl;
-        if (b < nb) {
-          cp_async_wait<PICP_DEPTH - 1>();  // G(b) and P(b+DEPTH) have landed
-          issue_gathers(b + PICP_DEPTH, (sl + PICP_DEPTH) % PICP_SLOTS);
-          issue_pairs(b + 2 * PICP_DEPTH, (sl + 2 * PICP_DEPTH) % PICP_SLOTS);
-          cp_async_commit();
-#pragma unroll
-          for (int pi = 0; pi < PICP_UNROLL / 2; ++pi)
-            picp_point2<PINHOLE, KEEP>(p, c, lds_f2(ring + picp_pts_off(sl, pi, 0)),
-                                       lds_f2(ring + picp_pts_off(sl, pi, 1)),
-                                       lds_f2(ring + picp_pts_off(sl, pi, 2)),
-                                       lds_f2(ring + picp_pts_off(sl, pi, 3)),
-                                       lds_f2(ring + picp_pts_off(sl, pi, 4)), true, a);
-        }
-      }
-    }
-    cp_async_wait<0>();
-    // the (< PICP_UNROLL) leftover items of this thread, again two at a time
-    for (int m = nb * PICP_UNROLL; m < mine; m += 2) {
-      const bool have1 = m + 1 < mine;
-      const int2 pr0 = __ldg(pp + (int64_t)m * stride);
-      const int2 pr1 = have1 ? __ldg(pp + (int64_t)(m + 1) * stride) : pr0;
-      const float* w0 = p.world + 3 * (int64_t)pr0.y;
-      const float* w1 = p.world + 3 * (int64_t)pr1.y;
-      const float2 m0 = __ldg(reinterpret_cast<const float2*>(p.image) + pr0.x);
-      const float2 m1 = __ldg(reinterpret_cast<const float2*>(p.image) + pr1.x);
-      picp_point2<PINHOLE, KEEP>(p, c, f2_pack(__ldg(w0), __ldg(w1)),
-                                 f2_pack(__ldg(w0 + 1), __ldg(w1 + 1)),
-                                 f2_pack(__ldg(w0 + 2), __ldg(w1 + 2)), f2_pack(m0.x, m1.x),
-                                 f2_pack(m0.y, m1.y), have1, a);
-    }
-  }
-
-  // ---- block reduction: shuffle within the warp, fixed-order sum across warps ----------------
-  float v[PICP_NACC];
-#pragma unroll
-  for (int i = 0; i < 29; ++i) {  // the two point slots
-    float lo, hi;
-    f2_unpack(i < 21 ? a.h[i] : (i < 27 ? a.b[i - 21] : (i == 27 ? a.chi_in : a.chi_out)), lo, hi);
-    v[i] = lo + hi;
-  }
-  int n_in = a.n_in;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-    for (int i = 0; i < 29; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
-    n_in += __shfl_xor_sync(0xffffffffu, n_in, o);
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < 29; ++i) s_red[warp][i] = v[i];
-    s_red[warp][29] = __int_as_float(n_in);
-  }
-  __syncthreads();
-  if (warp == 0 && lane < 30) {
-    float* out = p.partials + (int64_t)blockIdx.x * PICP_NACC;
-    if (lane < 29) {
-      float s = s_red[0][lane];
-#pragma unroll
-      for (int wv = 1; wv < PICP_THREADS / 32; ++wv) s += s_red[wv][lane];
-      out[lane] = s;
-    } else {
-      int s = 0;
-#pragma unroll
-      for (int wv = 0; wv < PICP_THREADS / 32; ++wv) s += __float_as_int(s_red[wv][29]);
-      out[29] = __int_as_float(s);
-    }
-  }
-
-  // ---- last block: fixed-order sum over the blocks, solve, pose update -----------------------
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned int t = atomicAdd(&p.st->ticket, 1u);
-    s_last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  {
-    // warp w sums blocks w, w+W, ... for component `lane` (16 independent loads in flight per
-    // step, combined in a fixed order); then warp 0 sums the W rows
-    constexpr int W = PICP_THREADS / 32;
-    constexpr int B = 16;
-    float s = 0.f;
-    int si = 0;
-    const int nblk = (int)gridDim.x;
-    for (int bk0 = warp; bk0 < nblk; bk0 += W * B) {
-      float x[B];
-#pragma unroll
-      for (int q = 0; q < B; ++q) {
-        const int bk = bk0 + q * W;
-        x[q] = (bk < nblk && lane < 30) ? __ldcg(p.partials + (int64_t)bk * PICP_NACC + lane) : 0.f;
-      }
-#pragma unroll
-      for (int q = 0; q < B; ++q) {
-        if (lane == 29) si += __float_as_int(x[q]);
-        else s += x[q];
-      }
-    }
-    __syncthreads();
-    s_red[warp][lane] = (lane == 29) ? __int_as_float(si) : s;
-    __syncthreads();
-    if (warp == 0) {
-      float tot = 0.f;
-      int toti = 0;
-#pragma unroll
-      for (int wv = 0; wv < W; ++wv) {
-        if (lane == 29) toti += __float_as_int(s_red[wv][29]);
-        else tot += s_red[wv][lane];
-      }
-      s_red[0][lane] = (lane == 29) ? __int_as_float(toti) : tot;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      picp_solve_and_update(p, &s_red[0][0]);
-      p.st->ticket = 0u;
-    }
-  }
-}
-
 // ---- resident kernel: all rounds of a frame-sized problem in ONE launch ---------------------------
 // The streaming kernel pays a fixed ~7 us per round (launch, last-block hand-off, one-thread solve
 // with global round-trips), which dwarfs the arithmetic when a frame has a few thousand
@@ -559,7 +303,7 @@ __device__ __forceinline__ float warp_reduce_transposed(float (&v)[32]) {
 
 // oneRound's tail (picp_solver.cpp:102-110) on register/shared state: tot = the 30 sums, T = the
 // 3x4 pose (column-major 3x3 then translation), updated in place.  Returns false when the round
-// is skipped (too few inliers).  Same operation sequence as picp_solve_and_update.
+// is skipped (too few inliers).
 __device__ __noinline__ bool picp_solve_local(const PicpParams& p, const float* tot, float* T,
                                               float* H_out, float* b_out) {
   float H[36], b[6];
@@ -740,6 +484,226 @@ picp_resident_kernel(const PicpParams p, const int rounds) {
   cluster.sync();
 }
 
+// ---- streaming kernel: more correspondences than the cluster's shared memory holds --------------
+// One cooperative launch for ALL rounds (grid = one CTA per SM).  Per round every CTA streams its
+// share of the correspondences through the cp.async ring, reduces to one partial row, and after a
+// single grid-wide barrier every CTA sums all rows in a fixed order and solves for its own copy of
+// the pose — no kernel boundary, no last-block hand-off and no global round-trip of the pose
+// between Gauss-Newton iterations.
+template <bool PINHOLE, bool KEEP>
+__global__ void __launch_bounds__(PICP_THREADS, 1)
+picp_stream_kernel(const PicpParams p, const int rounds) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ float s_red[PICP_THREADS / 32][PICP_NACC];
+  __shared__ float s_T[12], s_H[36], s_b[6], s_keep[4];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  if (tid < 12) s_T[tid] = p.st->s.T[(tid / 3) * 4 + (tid % 3)];
+  __syncthreads();
+  for (int round = 0; round < rounds; ++round) {
+
+  PicpConsts c;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) c.T[i] = s_T[i];
+
+  PicpAcc a;
+#pragma unroll
+  for (int i = 0; i < 21; ++i) a.h[i] = 0ull;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) a.b[i] = 0ull;
+  a.chi_in = a.chi_out = 0ull;
+  a.n_in = 0;
+
+  // ---- asynchronous stream over the correspondences ------------------------------------------
+  // thread t owns items t, t+stride, t+2*stride, ...; they are consumed in batches of PICP_UNROLL.
+  const int n = (int)p.n_pairs;
+  const int stride = (int)gridDim.x * PICP_THREADS;
+  const int i0 = (int)blockIdx.x * PICP_THREADS + tid;
+  const int mine = i0 < n ? (n - i0 + stride - 1) / stride : 0;  // items of this thread
+  const int nb = mine / PICP_UNROLL;                             // full batches
+  const int2* pp = p.pairs + i0;
+  {
+    extern __shared__ __align__(16) unsigned char picp_ring[];
+    const uint32_t ring = smem_u32(picp_ring) + (uint32_t)tid * 8u;
+    auto issue_pairs = [&](int b, int slot) {  // P(b)
+      if (b < nb) {
+#pragma unroll
+        for (int u = 0; u < PICP_UNROLL; ++u)
+          cp_async8(ring + picp_prs_off(slot, u), pp + (int64_t)(b * PICP_UNROLL + u) * stride);
+      }
+    };
+    auto issue_gathers = [&](int b, int slot) {  // G(b); P(b) has landed
+      if (b < nb) {
+#pragma unroll
+        for (int u = 0; u < PICP_UNROLL; ++u) {
+          const int2 pr = lds_int2(ring + picp_prs_off(slot, u));
+          const float* wp = p.world + 3 * (int64_t)pr.y;  // .second -> world (:67)
+          const float* ip = p.image + 2 * (int64_t)pr.x;  // .first -> image (:66)
+          const uint32_t lane = (uint32_t)(u & 1) * 4u;   // which half of the packed pair
+          cp_async4(ring + picp_pts_off(slot, u >> 1, 0) + lane, wp);
+          cp_async4(ring + picp_pts_off(slot, u >> 1, 1) + lane, wp + 1);
+          cp_async4(ring + picp_pts_off(slot, u >> 1, 2) + lane, wp + 2);
+          cp_async4(ring + picp_pts_off(slot, u >> 1, 3) + lane, ip);
+          cp_async4(ring + picp_pts_off(slot, u >> 1, 4) + lane, ip + 1);
+        }
+      }
+    };
+    // prologue: P(0..DEPTH-1); then G(j) + P(j+DEPTH) as the groups the main loop expects
+#pragma unroll
+    for (int j = 0; j < PICP_DEPTH; ++j) issue_pairs(j, j % PICP_SLOTS);
+    cp_async_commit();
+    cp_async_wait<0>();
+#pragma unroll
+    for (int j = 0; j < PICP_DEPTH; ++j) {
+      issue_gathers(j, j % PICP_SLOTS);
+      issue_pairs(j + PICP_DEPTH, (j + PICP_DEPTH) % PICP_SLOTS);
+      cp_async_commit();
+    }
+    for (int b0 = 0; b0 < nb; b0 += PICP_SLOTS) {
+#pragma unroll
+      for (int sl = 0; sl < PICP_SLOTS; ++sl) {
+        const int b = b0 + sl;
+        if (b < nb) {
+          cp_async_wait<PICP_DEPTH - 1>();  // G(b) and P(b+DEPTH) have landed
+          issue_gathers(b + PICP_DEPTH, (sl + PICP_DEPTH) % PICP_SLOTS);
+          issue_pairs(b + 2 * PICP_DEPTH, (sl + 2 * PICP_DEPTH) % PICP_SLOTS);
+          cp_async_commit();
+#pragma unroll
+          for (int pi = 0; pi < PICP_UNROLL / 2; ++pi)
+            picp_point2<PINHOLE, KEEP>(p, c, lds_f2(ring + picp_pts_off(sl, pi, 0)),
+                                       lds_f2(ring + picp_pts_off(sl, pi, 1)),
+                                       lds_f2(ring + picp_pts_off(sl, pi, 2)),
+                                       lds_f2(ring + picp_pts_off(sl, pi, 3)),
+                                       lds_f2(ring + picp_pts_off(sl, pi, 4)), true, a);
+        }
+      }
+    }
+    cp_async_wait<0>();
+    // the (< PICP_UNROLL) leftover items of this thread, again two at a time
+    for (int m = nb * PICP_UNROLL; m < mine; m += 2) {
+      const bool have1 = m + 1 < mine;
+      const int2 pr0 = __ldg(pp + (int64_t)m * stride);
+      const int2 pr1 = have1 ? __ldg(pp + (int64_t)(m + 1) * stride) : pr0;
+      const float* w0 = p.world + 3 * (int64_t)pr0.y;
+      const float* w1 = p.world + 3 * (int64_t)pr1.y;
+      const float2 m0 = __ldg(reinterpret_cast<const float2*>(p.image) + pr0.x);
+      const float2 m1 = __ldg(reinterpret_cast<const float2*>(p.image) + pr1.x);
+      picp_point2<PINHOLE, KEEP>(p, c, f2_pack(__ldg(w0), __ldg(w1)),
+                                 f2_pack(__ldg(w0 + 1), __ldg(w1 + 1)),
+                                 f2_pack(__ldg(w0 + 2), __ldg(w1 + 2)), f2_pack(m0.x, m1.x),
+                                 f2_pack(m0.y, m1.y), have1, a);
+    }
+  }
+
+  // ---- block reduction: shuffle within the warp, fixed-order sum across warps ----------------
+  float v[PICP_NACC];
+#pragma unroll
+  for (int i = 0; i < 29; ++i) {  // the two point slots
+    float lo, hi;
+    f2_unpack(i < 21 ? a.h[i] : (i < 27 ? a.b[i - 21] : (i == 27 ? a.chi_in : a.chi_out)), lo, hi);
+    v[i] = lo + hi;
+  }
+  int n_in = a.n_in;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 29; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+    n_in += __shfl_xor_sync(0xffffffffu, n_in, o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 29; ++i) s_red[warp][i] = v[i];
+    s_red[warp][29] = __int_as_float(n_in);
+  }
+  __syncthreads();
+  if (warp == 0 && lane < 30) {
+    float* out = p.partials + ((int64_t)(round & 1) * gridDim.x + blockIdx.x) * PICP_NACC;
+    if (lane < 29) {
+      float s = s_red[0][lane];
+#pragma unroll
+      for (int wv = 1; wv < PICP_THREADS / 32; ++wv) s += s_red[wv][lane];
+      out[lane] = s;
+    } else {
+      int s = 0;
+#pragma unroll
+      for (int wv = 0; wv < PICP_THREADS / 32; ++wv) s += __float_as_int(s_red[wv][29]);
+      out[29] = __int_as_float(s);
+    }
+  }
+
+  // ---- every block: fixed-order sum over all blocks' partials, solve, own copy of the pose -------
+  // One grid-wide barrier per round; the partial buffers alternate with the round's parity, so a
+  // fast block's next round cannot overwrite what a slow one is still reading.  Every block runs
+  // the same instruction stream on the same numbers, so all copies of the pose stay identical.
+  __threadfence();
+  grid.sync();
+  {
+    // warp w sums blocks w, w+W, ... for component `lane` (16 independent loads in flight per
+    // step, combined in a fixed order); then warp 0 sums the W rows
+    constexpr int W = PICP_THREADS / 32;
+    constexpr int B = 16;
+    float s = 0.f;
+    int si = 0;
+    const int nblk = (int)gridDim.x;
+    const float* part = p.partials + (int64_t)(round & 1) * gridDim.x * PICP_NACC;
+    for (int bk0 = warp; bk0 < nblk; bk0 += W * B) {
+      float x[B];
+#pragma unroll
+      for (int q = 0; q < B; ++q) {
+        const int bk = bk0 + q * W;
+        x[q] = (bk < nblk && lane < 30) ? __ldcg(part + (int64_t)bk * PICP_NACC + lane) : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < B; ++q) {
+        if (lane == 29) si += __float_as_int(x[q]);
+        else s += x[q];
+      }
+    }
+    __syncthreads();
+    s_red[warp][lane] = (lane == 29) ? __int_as_float(si) : s;
+    __syncthreads();
+    if (warp == 0) {
+      float tot = 0.f;
+      int toti = 0;
+#pragma unroll
+      for (int wv = 0; wv < W; ++wv) {
+        if (lane == 29) toti += __float_as_int(s_red[wv][29]);
+        else tot += s_red[wv][lane];
+      }
+      s_red[0][lane] = (lane == 29) ? __int_as_float(toti) : tot;
+      __syncwarp();
+      if (lane == 0) {
+        s_keep[3] = picp_solve_local(p, s_red[0], s_T, s_H, s_b) ? 1.f : 0.f;
+        s_keep[0] = s_red[0][27];
+        s_keep[1] = s_red[0][28];
+        s_keep[2] = s_red[0][29];
+      }
+    }
+    __syncthreads();
+  }
+  }  // rounds
+  // state write-back (block 0, thread 0): the pose and the LAST linearisation
+  if (blockIdx.x == 0 && tid == 0 && rounds > 0) {
+    vo_picp_state& st = p.st->s;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) st.T[j * 4 + i] = s_T[j * 3 + i];
+    st.T[3] = st.T[7] = st.T[11] = 0.f;
+    st.T[15] = 1.f;
+#pragma unroll
+    for (int i = 0; i < 36; ++i) st.H[i] = s_H[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) st.b[i] = s_b[i];
+    st.chi_inliers = s_keep[0];
+    st.chi_outliers = s_keep[1];
+    st.num_inliers = __float_as_int(s_keep[2]);
+    st.rounds_done += rounds;
+    st.last_ok = s_keep[3] != 0.f ? 1 : 0;
+  }
+}
+
 }  // namespace vo
 
 // =================================================================================================
@@ -750,7 +714,6 @@ using namespace vo;
 struct vo_picp_s {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaStream_t capture_stream = nullptr;
   bool own_stream = false;
   vo_camera cam{};
   bool have_cam = false;
@@ -765,26 +728,7 @@ struct vo_picp_s {
   const int32_t* pairs = nullptr;
   int64_t n_world = 0, n_image = 0, n_pairs = 0;
   int grid = 0;
-  // CUDA graphs of `rounds` back-to-back launches, keyed by everything baked into the nodes
-  struct GraphKey {
-    const void *world, *image, *pairs, *partials;
-    int64_t n;
-    int keep, rounds, grid;
-    float thr, damping;
-    int min_inliers;
-    bool operator<(const GraphKey& o) const {
-      return std::tie(world, image, pairs, partials, n, keep, rounds, grid, thr, damping,
-                      min_inliers) < std::tie(o.world, o.image, o.pairs, o.partials, o.n, o.keep,
-                                              o.rounds, o.grid, o.thr, o.damping, o.min_inliers);
-    }
-  };
-  std::map<GraphKey, cudaGraphExec_t> graphs;
 };
-
-static void picp_drop_graphs(vo_picp_s* h) {
-  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
-  h->graphs.clear();
-}
 
 static int picp_upload_state(vo_picp_s* h) {
   int rc = h->state_buf.reserve(sizeof(PicpDeviceState));
@@ -823,7 +767,7 @@ static int picp_fill_params(vo_picp_s* h, int keep_outliers, PicpParams* p) {
 static int picp_pick_grid(vo_picp_s* h) {
   const int sms = num_sms(h->device);
   int per_sm = 2;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, picp_round_kernel<false, true>, PICP_THREADS,
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, picp_stream_kernel<false, true>, PICP_THREADS,
                                                 PICP_SMEM_BYTES);
   if (per_sm < 1) per_sm = 1;
   const int64_t full = (int64_t)sms * per_sm;
@@ -867,8 +811,6 @@ int vo_picp_destroy(vo_picp_t h) {
   if (!h) return VO_OK;
   DeviceGuard g(h->device);
   cudaStreamSynchronize(h->stream);
-  picp_drop_graphs(h);
-  if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
   h->world_buf.release();
   h->image_buf.release();
   h->pairs_buf.release();
@@ -1002,10 +944,10 @@ static int picp_compute_common(vo_picp_t h, int keep_outliers, int rounds, const
   if (rounds == 0) return VO_OK;
   DeviceGuard g(h->device);
   if (!h->smem_opted_in) {  // the staging ring needs the opt-in shared-memory carve-out (per device)
-    VO_CUDA(cudaFuncSetAttribute(picp_round_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_SMEM_BYTES));
-    VO_CUDA(cudaFuncSetAttribute(picp_round_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_SMEM_BYTES));
-    VO_CUDA(cudaFuncSetAttribute(picp_round_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_SMEM_BYTES));
-    VO_CUDA(cudaFuncSetAttribute(picp_round_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_SMEM_BYTES));
+    VO_CUDA(cudaFuncSetAttribute(picp_stream_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_SMEM_BYTES));
+    VO_CUDA(cudaFuncSetAttribute(picp_stream_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_SMEM_BYTES));
+    VO_CUDA(cudaFuncSetAttribute(picp_stream_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_SMEM_BYTES));
+    VO_CUDA(cudaFuncSetAttribute(picp_stream_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_SMEM_BYTES));
     VO_CUDA(cudaFuncSetAttribute(picp_resident_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_RES_SMEM));
     VO_CUDA(cudaFuncSetAttribute(picp_resident_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_RES_SMEM));
     VO_CUDA(cudaFuncSetAttribute(picp_resident_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_RES_SMEM));
@@ -1013,7 +955,7 @@ static int picp_compute_common(vo_picp_t h, int keep_outliers, int rounds, const
     h->smem_opted_in = true;
   }
   const int grid = picp_pick_grid(h);
-  int rc = h->partials_buf.reserve((size_t)grid * PICP_NACC * sizeof(float));
+  int rc = h->partials_buf.reserve((size_t)2 * grid * PICP_NACC * sizeof(float));
   if (rc) return rc;
   PicpParams p;
   picp_fill_params(h, keep_outliers, &p);
@@ -1028,8 +970,8 @@ static int picp_compute_common(vo_picp_t h, int keep_outliers, int rounds, const
   const float* K = h->cam.K;
   const bool pinhole = !h->force_general && K[1] == 0.f && K[2] == 0.f && K[3] == 0.f &&
                        K[5] == 0.f && K[8] == 1.f;
-  auto kernel = pinhole ? (p.keep_outliers ? picp_round_kernel<true, true> : picp_round_kernel<true, false>)
-                        : (p.keep_outliers ? picp_round_kernel<false, true> : picp_round_kernel<false, false>);
+  auto kernel = pinhole ? (p.keep_outliers ? picp_stream_kernel<true, true> : picp_stream_kernel<true, false>)
+                        : (p.keep_outliers ? picp_stream_kernel<false, true> : picp_stream_kernel<false, false>);
   if (h->n_pairs <= PICP_RES_MAX && !h->force_stream) {
     // a frame-sized problem: every round inside one resident thread-block cluster
     auto rk = pinhole ? (p.keep_outliers ? picp_resident_kernel<true, true> : picp_resident_kernel<true, false>)
@@ -1054,44 +996,14 @@ static int picp_compute_common(vo_picp_t h, int keep_outliers, int rounds, const
     VO_LAUNCH_CHECK();
     return VO_OK;
   }
-  if (rounds < 4) {
-    for (int r = 0; r < rounds; ++r) {
-      kernel<<<grid, PICP_THREADS, PICP_SMEM_BYTES, h->stream>>>(p);
-      VO_LAUNCH_CHECK();
-    }
-    return VO_OK;
+  // streaming kernel: ONE cooperative launch runs every round (grid-wide barrier per round)
+  {
+    int rounds_arg = rounds;
+    void* args[] = {(void*)&p, (void*)&rounds_arg};
+    VO_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3((unsigned)grid), dim3(PICP_THREADS),
+                                        args, PICP_SMEM_BYTES, h->stream));
+    VO_LAUNCH_CHECK();
   }
-  // many rounds: replay a captured graph of `rounds` launches (one submit, no per-launch
-  // driver work between rounds)
-  vo_picp_s::GraphKey key{h->world, h->image, h->pairs, h->partials_buf.p, h->n_pairs,
-                          p.keep_outliers, rounds, pinhole ? -grid : grid, h->thr, h->damping,
-                          h->min_inliers};
-  auto it = h->graphs.find(key);
-  if (it == h->graphs.end()) {
-    if (h->graphs.size() > 16) picp_drop_graphs(h);
-    cudaGraph_t graph = nullptr;
-    // capture on a private stream: the caller's stream may be the legacy default stream,
-    // which cannot be captured
-    if (!h->capture_stream)
-      VO_CUDA(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
-    VO_CUDA(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
-    for (int r = 0; r < rounds; ++r) kernel<<<grid, PICP_THREADS, PICP_SMEM_BYTES, h->capture_stream>>>(p);
-    cudaError_t e = cudaStreamEndCapture(h->capture_stream, &graph);
-    if (e != cudaSuccess) {
-      set_error("cudaStreamEndCapture -> %s", cudaGetErrorString(e));
-      return VO_ERR_CUDA;
-    }
-    cudaGraphExec_t exec = nullptr;
-    e = cudaGraphInstantiate(&exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) {
-      set_error("cudaGraphInstantiate -> %s", cudaGetErrorString(e));
-      return VO_ERR_CUDA;
-    }
-    it = h->graphs.emplace(key, exec).first;
-  }
-  VO_CUDA(cudaGraphLaunch(it->second, h->stream));
-  g_launches.fetch_add(rounds);
   return VO_OK;
 }
 

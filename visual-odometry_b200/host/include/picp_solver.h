@@ -6,7 +6,7 @@
 // launch (projection, 2x6 Jacobians, robust weights, the 6x6 H / b reduction, the LDL^T solve and
 // the pose update all stay on the device), and the host only synchronises when an accessor is
 // read.  compute(correspondences, keep_outliers, n) is the additive multi-round entry: n rounds
-// as one CUDA-graph launch.
+// in one kernel launch.
 #pragma once
 #include <vector>
 
