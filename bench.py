@@ -375,7 +375,8 @@ def bench_picp(torch, vo, synth, args, cores):
                 "d2h_bytes_per_step": 268},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                      "frac": achieved / hbm, **traffic_fields("picp", n_gen == 10_000_000),
-                     "algorithmic_bytes_per_launch": PICP_BYTES_PER_CORR * n_corr,
+                     # one cooperative launch runs all `rounds` Gauss-Newton iterations
+                     "algorithmic_bytes_per_launch": PICP_BYTES_PER_CORR * n_corr * rounds,
                      "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         "cpu_baseline": {"value": len(sub) / cpu_dt, "unit": "point-iters/s", "cores": 1,
                          "kind": "port", "sample": f"1 round over {len(sub)} correspondences"},
