@@ -94,13 +94,15 @@ def test_compute_graph_path_equals_launch_loop_streaming(vo, synth, monkeypatch)
     b.close()
 
 
-@pytest.mark.parametrize("n_corr", [1, 2, 3, 77, 1024, 1025, 2049, 4097, 8193, 30001, 65536])
+@pytest.mark.parametrize("n_corr", [1, 2, 3, 77, 1024, 1025, 2049, 4097, 8193, 30001, 65536, 65537,
+                                    200001])
 @pytest.mark.parametrize("keep", [False, True])
 def test_resident_kernel_matches_streaming_kernel(vo, synth, monkeypatch, n_corr, keep):
     """n <= 65536 correspondences run every round inside one resident thread-block cluster of 1, 2,
-    4 or 8 CTAs (shared-memory copy of the points, DSMEM reduction); VO_PICP_FORCE_STREAM=1 sends
-    the same problem through the streaming kernel.  The two differ only in summation order."""
-    pr = synth.picp_problem(70000, seed=29, outlier_frac=0.05)
+    4 or 8 CTAs (shared-memory copy of the points, DSMEM reduction), up to SMs x 8192 inside the
+    shared memory of the whole chip (cooperative launch, grid barrier); VO_PICP_FORCE_STREAM=1 sends
+    the same problem through the streaming kernel.  The three differ only in summation order."""
+    pr = synth.picp_problem(70000 if n_corr <= 65536 else 215000, seed=29, outlier_frac=0.05)
     pairs = pr["pairs"][:n_corr]
     assert len(pairs) == n_corr
     cam = vo.Camera(pr["rows"], pr["cols"], pr["z_near"], pr["z_far"], pr["K"], np.eye(4))

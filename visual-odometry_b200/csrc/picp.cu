@@ -356,13 +356,18 @@ __device__ __noinline__ bool picp_solve_local(const PicpParams& p, const float* 
   return true;
 }
 
-template <bool PINHOLE, bool KEEP>
+// GRID == false: one thread-block cluster (<= 65536 correspondences), partials exchanged through
+// DSMEM and a cluster barrier.  GRID == true: the whole chip — one CTA per SM, cooperative launch,
+// up to SMs x 8192 correspondences (1.2e6 on a B200) resident in the SMs' shared memory; partial
+// rows go through global memory (L2) and a grid-wide barrier, and every CTA sums all of them.
+template <bool PINHOLE, bool KEEP, bool GRID>
 __global__ void __launch_bounds__(PICP_RES_THREADS, 1)
 picp_resident_kernel(const PicpParams p, const int rounds) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
-  const int csize = (int)cluster.num_blocks();
-  const int rank = (int)cluster.block_rank();
+  cg::grid_group grid = cg::this_grid();
+  const int csize = GRID ? (int)gridDim.x : (int)cluster.num_blocks();
+  const int rank = GRID ? (int)blockIdx.x : (int)cluster.block_rank();
   extern __shared__ __align__(16) unsigned char picp_ring[];
   f2_t* pts = reinterpret_cast<f2_t*>(picp_ring);  // [5][PICP_RES_SLOTS]
   constexpr int W = PICP_RES_THREADS / 32;
@@ -407,7 +412,8 @@ picp_resident_kernel(const PicpParams p, const int rounds) {
   }
   if (tid < 12) s_T[tid] = p.st->s.T[(tid / 3) * 4 + (tid % 3)];
   // every CTA's shared memory must exist before anyone pushes into it
-  cluster.sync();
+  if (GRID) __syncthreads();
+  else cluster.sync();
 
   __shared__ float s_H[36], s_b[6], s_keep[4];  // last linearisation, written by thread 0
   for (int round = 0; round < rounds; ++round) {
@@ -433,7 +439,7 @@ picp_resident_kernel(const PicpParams p, const int rounds) {
       f2_unpack(i < 21 ? a.h[i] : (i < 27 ? a.b[i - 21] : (i == 27 ? a.chi_in : a.chi_out)), lo, hi);
       v[i] = lo + hi;
     }
-    v[29] = (float)a.n_in;  // exact: at most 2^17 points per thread-block cluster
+    v[29] = (float)a.n_in;  // exact in FP32: at most 1.2e6 < 2^24 points are resident
     v[30] = v[31] = 0.f;
     s_red[warp][lane] = warp_reduce_transposed(v);
     __syncthreads();
@@ -441,14 +447,47 @@ picp_resident_kernel(const PicpParams p, const int rounds) {
       float t = s_red[0][lane];
 #pragma unroll
       for (int wv = 1; wv < W; ++wv) t += s_red[wv][lane];
-      // push this CTA's partial into every CTA of the cluster (DSMEM)
-      float* slot = &s_part[round & 1][rank][lane];
-      for (int r = 0; r < csize; ++r) *cluster.map_shared_rank(slot, r) = t;
+      if (GRID) {
+        // this CTA's partial row, in the buffer of this round's parity
+        p.partials[((int64_t)(round & 1) * csize + rank) * PICP_NACC + lane] = t;
+      } else {
+        // push this CTA's partial into every CTA of the cluster (DSMEM)
+        float* slot = &s_part[round & 1][rank][lane];
+        for (int r = 0; r < csize; ++r) *cluster.map_shared_rank(slot, r) = t;
+      }
     }
-    cluster.sync();  // release/acquire: all partials of this round are visible everywhere
+    if (GRID) {
+      __threadfence();
+      grid.sync();
+      // warp w sums rows w, w+W, ... (all loads in flight at once), warp 0 then sums the W results
+      const float* part = p.partials + (int64_t)(round & 1) * csize * PICP_NACC;
+      float acc = 0.f;
+      for (int r0 = warp; r0 < csize; r0 += W * 4) {
+        float x[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = r0 + q * W;
+          x[q] = r < csize ? __ldcg(part + (int64_t)r * PICP_NACC + lane) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc += x[q];
+      }
+      __syncthreads();  // s_red is about to be reused
+      s_red[warp][lane] = acc;
+      __syncthreads();
+    } else {
+      cluster.sync();  // release/acquire: all partials of this round are visible everywhere
+    }
     if (warp == 0) {
-      float t = s_part[round & 1][0][lane];
-      for (int r = 1; r < csize; ++r) t += s_part[round & 1][r][lane];
+      float t;
+      if (GRID) {
+        t = s_red[0][lane];
+#pragma unroll
+        for (int wv = 1; wv < W; ++wv) t += s_red[wv][lane];
+      } else {
+        t = s_part[round & 1][0][lane];
+        for (int r = 1; r < csize; ++r) t += s_part[round & 1][r][lane];
+      }
       if (lane == 29) t = __int_as_float((int)t);  // the solve reads n_in as an integer
       s_red[0][lane] = t;
       __syncwarp();
@@ -481,7 +520,7 @@ picp_resident_kernel(const PicpParams p, const int rounds) {
     s.last_ok = s_keep[3] != 0.f ? 1 : 0;
   }
   // no CTA may exit while a peer can still push into its shared memory
-  cluster.sync();
+  if (!GRID) cluster.sync();
 }
 
 // ---- streaming kernel: more correspondences than the cluster's shared memory holds --------------
@@ -948,10 +987,14 @@ static int picp_compute_common(vo_picp_t h, int keep_outliers, int rounds, const
     VO_CUDA(cudaFuncSetAttribute(picp_stream_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_SMEM_BYTES));
     VO_CUDA(cudaFuncSetAttribute(picp_stream_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_SMEM_BYTES));
     VO_CUDA(cudaFuncSetAttribute(picp_stream_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_SMEM_BYTES));
-    VO_CUDA(cudaFuncSetAttribute(picp_resident_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_RES_SMEM));
-    VO_CUDA(cudaFuncSetAttribute(picp_resident_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_RES_SMEM));
-    VO_CUDA(cudaFuncSetAttribute(picp_resident_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_RES_SMEM));
-    VO_CUDA(cudaFuncSetAttribute(picp_resident_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_RES_SMEM));
+    VO_CUDA(cudaFuncSetAttribute(picp_resident_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_RES_SMEM));
+    VO_CUDA(cudaFuncSetAttribute(picp_resident_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_RES_SMEM));
+    VO_CUDA(cudaFuncSetAttribute(picp_resident_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_RES_SMEM));
+    VO_CUDA(cudaFuncSetAttribute(picp_resident_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_RES_SMEM));
+    VO_CUDA(cudaFuncSetAttribute(picp_resident_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_RES_SMEM));
+    VO_CUDA(cudaFuncSetAttribute(picp_resident_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_RES_SMEM));
+    VO_CUDA(cudaFuncSetAttribute(picp_resident_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_RES_SMEM));
+    VO_CUDA(cudaFuncSetAttribute(picp_resident_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICP_RES_SMEM));
     h->smem_opted_in = true;
   }
   const int grid = picp_pick_grid(h);
@@ -974,8 +1017,8 @@ static int picp_compute_common(vo_picp_t h, int keep_outliers, int rounds, const
                         : (p.keep_outliers ? picp_stream_kernel<false, true> : picp_stream_kernel<false, false>);
   if (h->n_pairs <= PICP_RES_MAX && !h->force_stream) {
     // a frame-sized problem: every round inside one resident thread-block cluster
-    auto rk = pinhole ? (p.keep_outliers ? picp_resident_kernel<true, true> : picp_resident_kernel<true, false>)
-                      : (p.keep_outliers ? picp_resident_kernel<false, true> : picp_resident_kernel<false, false>);
+    auto rk = pinhole ? (p.keep_outliers ? picp_resident_kernel<true, true, false> : picp_resident_kernel<true, false, false>)
+                      : (p.keep_outliers ? picp_resident_kernel<false, true, false> : picp_resident_kernel<false, false, false>);
     // one packed slot per thread where possible; cluster sizes 1, 2, 4, 8
     const int64_t nslots = (h->n_pairs + 1) / 2;
     int csize = 1;
@@ -995,6 +1038,24 @@ static int picp_compute_common(vo_picp_t h, int keep_outliers, int rounds, const
     VO_CUDA(cudaLaunchKernelEx(&cfg, rk, p, rounds));
     VO_LAUNCH_CHECK();
     return VO_OK;
+  }
+  // mid-sized problems: resident in the shared memory of the whole chip (one CTA per SM)
+  {
+    const int sms = num_sms(h->device);
+    const int64_t nslots = (h->n_pairs + 1) / 2;
+    if (!h->force_stream && nslots <= (int64_t)sms * PICP_RES_SLOTS) {
+      auto gk = pinhole ? (p.keep_outliers ? picp_resident_kernel<true, true, true> : picp_resident_kernel<true, false, true>)
+                        : (p.keep_outliers ? picp_resident_kernel<false, true, true> : picp_resident_kernel<false, false, true>);
+      rc = h->partials_buf.reserve((size_t)2 * sms * PICP_NACC * sizeof(float));
+      if (rc) return rc;
+      p.partials = h->partials_buf.as<float>();
+      int rounds_arg = rounds;
+      void* args[] = {(void*)&p, (void*)&rounds_arg};
+      VO_CUDA(cudaLaunchCooperativeKernel((const void*)gk, dim3((unsigned)sms), dim3(PICP_RES_THREADS), args,
+                                          PICP_RES_SMEM, h->stream));
+      VO_LAUNCH_CHECK();
+      return VO_OK;
+    }
   }
   // streaming kernel: ONE cooperative launch runs every round (grid-wide barrier per round)
   {
