@@ -5,21 +5,28 @@
 //
 // Design (DESIGN.md §NN has the full derivation):
 //   * set_map re-packs the caller's AoS rows [id | a0..a9] (44 B, the reference's Vector11f) into
-//     48-byte rows  [a0..a3][a4..a7][a8 a9 |a|^2 0]  so that a tile of TM rows is one contiguous,
-//     16-byte aligned block that a single 1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) stages
-//     into shared memory; STAGES tiles are in flight behind mbarriers.
-//   * the filter kernel keeps TQ queries per thread in registers as (-2*q_k) and evaluates, for
-//     every (query,row) pair,   acc = |m|^2 + sum_k (-2 q_k) m_k   = d^2 - |q|^2
-//     with 10 FFMA on the FP32 pipe (K=10 is too shallow for tensor cores) and one FMNMX that
-//     folds the row into a per-query running minimum.  Rows are broadcast LDS.128 reads.
+//     48-byte rows  [a0..a3][a4 a5 |a|^2_F |a|^2][a6..a9]  (|a|^2_F over the first NN_FDIM
+//     coefficients) so that a tile of TM rows is one contiguous, 16-byte aligned block that a single
+//     1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) stages into shared memory; STAGES tiles are in
+//     flight behind mbarriers.
+//   * the streaming filter is a PARTIAL-DISTANCE test: the squared distance over the first NN_FDIM
+//     dimensions is a lower bound of the full one, so a row whose partial distance is not below the
+//     bound cannot be the answer.  Each thread keeps the first NN_FDIM coefficients of TQ queries
+//     in registers as (-2*q_k), packed two queries per FP32 pair, and evaluates, for every
+//     (query,row) pair,   acc = |m|^2_F + sum_{k<F} (-2 q_k) m_k   = d_F^2 - |q|^2_F
+//     with NN_FDIM packed FMAs per PAIR of queries (SASS FFMA2; K=10 is too shallow for tensor
+//     cores) and one 3-input minimum per two rows.  Rows are two broadcast LDS.128 reads.
 //   * a pair can only be the reference's answer if its d^2 (in the reference's own rounding
-//     order) is < bound; the FMA form differs from that by at most eps_q (proved in DESIGN.md), so
-//     after every tile a thread whose running minimum dips below (bound - |q|^2 + eps_q) re-scans
-//     that tile for that query, recomputes the candidate rows in the REFERENCE order with
-//     __fsub_rn/__fmul_rn/__fadd_rn (no contraction) and merges (d2_bits<<32 | row) into the
+//     order) is < bound; the FMA form differs from that by at most eps_q, so
+//     after every tile a warp whose running minimum dipped below (bound - |q|^2_F + eps_q) for
+//     some query re-scans that tile for that query TOGETHER (lane l takes rows l, l+32, ...): full
+//     10-D FMA test first, then the candidates in the REFERENCE order with
+//     __fsub_rn/__fmul_rn/__fadd_rn (no contraction), merged as (d2_bits<<32 | row) into the
 //     query's 64-bit key with atomicMin — strict minimum, lowest row index on ties, exactly
 //     brute_force_search.h:30-40.  The bound then tightens to the best exact d^2 found, so the
-//     kernel is a correct argmin for any radius, not only small ones.
+//     kernel is a correct argmin for any radius and any data; how much the partial test prunes
+//     (all but ~1.6e-6 of the rows for uniform appearances and radius 0.1) only decides how often
+//     the re-scan runs.
 //   * no float atomics, no data-dependent result: indices are bit-exact vs the oracle.
 #include <float.h>
 #include <math.h>
@@ -32,6 +39,7 @@
 namespace vo {
 
 constexpr int NN_DIM = 10;            // fast-path dimension (Vector11f minus the id column)
+constexpr int NN_FDIM = 5;            // leading dimensions the streaming filter looks at (<= 6)
 constexpr int NN_TM = 128;            // map rows per shared-memory tile
 constexpr int NN_STAGES = 4;          // TMA stages in flight
 constexpr int NN_ROW_BYTES = 48;      // packed row: 3 x float4
@@ -136,24 +144,28 @@ nn_repack_kernel(const float* __restrict__ rows, int64_t n_rows, int64_t n_rows_
   float mm_for_max = 0.f;
   if (r < n_rows_padded) {
     float v[NN_DIM];
-    float mm;
+    float mm, mm6;
     if (r < n_rows) {
       const float* src = rows + r * (int64_t)row_stride + skip;
 #pragma unroll
       for (int k = 0; k < NN_DIM; ++k) v[k] = __ldg(src + k);
-      mm = 0.f;
+      mm6 = 0.f;
 #pragma unroll
-      for (int k = 0; k < NN_DIM; ++k) mm = fmaf(v[k], v[k], mm);
+      for (int k = 0; k < NN_FDIM; ++k) mm6 = fmaf(v[k], v[k], mm6);
+      mm = mm6;
+#pragma unroll
+      for (int k = NN_FDIM; k < NN_DIM; ++k) mm = fmaf(v[k], v[k], mm);
       if (isfinite(mm)) mm_for_max = mm;
     } else {
 #pragma unroll
       for (int k = 0; k < NN_DIM; ++k) v[k] = 0.f;
-      mm = INFINITY;
+      mm = mm6 = INFINITY;
     }
+    // [a0 a1 a2 a3] [a4 a5 |a|^2(first 6) |a|^2] [a6 a7 a8 a9]: the filter reads the first 32 bytes
     float4* dst = packed + r * 3;
     dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-    dst[2] = make_float4(v[8], v[9], mm, 0.f);
+    dst[1] = make_float4(v[4], v[5], mm6, mm);
+    dst[2] = make_float4(v[6], v[7], v[8], v[9]);
   }
   // block max of |m|^2 (non-negative -> uint order == float order)
   unsigned int bits = __float_as_uint(mm_for_max);
@@ -177,58 +189,82 @@ struct NNParams {
   unsigned long long* keys; // per query, pre-set to NN_KEY_NONE
 };
 
-// filter threshold for one query:  acc < (bound - |q|^2) + eps_q  is implied by  d2_ref < bound.
-// eps_q bounds |acc + |q|^2 - d2_ref| (FMA chain, |m|^2 and |q|^2 roundings); DESIGN.md §NN.
-__device__ __forceinline__ float nn_filter_threshold(const float (&qn)[NN_DIM], float bound,
-                                                     float mm_max) {
-  float qq = 0.f;
-#pragma unroll
-  for (int k = 0; k < NN_DIM; ++k) {
-    const float q = -0.5f * qn[k];
-    qq = fmaf(q, q, qq);
-  }
+// Filter thresholds for one query.  With u = 2^-24, d2_ref < bound implies
+//   full:     acc10 = |m|^2   + sum_{k<10} (-2 q_k) m_k  <  (bound - |q|^2)   + eps
+//   partial:  acc6  = |m|^2_6 + sum_{k<6}  (-2 q_k) m_k  <  (bound - |q|^2_6) + eps
+// (the partial squared distance over the first NN_FDIM dimensions is a lower bound of the full
+// one), where eps = 64u(|q|^2 + max|m|^2) + 32u|bound| covers the FMA chains and the roundings of
+// |m|^2, |q|^2 and of the reference's own d2.  `qn` is the query scaled by -2.
+__device__ __forceinline__ float nn_eps(float qq, float bound, float mm_max) {
   const float u64 = 64.f * 5.9604645e-8f;  // 64 * 2^-24
-  const float eps = u64 * (qq + mm_max) + 0.5f * u64 * fabsf(bound);
-  return (bound - qq) + eps;
+  return u64 * (qq + mm_max) + 0.5f * u64 * fabsf(bound);
+}
+__device__ __forceinline__ void nn_query_norms(const float (&qn)[NN_DIM], float* qq6, float* qq) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NN_FDIM; ++k) {
+    const float q = -0.5f * qn[k];
+    s = fmaf(q, q, s);
+  }
+  *qq6 = s;
+#pragma unroll
+  for (int k = NN_FDIM; k < NN_DIM; ++k) {
+    const float q = -0.5f * qn[k];
+    s = fmaf(q, q, s);
+  }
+  *qq = s;
+}
+__device__ __forceinline__ float nn_threshold_partial(float qq6, float qq, float bound, float mm_max) {
+  return (bound - qq6) + nn_eps(qq, bound, mm_max);
+}
+__device__ __forceinline__ float nn_threshold_full(float qq, float bound, float mm_max) {
+  return (bound - qq) + nn_eps(qq, bound, mm_max);
 }
 
-// Slow path: re-scan one tile for ONE query, exact arithmetic for the candidates — executed by the
-// whole warp (lane l takes rows l, l+32, ...), because in frame-to-frame association nearly every
-// query has a match, and a single lane walking 128 rows while 31 idle made the re-scans cost
-// several times the filter on frame-sized maps.  `qn` (the query, pre-scaled by -2), `tq` (its
-// filter threshold) and `key` are warp-uniform.  The running exact bound is NOT kept in
-// registers: it is the d2 stored in the query's global key (possibly improved by another map split
-// in the meantime).  A candidate is merged when d2 < norm^2 (strict, brute_force_search.h:35) and
+// Slow path: re-scan one tile for ONE query with the full distance, exact arithmetic for the
+// candidates — executed by the whole warp (lane l takes rows l, l+32, ...), because in
+// frame-to-frame association nearly every query has a match, and a single lane walking 128 rows
+// while 31 idle made the re-scans cost several times the filter on frame-sized maps.  The query is
+// re-read from global memory (warp-uniform address): the streaming loop only keeps its first
+// NN_FDIM coefficients in registers.  The running exact bound is NOT kept in registers either: it
+// is the d2 stored in the query's global key (possibly improved by another map split in the
+// meantime).  A candidate is merged when d2 < norm^2 (strict, brute_force_search.h:35) and
 // d2 <= best-so-far; among equal d2 the packed atomicMin keeps the lowest row (the reference's
-// first-match-wins order).  Returns the new bound (warp-uniform).
+// first-match-wins order).  Returns the query's new PARTIAL threshold (warp-uniform).
 __device__ __forceinline__ float nn_rescan_tile_warp(const float4* __restrict__ tile, int64_t row0,
-                                                     int64_t n_rows, const float (&qn)[NN_DIM],
-                                                     float tq, float radius2,
+                                                     int64_t n_rows, const float* __restrict__ query,
+                                                     float radius2, float mm_max,
                                                      unsigned long long* key) {
   const int lane = threadIdx.x & 31;
-  float q[NN_DIM];
+  float q[NN_DIM], qn[NN_DIM];
 #pragma unroll
-  for (int k = 0; k < NN_DIM; ++k) q[k] = -0.5f * qn[k];
+  for (int k = 0; k < NN_DIM; ++k) {
+    q[k] = __ldg(query + k);
+    qn[k] = -2.f * q[k];
+  }
+  float qq6, qq;
+  nn_query_norms(qn, &qq6, &qq);
   const unsigned long long k0 = *reinterpret_cast<volatile unsigned long long*>(key);
-  float best = (k0 == NN_KEY_NONE) ? radius2 : __uint_as_float(static_cast<unsigned int>(k0 >> 32));
+  const float best = (k0 == NN_KEY_NONE) ? radius2 : __uint_as_float(static_cast<unsigned int>(k0 >> 32));
+  const float tq = nn_threshold_full(qq, best, mm_max);
   float found = best;
 #pragma unroll
   for (int r = lane; r < NN_TM; r += 32) {
     const float4 a = tile[r * 3 + 0], b = tile[r * 3 + 1], c = tile[r * 3 + 2];
-    float acc = c.z;
+    float acc = b.w;
     acc = fmaf(qn[0], a.x, acc);
     acc = fmaf(qn[1], a.y, acc);
     acc = fmaf(qn[2], a.z, acc);
     acc = fmaf(qn[3], a.w, acc);
     acc = fmaf(qn[4], b.x, acc);
     acc = fmaf(qn[5], b.y, acc);
-    acc = fmaf(qn[6], b.z, acc);
-    acc = fmaf(qn[7], b.w, acc);
-    acc = fmaf(qn[8], c.x, acc);
-    acc = fmaf(qn[9], c.y, acc);
+    acc = fmaf(qn[6], c.x, acc);
+    acc = fmaf(qn[7], c.y, acc);
+    acc = fmaf(qn[8], c.z, acc);
+    acc = fmaf(qn[9], c.w, acc);
     if (acc < tq) {
       const int64_t row = row0 + r;
-      const float m[NN_DIM] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y};
+      const float m[NN_DIM] = {a.x, a.y, a.z, a.w, b.x, b.y, c.x, c.y, c.z, c.w};
       const float d2 = ref_sqdist<NN_DIM>(m, q);
       if (row < n_rows && d2 < radius2 && d2 <= best) {
         found = fminf(found, d2);
@@ -238,7 +274,8 @@ __device__ __forceinline__ float nn_rescan_tile_warp(const float4* __restrict__ 
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) found = fminf(found, __shfl_xor_sync(0xffffffffu, found, o));
-  return found;
+  // later rows only matter if they can reach d2 <= found
+  return nn_threshold_partial(qq6, qq, found, mm_max);
 }
 
 __device__ __forceinline__ float f_min3(float a, float b, float c) {
@@ -247,15 +284,15 @@ __device__ __forceinline__ float f_min3(float a, float b, float c) {
   return r;
 }
 
-// one map row against the TP query pairs of this thread: 10 FFMA2 per pair of queries
+// one map row against the TP query pairs of this thread: the partial distance over the first
+// NN_FDIM dimensions, NN_FDIM FFMA2 per pair of queries, two 16-byte shared-memory reads per row
 template <int TP>
 __device__ __forceinline__ void nn_row(const float4* __restrict__ row,
-                                       const unsigned long long (&q2)[TP][NN_DIM],
+                                       const unsigned long long (&q2)[TP][NN_FDIM],
                                        unsigned long long (&acc)[TP]) {
   const float4 a = row[0];
   const float4 b = row[1];
-  const float4 c = row[2];
-  const unsigned long long mm2 = f2_pack(c.z, c.z);
+  const unsigned long long mm2 = f2_pack(b.z, b.z);
 #pragma unroll
   for (int jp = 0; jp < TP; ++jp) {
     unsigned long long x = f2_fma(q2[jp][0], f2_pack(a.x, a.x), mm2);
@@ -263,11 +300,8 @@ __device__ __forceinline__ void nn_row(const float4* __restrict__ row,
     x = f2_fma(q2[jp][2], f2_pack(a.z, a.z), x);
     x = f2_fma(q2[jp][3], f2_pack(a.w, a.w), x);
     x = f2_fma(q2[jp][4], f2_pack(b.x, b.x), x);
-    x = f2_fma(q2[jp][5], f2_pack(b.y, b.y), x);
-    x = f2_fma(q2[jp][6], f2_pack(b.z, b.z), x);
-    x = f2_fma(q2[jp][7], f2_pack(b.w, b.w), x);
-    x = f2_fma(q2[jp][8], f2_pack(c.x, c.x), x);
-    acc[jp] = f2_fma(q2[jp][9], f2_pack(c.y, c.y), x);
+    if (NN_FDIM > 5) x = f2_fma(q2[jp][NN_FDIM > 5 ? 5 : 0], f2_pack(b.y, b.y), x);
+    acc[jp] = x;
   }
 }
 
@@ -312,14 +346,15 @@ nn_filter_kernel(const NNParams p) {
     }
   }
 
-  // queries of this thread, pre-scaled by -2 and packed two-by-two (query 2j in the low half,
-  // 2j+1 in the high half), and the per-query running minima of  d^2 - |q|^2
+  // the first NN_FDIM coefficients of this thread's queries, pre-scaled by -2 and packed two-by-two
+  // (query 2j in the low half, 2j+1 in the high half), and the per-query running minima of the
+  // partial  d^2 - |q|^2
   const float mm_max = __ldg(p.mm_max);
-  unsigned long long q2[TP][NN_DIM];
+  unsigned long long q2[TP][NN_FDIM];
   float mn[TQ];
 #pragma unroll
   for (int jp = 0; jp < TP; ++jp) {
-    float qn[2][NN_DIM];
+    float qf[2][NN_FDIM];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int j = 2 * jp + h;
@@ -327,19 +362,24 @@ nn_filter_kernel(const NNParams p) {
       float t;
       if (qi < p.n_queries) {
         const float* src = p.queries + qi * (int64_t)p.query_stride + p.skip;
+        float qn[NN_DIM];
 #pragma unroll
-        for (int k = 0; k < NN_DIM; ++k) qn[h][k] = -2.f * __ldg(src + k);
-        t = nn_filter_threshold(qn[h], p.bound, mm_max);
+        for (int k = 0; k < NN_DIM; ++k) qn[k] = -2.f * __ldg(src + k);
+        float qq6, qq;
+        nn_query_norms(qn, &qq6, &qq);
+        t = nn_threshold_partial(qq6, qq, p.bound, mm_max);
+#pragma unroll
+        for (int k = 0; k < NN_FDIM; ++k) qf[h][k] = qn[k];
       } else {
 #pragma unroll
-        for (int k = 0; k < NN_DIM; ++k) qn[h][k] = 0.f;
+        for (int k = 0; k < NN_FDIM; ++k) qf[h][k] = 0.f;
         t = -INFINITY;
       }
       tq_s[j * THREADS + tid] = t;
       mn[j] = INFINITY;
     }
 #pragma unroll
-    for (int k = 0; k < NN_DIM; ++k) q2[jp][k] = f2_pack(qn[0][k], qn[1][k]);
+    for (int k = 0; k < NN_FDIM; ++k) q2[jp][k] = f2_pack(qf[0][k], qf[1][k]);
   }
 
   int stage = 0;
@@ -368,25 +408,15 @@ nn_filter_kernel(const NNParams p) {
 #pragma unroll
     for (int j = 0; j < TQ; ++j) {
       const float tqj = tq_s[j * THREADS + tid];
-      float own[NN_DIM];
-#pragma unroll
-      for (int k = 0; k < NN_DIM; ++k) {
-        float lo, hi;
-        f2_unpack(q2[j >> 1][k], lo, hi);
-        own[k] = (j & 1) ? hi : lo;
-      }
       unsigned pending = __ballot_sync(0xffffffffu, mn[j] < tqj);
       while (pending) {
         const int src = __ffs(pending) - 1;
         pending &= pending - 1;
-        float qn[NN_DIM];
-#pragma unroll
-        for (int k = 0; k < NN_DIM; ++k) qn[k] = __shfl_sync(0xffffffffu, own[k], src);
-        const float tqs = __shfl_sync(0xffffffffu, tqj, src);
         const int64_t qi = qbase + (int64_t)j * THREADS + (tid & ~31) + src;
-        const float nb = nn_rescan_tile_warp(tile, t * NN_TM, p.n_rows, qn, tqs, p.bound, p.keys + qi);
-        // tighten: later rows only matter if they can reach d2 <= nb
-        if ((tid & 31) == src) tq_s[j * THREADS + tid] = fminf(tqj, nn_filter_threshold(own, nb, mm_max));
+        const float nt = nn_rescan_tile_warp(tile, t * NN_TM, p.n_rows,
+                                             p.queries + qi * (int64_t)p.query_stride + p.skip, p.bound,
+                                             mm_max, p.keys + qi);
+        if ((tid & 31) == src) tq_s[j * THREADS + tid] = fminf(tqj, nt);
       }
       mn[j] = INFINITY;
     }
@@ -464,7 +494,7 @@ __global__ void __launch_bounds__(128)
 nn_radius_kernel(const float* __restrict__ rows, int64_t n_rows, int row_stride, int skip, int dim,
                  const float* __restrict__ queries, int64_t n_queries, int query_stride,
                  int query_skip, float bound, int32_t* __restrict__ counts,
-                 int32_t* __restrict__ idx_out, int32_t max_per_query) {
+                 int32_t* __restrict__ idx_out, int32_t max_per_query, int packed) {
   const int lane = threadIdx.x & 31;
   const int64_t qi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (qi >= n_queries) return;
@@ -475,8 +505,17 @@ nn_radius_kernel(const float* __restrict__ rows, int64_t n_rows, int row_stride,
   for (int64_t base = 0; base < n_rows; base += 32) {
     const int64_t r = base + lane;
     bool hit = false;
-    if (r < n_rows)
-      hit = ref_sqdist_dyn(rows + r * (int64_t)row_stride + skip, q, dim) < bound;
+    if (r < n_rows) {
+      const float* src = rows + r * (int64_t)row_stride + skip;
+      if (packed) {  // fast-path layout: [a0..a3][a4 a5 . .][a6..a9]
+        float m[NN_DIM];
+#pragma unroll
+        for (int k = 0; k < NN_DIM; ++k) m[k] = src[k < 6 ? k : k + 2];  // two norms sit after a5
+        hit = ref_sqdist_dyn(m, q, NN_DIM) < bound;
+      } else {
+        hit = ref_sqdist_dyn(src, q, dim) < bound;
+      }
+    }
     const unsigned int ballot = __ballot_sync(0xffffffffu, hit);
     if (hit && idx_out) {
       const int32_t pos = total + __popc(ballot & ((1u << lane) - 1u));
@@ -580,18 +619,20 @@ static int nn_launch_filter(vo_nn_s* h, const float* queries_dev, int64_t nq, in
   // whole tiles plus ONE remainder launch whose per-thread query count is the smallest that holds
   // it: a sharded batch (Q/8 = 12500 queries = 4.07 tiles) then costs 4 waves plus a thin one
   // instead of 5 (what near-linear scaling of the query-sharded sweep hinges on).
-  constexpr int64_t WIDE = 8 * 384;
+  constexpr int64_t WIDE = 12 * 384;
   // a map of only a few tiles cannot feed 148 wide CTAs with work: frame-sized problems take the
   // narrow register tile whatever the query count
   if (nq <= 8192 || h->n_tiles < 2 * (int64_t)sms) return launch_small(0, nq);
   const int64_t full = nq / WIDE * WIDE, rem = nq - full;
-  int rc = launch(nn_filter_kernel<8, 384>, 8, 384, 0, full);
+  int rc = launch(nn_filter_kernel<12, 384>, 12, 384, 0, full);
   if (rc || rem == 0) return rc;
   if (rem <= 512) return launch(nn_filter_kernel<2, 256>, 2, 256, full, rem);
   if (rem <= 2 * 384) return launch(nn_filter_kernel<2, 384>, 2, 384, full, rem);
   if (rem <= 4 * 384) return launch(nn_filter_kernel<4, 384>, 4, 384, full, rem);
   if (rem <= 6 * 384) return launch(nn_filter_kernel<6, 384>, 6, 384, full, rem);
-  return launch(nn_filter_kernel<8, 384>, 8, 384, full, rem);
+  if (rem <= 8 * 384) return launch(nn_filter_kernel<8, 384>, 8, 384, full, rem);
+  if (rem <= 10 * 384) return launch(nn_filter_kernel<10, 384>, 10, 384, full, rem);
+  return launch(nn_filter_kernel<12, 384>, 12, 384, full, rem);
 }
 
 static int nn_set_map_common(vo_nn_s* h, const float* rows_dev, int64_t n_rows, int row_stride,
@@ -829,7 +870,8 @@ int vo_nn_radius_search(vo_nn_t h, const float* queries_host, int64_t n_queries,
   nn_radius_kernel<<<(unsigned)blocks, threads, 0, h->stream>>>(
       h->rows_dev, h->n_rows, h->map_stride, h->map_skip, h->dim, h->q_stage.as<float>(),
       n_queries, query_stride, h->skip, norm * norm, h->cnt_stage.as<int32_t>(),
-      (idx_out_host && lbytes) ? h->list_stage.as<int32_t>() : nullptr, max_per_query);
+      (idx_out_host && lbytes) ? h->list_stage.as<int32_t>() : nullptr, max_per_query,
+      h->fast ? 1 : 0);
   VO_LAUNCH_CHECK();
   VO_CUDA(cudaMemcpyAsync(counts_host, h->cnt_stage.p, (size_t)n_queries * sizeof(int32_t),
                           cudaMemcpyDeviceToHost, h->stream));
