@@ -4,26 +4,24 @@
 // src/picp_solver.cpp:16-112) with Camera::projectPoint inlined (include/camera.h:25-37) and
 // v2tEuler / Rotation{X,Y,Z} / skew (include/utils.h:16-102).
 //
-// One launch == one oneRound():
-//   * grid = a multiple of the SM count, grid-stride over the correspondences; every thread
-//     batches PICP_UNROLL independent (pair -> world point, image point) gathers before it does
-//     any arithmetic so that enough bytes are in flight to cover HBM latency;
-//   * per correspondence: pc = T*p, z-range / image-bounds rejection, e = proj - meas,
-//     J = Jp*K*[I | skew(-pc)] in the factored form  A = iz*(K_row - uv*K_row2), J = [A | A*S]
-//     (K is treated as a general 3x3), robust weight, and the 21 upper-triangular entries of
-//     lambda*J^T J plus the 6 of lambda*J^T e accumulated in registers;
-//   * warp-shuffle + shared-memory block reduction -> one 32-float partial per block in global
-//     memory -> the LAST block to finish (atomic ticket) sums the partials in a fixed order, adds
-//     the damping, runs the pivoted 6x6 LDL^T solve, builds v2tEuler(dx) and left-multiplies the
-//     pose.  No float atomics: results are run-to-run deterministic.
-// The pose lives in device memory and is re-read by the next launch, so `rounds` launches are
-// simply queued (or replayed from a CUDA graph): no host round-trip between rounds.
+// One launch == ALL the rounds of a vo_picp_compute() call; three kernels by problem size:
+//   * picp_resident_kernel<.., GRID=false>  (<= 65536 correspondences, every VO frame): one
+//     thread-block cluster keeps the correspondences in shared memory, DSMEM reduction;
+//   * picp_resident_kernel<.., GRID=true>   (<= SMs x 8192): the same across the whole chip,
+//     cooperative launch, partial rows through L2 and a grid barrier;
+//   * picp_stream_kernel                    (larger): cooperative launch, the correspondences are
+//     streamed from HBM through a per-thread cp.async ring every round.
+// Shared arithmetic (picp_point2), per correspondence: pc = T*p, z-range / image-bounds rejection,
+// e = proj - meas, J = Jp*K*[I | skew(-pc)] in the factored form  A = iz*(K_row - uv*K_row2),
+// J = [A | A*S]  (K is treated as a general 3x3), robust weight, and the 21 upper-triangular
+// entries of lambda*J^T J plus the 6 of lambda*J^T e accumulated in registers — two correspondences
+// at a time in the lanes of packed FP32 pairs.  Reductions are fixed-order (no float atomics:
+// results are run-to-run deterministic); the damping, the pivoted 6x6 LDL^T solve, v2tEuler(dx)
+// and the pose update run on the device, so there is no host round-trip between rounds.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
-#include <map>
-#include <tuple>
 
 #include <cooperative_groups.h>
 
@@ -38,7 +36,6 @@ constexpr int PICP_NACC = 32;  // 21 H + 6 b + chi_in + chi_out + n_in (as float
 
 struct PicpDeviceState {
   vo_picp_state s;       // what vo_picp_get_state copies back
-  unsigned int ticket;   // last-block-done counter
 };
 
 struct PicpParams {

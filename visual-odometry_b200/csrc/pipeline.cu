@@ -397,6 +397,16 @@ int vo_pipe_create(vo_pipe_t* out, int device, const vo_camera* cam, int64_t max
   VO_REQUIRE(device >= 0 && device < n, VO_ERR_ARG, "bad device ordinal");
   DeviceGuard g(device);
   vo_pipe_s* h = new vo_pipe_s();
+  // a CUDA failure from here on releases everything acquired so far
+#define PIPE_TRY(expr)                                                  \
+  do {                                                                  \
+    const cudaError_t e_ = (expr);                                      \
+    if (e_ != cudaSuccess) {                                            \
+      set_error("vo_pipe_create: %s -> %s", #expr, cudaGetErrorString(e_)); \
+      vo_pipe_destroy(h);                                               \
+      return VO_ERR_CUDA;                                               \
+    }                                                                   \
+  } while (0)
   h->device = device;
   h->cam = *cam;
   h->max_pts = max_points_per_frame;
@@ -440,17 +450,18 @@ int vo_pipe_create(vo_pipe_t* out, int device, const vo_camera* cam, int64_t max
       (rc = h->map_app.reserve((size_t)h->max_map * 40 + 16)) ||
       (rc = h->map_slots.reserve((size_t)cap * 4)) || (rc = h->map_last.reserve((size_t)cap * 4)))
     return fail(rc);
-  VO_CUDA(cudaMemsetAsync(h->counts.p, 0, C_N * 8, h->stream));
-  VO_CUDA(cudaMemsetAsync(h->map_slots.p, 0xFF, (size_t)cap * 4, h->stream));
-  VO_CUDA(cudaMemsetAsync(h->map_last.p, 0xFF, (size_t)cap * 4, h->stream));
-  VO_CUDA(cudaFuncSetAttribute(assoc_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  PIPE_TRY(cudaMemsetAsync(h->counts.p, 0, C_N * 8, h->stream));
+  PIPE_TRY(cudaMemsetAsync(h->map_slots.p, 0xFF, (size_t)cap * 4, h->stream));
+  PIPE_TRY(cudaMemsetAsync(h->map_last.p, 0xFF, (size_t)cap * 4, h->stream));
+  PIPE_TRY(cudaFuncSetAttribute(assoc_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                PIPE_MAX_POINTS * (int)sizeof(int)));
   iso_identity(h->X_curr);
   iso_identity(h->history);
-  VO_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->pinned), C_N * 8 + sizeof(vo_picp_state) + 64,
+  PIPE_TRY(cudaHostAlloc(reinterpret_cast<void**>(&h->pinned), C_N * 8 + sizeof(vo_picp_state) + 64,
                         cudaHostAllocDefault));
-  VO_CUDA(cudaStreamSynchronize(h->stream));
-  VO_CUDA(cudaEventRecord(h->map_done, h->map_stream));  // "no merge pending"
+  PIPE_TRY(cudaStreamSynchronize(h->stream));
+  PIPE_TRY(cudaEventRecord(h->map_done, h->map_stream));  // "no merge pending"
+#undef PIPE_TRY
   *out = h;
   return VO_OK;
 }
