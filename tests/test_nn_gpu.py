@@ -69,6 +69,33 @@ def test_remainder_launch_variants_vs_oracle(vo, oracle, synth, Q):
     assert np.array_equal(d2[oi >= 0], od[oi >= 0])
 
 
+@pytest.mark.parametrize("kind", ["constant_prefix", "clustered"])
+def test_partial_filter_worst_cases_stay_exact(vo, oracle, kind):
+    """The streaming filter only looks at the first 5 of the 10 dimensions (a lower bound of the
+    distance); data on which that bound prunes nothing — every row equal to the query in those
+    dimensions, or all rows in one tight cluster — must only cost re-scans, never exactness."""
+    rng = np.random.RandomState(11)
+    M, Q = 6000, 900
+    m = rng.uniform(-1, 1, (M, 11)).astype(np.float32)
+    q = rng.uniform(-1, 1, (Q, 11)).astype(np.float32)
+    if kind == "constant_prefix":
+        m[:, 1:6] = 0.25  # the partial distance of every (query,row) pair is identical
+        q[:, 1:6] = 0.25
+        q[::2, 6:] = m[rng.randint(0, M, (Q + 1) // 2), 6:]  # half the queries have an exact match
+    else:
+        centre = rng.uniform(-1, 1, 11).astype(np.float32)
+        m = (centre + rng.uniform(-0.03, 0.03, (M, 11))).astype(np.float32)
+        q = (centre + rng.uniform(-0.03, 0.03, (Q, 11))).astype(np.float32)
+    nn = vo.NNIndex(0)
+    nn.set_map(m)
+    idx, d2 = nn.best_match(q, 0.1, want_d2=True)
+    nn.close()
+    oi, od = oracle.nn_best_match(m, q, 0.1)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(d2[oi >= 0], od[oi >= 0])
+    assert (oi >= 0).sum() > Q // 3
+
+
 def test_large_radius_true_argmin(vo, oracle):
     """radius large enough that EVERY row is a candidate: exercises the bound-tightening path."""
     rng = np.random.RandomState(5)
