@@ -537,6 +537,59 @@ picp_stream_kernel(const PicpParams p, const int rounds) {
   const int warp = tid >> 5, lane = tid & 31;
   if (tid < 12) s_T[tid] = p.st->s.T[(tid / 3) * 4 + (tid % 3)];
   __syncthreads();
+
+  // ---- asynchronous stream over the correspondences ------------------------------------------
+  // thread t owns items t, t+stride, t+2*stride, ...; they are consumed in batches of PICP_UNROLL.
+  const int n = (int)p.n_pairs;
+  const int stride = (int)gridDim.x * PICP_THREADS;
+  const int i0 = (int)blockIdx.x * PICP_THREADS + tid;
+  const int mine = i0 < n ? (n - i0 + stride - 1) / stride : 0;  // items of this thread
+  const int nb = mine / PICP_UNROLL;                             // full batches
+  const int2* pp = p.pairs + i0;
+  extern __shared__ __align__(16) unsigned char picp_ring[];
+  const uint32_t ring = smem_u32(picp_ring) + (uint32_t)tid * 8u;
+  auto issue_pairs = [&](int b, int slot) {  // P(b)
+    if (b < nb) {
+#pragma unroll
+      for (int u = 0; u < PICP_UNROLL; ++u)
+        cp_async8(ring + picp_prs_off(slot, u), pp + (int64_t)(b * PICP_UNROLL + u) * stride);
+    }
+  };
+  auto issue_gathers = [&](int b, int slot) {  // G(b); P(b) has landed
+    if (b < nb) {
+#pragma unroll
+      for (int u = 0; u < PICP_UNROLL; ++u) {
+        const int2 pr = lds_int2(ring + picp_prs_off(slot, u));
+        const float* wp = p.world + 3 * (int64_t)pr.y;  // .second -> world (:67)
+        const float* ip = p.image + 2 * (int64_t)pr.x;  // .first -> image (:66)
+        const uint32_t half = (uint32_t)(u & 1) * 4u;   // which half of the packed pair
+        cp_async4(ring + picp_pts_off(slot, u >> 1, 0) + half, wp);
+        cp_async4(ring + picp_pts_off(slot, u >> 1, 1) + half, wp + 1);
+        cp_async4(ring + picp_pts_off(slot, u >> 1, 2) + half, wp + 2);
+        cp_async4(ring + picp_pts_off(slot, u >> 1, 3) + half, ip);
+        cp_async4(ring + picp_pts_off(slot, u >> 1, 4) + half, ip + 1);
+      }
+    }
+  };
+  // The ring's fill does not depend on the pose, only the arithmetic does: the fill of round r+1
+  // (three dependent memory round-trips) is issued while round r is being reduced and solved.
+  auto fill_pairs = [&]() {  // P(0..DEPTH-1)
+#pragma unroll
+    for (int j = 0; j < PICP_DEPTH; ++j) issue_pairs(j, j % PICP_SLOTS);
+    cp_async_commit();
+  };
+  auto fill_gathers = [&]() {  // G(j) + P(j+DEPTH) as the groups the main loop expects
+    cp_async_wait<0>();
+#pragma unroll
+    for (int j = 0; j < PICP_DEPTH; ++j) {
+      issue_gathers(j, j % PICP_SLOTS);
+      issue_pairs(j + PICP_DEPTH, (j + PICP_DEPTH) % PICP_SLOTS);
+      cp_async_commit();
+    }
+  };
+  fill_pairs();
+  fill_gathers();
+
   for (int round = 0; round < rounds; ++round) {
 
   PicpConsts c;
@@ -551,51 +604,7 @@ picp_stream_kernel(const PicpParams p, const int rounds) {
   a.chi_in = a.chi_out = 0ull;
   a.n_in = 0;
 
-  // ---- asynchronous stream over the correspondences ------------------------------------------
-  // thread t owns items t, t+stride, t+2*stride, ...; they are consumed in batches of PICP_UNROLL.
-  const int n = (int)p.n_pairs;
-  const int stride = (int)gridDim.x * PICP_THREADS;
-  const int i0 = (int)blockIdx.x * PICP_THREADS + tid;
-  const int mine = i0 < n ? (n - i0 + stride - 1) / stride : 0;  // items of this thread
-  const int nb = mine / PICP_UNROLL;                             // full batches
-  const int2* pp = p.pairs + i0;
   {
-    extern __shared__ __align__(16) unsigned char picp_ring[];
-    const uint32_t ring = smem_u32(picp_ring) + (uint32_t)tid * 8u;
-    auto issue_pairs = [&](int b, int slot) {  // P(b)
-      if (b < nb) {
-#pragma unroll
-        for (int u = 0; u < PICP_UNROLL; ++u)
-          cp_async8(ring + picp_prs_off(slot, u), pp + (int64_t)(b * PICP_UNROLL + u) * stride);
-      }
-    };
-    auto issue_gathers = [&](int b, int slot) {  // G(b); P(b) has landed
-      if (b < nb) {
-#pragma unroll
-        for (int u = 0; u < PICP_UNROLL; ++u) {
-          const int2 pr = lds_int2(ring + picp_prs_off(slot, u));
-          const float* wp = p.world + 3 * (int64_t)pr.y;  // .second -> world (:67)
-          const float* ip = p.image + 2 * (int64_t)pr.x;  // .first -> image (:66)
-          const uint32_t lane = (uint32_t)(u & 1) * 4u;   // which half of the packed pair
-          cp_async4(ring + picp_pts_off(slot, u >> 1, 0) + lane, wp);
-          cp_async4(ring + picp_pts_off(slot, u >> 1, 1) + lane, wp + 1);
-          cp_async4(ring + picp_pts_off(slot, u >> 1, 2) + lane, wp + 2);
-          cp_async4(ring + picp_pts_off(slot, u >> 1, 3) + lane, ip);
-          cp_async4(ring + picp_pts_off(slot, u >> 1, 4) + lane, ip + 1);
-        }
-      }
-    };
-    // prologue: P(0..DEPTH-1); then G(j) + P(j+DEPTH) as the groups the main loop expects
-#pragma unroll
-    for (int j = 0; j < PICP_DEPTH; ++j) issue_pairs(j, j % PICP_SLOTS);
-    cp_async_commit();
-    cp_async_wait<0>();
-#pragma unroll
-    for (int j = 0; j < PICP_DEPTH; ++j) {
-      issue_gathers(j, j % PICP_SLOTS);
-      issue_pairs(j + PICP_DEPTH, (j + PICP_DEPTH) % PICP_SLOTS);
-      cp_async_commit();
-    }
     for (int b0 = 0; b0 < nb; b0 += PICP_SLOTS) {
 #pragma unroll
       for (int sl = 0; sl < PICP_SLOTS; ++sl) {
@@ -616,6 +625,9 @@ picp_stream_kernel(const PicpParams p, const int rounds) {
       }
     }
     cp_async_wait<0>();
+    // next round's pair loads go out now; its gathers follow after the warp reduction below
+    const bool more = round + 1 < rounds;
+    if (more) fill_pairs();
     // the (< PICP_UNROLL) leftover items of this thread, again two at a time
     for (int m = nb * PICP_UNROLL; m < mine; m += 2) {
       const bool have1 = m + 1 < mine;
@@ -652,6 +664,7 @@ picp_stream_kernel(const PicpParams p, const int rounds) {
     for (int i = 0; i < 29; ++i) s_red[warp][i] = v[i];
     s_red[warp][29] = __int_as_float(n_in);
   }
+  if (round + 1 < rounds) fill_gathers();  // in flight across the grid barrier and the solve
   __syncthreads();
   if (warp == 0 && lane < 30) {
     float* out = p.partials + ((int64_t)(round & 1) * gridDim.x + blockIdx.x) * PICP_NACC;
