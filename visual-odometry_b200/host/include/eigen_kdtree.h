@@ -14,8 +14,6 @@
 #include <vector>
 
 #include "brute_force_search.h"
-#include "eigen_covariance.h"
-#include "split.h"
 
 template <typename IteratorType_>
 class TreeNode_ {
@@ -24,7 +22,6 @@ class TreeNode_ {
   using PointType = typename IteratorType_::value_type;
   using Scalar = typename PointType::Scalar;
   static constexpr int Dim = PointType::RowsAtCompileTime;
-  using CovarianceType = Eigen::Matrix<Scalar, Dim - 1, Dim - 1>;
   using ThisType = TreeNode_<IteratorType>;
   using PtrType = std::unique_ptr<ThisType>;
   using AnswerType = std::vector<PointType*>;

@@ -3,31 +3,26 @@
 
 #include "vo_b200_host.h"
 
-Camera::Camera(int rows, int cols, int z_near, int z_far, const Eigen::Matrix3f& camera_matrix,
-               const Eigen::Isometry3f& world_in_camera_pose)
-    : _rows(rows),
-      _cols(cols),
-      _z_near(z_near),
-      _z_far(z_far),
-      _camera_matrix(camera_matrix),
-      _world_in_camera_pose(world_in_camera_pose) {}
+Camera::Camera(int height, int width, int near_plane, int far_plane, const Eigen::Matrix3f& K,
+               const Eigen::Isometry3f& pose)
+    : _pose(pose), _K(K), _height(height), _width(width), _near(near_plane), _far(far_plane) {}
 
-int Camera::projectPoints(Vector2fVector& image_points, const Vector3fVector& world_points,
-                          bool keep_indices) {
-  vo_camera cam;
-  cam.rows = _rows;
-  cam.cols = _cols;
-  cam.z_near = _z_near;
-  cam.z_far = _z_far;
-  vo_b200::pack3(_camera_matrix, cam.K);
-  vo_b200::pack_iso(_world_in_camera_pose, cam.T);
-  image_points.resize(world_points.size());
-  int64_t n_out = 0, n_inside = 0;
-  if (!world_points.empty())
-    vo_b200::check(vo_project_points(vo_b200::device(), &cam, world_points[0].data(),
-                                     (int64_t)world_points.size(), keep_indices ? 1 : 0,
-                                     image_points[0].data(), &n_out, &n_inside),
-                   "vo_project_points");
-  image_points.resize((size_t)n_out);
-  return (int)n_inside;
+// Camera::projectPoints of the reference (src/camera.cpp:16-37), executed by project_points_kernel
+int Camera::projectPoints(Vector2fVector& pixels, const Vector3fVector& world_points, bool keep_indices) {
+  const int64_t n = (int64_t)world_points.size();
+  pixels.resize(world_points.size());
+  if (n == 0) return 0;
+  vo_camera description;
+  description.rows = _height;
+  description.cols = _width;
+  description.z_near = _near;
+  description.z_far = _far;
+  vo_b200::pack3(_K, description.K);
+  vo_b200::pack_iso(_pose, description.T);
+  int64_t written = 0, accepted = 0;
+  vo_b200::check(vo_project_points(vo_b200::device(), &description, world_points[0].data(), n,
+                                   keep_indices ? 1 : 0, pixels[0].data(), &written, &accepted),
+                 "vo_project_points");
+  pixels.resize((size_t)written);
+  return (int)accepted;
 }
