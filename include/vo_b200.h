@@ -230,9 +230,10 @@ int vo_pipe_create(vo_pipe_t* out, int device, const vo_camera* cam, int64_t max
 int vo_pipe_destroy(vo_pipe_t h);
 int vo_pipe_first_frame(vo_pipe_t h, const float* points_host, const float* app_host, int64_t n);
 /* uploads the second frame and returns the (first, second) index pairs of the appearance
- * matches (corr_host: int32 pairs, capacity >= min(n0, n1); nullable)                          */
+ * matches: *n_corr = how many there are (at most min(n0, n1)); the first min(*n_corr,
+ * corr_capacity) pairs are written to corr_host (int32 pairs; nullable with capacity 0)        */
 int vo_pipe_second_frame(vo_pipe_t h, const float* points_host, const float* app_host, int64_t n,
-                         int32_t* corr_host, int64_t* n_corr);
+                         int32_t* corr_host, int64_t corr_capacity, int64_t* n_corr);
 /* X: pose of the first camera in the second (what estimate_transform returns); triangulates the
  * first pair, starts the map                                                                   */
 int vo_pipe_bootstrap(vo_pipe_t h, const float X[16]);

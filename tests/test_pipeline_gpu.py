@@ -128,7 +128,7 @@ def test_degenerate_frames_do_not_break_the_loop(vo):
     p1, a1 = frame(40)  # unrelated appearances: no match
     corr = np.zeros((64, 2), np.int32)
     n = C.c_int64(-1)
-    assert lib.vo_pipe_second_frame(h, _p(p1), _p(a1), 40, _p(corr), C.byref(n)) == 0
+    assert lib.vo_pipe_second_frame(h, _p(p1), _p(a1), 40, _p(corr), 64, C.byref(n)) == 0
     assert n.value == 0
     X = np.eye(4, dtype=np.float32).reshape(-1)
     assert lib.vo_pipe_bootstrap(h, X.ctypes.data_as(C.POINTER(C.c_float))) == 0
@@ -147,3 +147,36 @@ def test_degenerate_frames_do_not_break_the_loop(vo):
     assert lib.vo_pipe_get_map(h, None, None, 0, C.byref(n_map)) == 0
     assert n_map.value >= 0
     lib.vo_pipe_destroy(h)
+
+
+def test_python_frame_pipeline_on_a_synthetic_pair_sequence(vo, synth):
+    """vo.FramePipeline (the ctypes mirror of vo_pipe_*): a static scene seen from a camera that
+    moves along its optical axis; matches are the identity, the pose is recovered up to the
+    monocular scale, and the map holds every landmark once."""
+    rng = np.random.RandomState(21)
+    K = np.array([[180, 0, 320], [0, 180, 240], [0, 0, 1]], np.float64)
+    n = 600
+    world = np.stack([rng.uniform(-2, 2, n), rng.uniform(-1.5, 1.5, n), rng.uniform(2.0, 4.5, n)], 1)
+    app = rng.uniform(-1, 1, (n, 10)).astype(np.float32)
+
+    def view(tz):  # camera at (0,0,tz): world-in-camera translation (0,0,-tz)
+        pc = world - np.array([0, 0, tz])
+        uv = (pc @ K.T)[:, :2] / pc[:, 2:3]
+        return uv.astype(np.float32)
+
+    cam = vo.Camera(480, 640, 0, 50, K, np.eye(4))
+    pipe = vo.FramePipeline(cam, max_points_per_frame=1024, max_map_points=2000)
+    pipe.first_frame(view(0.0), app)
+    matches = pipe.second_frame(view(0.1), app)
+    assert np.array_equal(matches, np.stack([np.arange(n), np.arange(n)], 1))
+    X = np.eye(4)
+    X[2, 3] = -0.1  # ground truth relative pose of the first pair
+    pipe.bootstrap(X)
+    for k in range(2, 6):
+        pose, info = pipe.step(view(0.1 * k), app, rounds=30)
+        assert info["n_matches"] == n and info["n_correspondences"] == n
+        assert np.allclose(pose[:3, :3], np.eye(3), atol=2e-4)
+        assert np.allclose(pose[:3, 3], [0, 0, -0.1], atol=2e-3)
+    pts, apps = pipe.map()
+    assert len(pts) == n and np.array_equal(apps, app)
+    pipe.close()

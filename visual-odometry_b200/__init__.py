@@ -14,6 +14,7 @@ missing or no device is visible.
 from ._abi import VoError, lib, lib_path, launch_count, device_count, measure_ffma_peak  # noqa: F401
 from .api import (  # noqa: F401
     Camera,
+    FramePipeline,
     NNIndex,
     PICPSolver,
     bruteForceBestMatch,

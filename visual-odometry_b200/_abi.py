@@ -104,7 +104,7 @@ PROTOTYPES = {
     "vo_pipe_destroy": (C.c_int, [C.c_void_p]),
     "vo_pipe_first_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "vo_pipe_second_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
-                                       c_i64p]),
+                                       C.c_int64, c_i64p]),
     "vo_pipe_bootstrap": (C.c_int, [C.c_void_p, c_f32p]),
     "vo_pipe_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float,
                                C.c_void_p]),

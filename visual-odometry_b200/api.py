@@ -6,6 +6,7 @@ Names and argument meaning follow the reference (file:line relative to its check
   bruteForceBestMatch     include/brute_force_search.h:22-41
   bruteForceSearch        include/brute_force_search.h:3-20
   triangulate_points      src/utils.cpp:51-134
+  FramePipeline           the loop body of src/apps/vo_complete.cpp:150-178 (device-resident)
 Everything computes on the GPU through libvo_b200.so; nothing here does arithmetic on the host.
 """
 import ctypes as C
@@ -324,3 +325,92 @@ def triangulate_points(k, X, correspondences, p1_img, p2_img, appearances2=None,
     if want_src:
         out.append(src[:m])
     return tuple(out)
+
+
+class vo_pipe_result(C.Structure):
+    """include/vo_b200.h: vo_pipe_result"""
+    _fields_ = [("T", C.c_float * 16), ("n_measurements", C.c_int64), ("n_matches", C.c_int64),
+                ("n_correspondences", C.c_int64), ("map_points", C.c_int64),
+                ("chi_inliers", C.c_float), ("n_inliers", C.c_int32), ("map_overflow", C.c_int32)]
+
+
+class FramePipeline:
+    """The loop body of the reference's main (src/apps/vo_complete.cpp:150-178) with the frames, the
+    match lists, the triangulated cloud and the map resident on the device (vo_pipe_*).
+
+        pipe = FramePipeline(camera)
+        pipe.first_frame(points0, appearances0)
+        matches = pipe.second_frame(points1, appearances1)   # (n,2) int32: for the epipolar init
+        pipe.bootstrap(X)                                    # X from estimate_transform (host)
+        pose, info = pipe.step(points, appearances)          # every further frame
+        map_points, map_appearances = pipe.map()
+    """
+
+    def __init__(self, camera, device=0, max_points_per_frame=32768, max_map_points=1 << 20):
+        self._h = C.c_void_p()
+        cam = camera.to_struct()
+        check(lib().vo_pipe_create(C.byref(self._h), device, C.byref(cam), max_points_per_frame,
+                                   max_map_points), "vo_pipe_create")
+        self._max_map = max_map_points
+
+    def close(self):
+        if self._h:
+            lib().vo_pipe_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _frame(points, appearances):
+        p, a = _f32(points, 2), _f32(appearances, 10)
+        if p.shape[0] != a.shape[0]:
+            raise ValueError("points and appearances must have the same length")
+        return p, a
+
+    def first_frame(self, points, appearances):
+        p, a = self._frame(points, appearances)
+        check(lib().vo_pipe_first_frame(self._h, _ptr(p), _ptr(a), p.shape[0]), "vo_pipe_first_frame")
+        self._n0 = p.shape[0]
+
+    def second_frame(self, points, appearances):
+        p, a = self._frame(points, appearances)
+        cap = max(1, min(self._n0, p.shape[0]))
+        corr = np.empty((cap, 2), dtype=np.int32)
+        n = C.c_int64(0)
+        check(lib().vo_pipe_second_frame(self._h, _ptr(p), _ptr(a), p.shape[0], _ptr(corr), cap,
+                                         C.byref(n)), "vo_pipe_second_frame")
+        return corr[: n.value].copy()
+
+    def bootstrap(self, X):
+        Xc = np.array(X, dtype=np.float32).reshape(4, 4).T.copy().reshape(-1)
+        check(lib().vo_pipe_bootstrap(self._h, Xc.ctypes.data_as(_abi.c_f32p)), "vo_pipe_bootstrap")
+
+    def step(self, points, appearances, rounds=100, kernel_threshold=10000.0):
+        p, a = self._frame(points, appearances)
+        res = vo_pipe_result()
+        check(lib().vo_pipe_step(self._h, _ptr(p), _ptr(a), p.shape[0], rounds,
+                                 C.c_float(kernel_threshold), C.byref(res)), "vo_pipe_step")
+        pose = np.array(res.T[:], dtype=np.float32).reshape(4, 4).T.copy()
+        info = {k: getattr(res, k) for k in ("n_measurements", "n_matches", "n_correspondences",
+                                             "map_points", "chi_inliers", "n_inliers", "map_overflow")}
+        return pose, info
+
+    def merge_cloud(self, points, appearances, X=np.eye(4)):
+        """PointCloudVector::update (PointCloud.h:52-66) of a host cloud moved by X"""
+        p, a = _f32(points, 3), _f32(appearances, 10)
+        Xc = np.array(X, dtype=np.float32).reshape(4, 4).T.copy().reshape(-1)
+        check(lib().vo_pipe_merge_cloud(self._h, _ptr(p), _ptr(a), p.shape[0],
+                                        Xc.ctypes.data_as(_abi.c_f32p)), "vo_pipe_merge_cloud")
+
+    def map(self):
+        n = C.c_int64(0)
+        check(lib().vo_pipe_get_map(self._h, None, None, 0, C.byref(n)), "vo_pipe_get_map")
+        pts = np.empty((max(n.value, 1), 3), dtype=np.float32)
+        app = np.empty((max(n.value, 1), 10), dtype=np.float32)
+        check(lib().vo_pipe_get_map(self._h, _ptr(pts), _ptr(app), pts.shape[0], C.byref(n)),
+              "vo_pipe_get_map")
+        return pts[: n.value], app[: n.value]

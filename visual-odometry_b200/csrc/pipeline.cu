@@ -511,8 +511,10 @@ int vo_pipe_first_frame(vo_pipe_t h, const float* points_host, const float* app_
 }
 
 int vo_pipe_second_frame(vo_pipe_t h, const float* points_host, const float* app_host, int64_t n,
-                         int32_t* corr_host, int64_t* n_corr) {
+                         int32_t* corr_host, int64_t corr_capacity, int64_t* n_corr) {
   VO_REQUIRE(h != nullptr && n_corr != nullptr, VO_ERR_ARG, "null pointer");
+  VO_REQUIRE(corr_capacity >= 0 && (corr_host != nullptr || corr_capacity == 0), VO_ERR_ARG,
+             "bad match buffer");
   VO_REQUIRE(h->have_ref && !h->bootstrapped, VO_ERR_STATE, "call vo_pipe_first_frame first");
   DeviceGuard g(h->device);
   int rc = pipe_upload_frame(h, 1 - h->ref, points_host, app_host, n);
@@ -522,8 +524,9 @@ int vo_pipe_second_frame(vo_pipe_t h, const float* points_host, const float* app
   long long cnt = 0;
   VO_CUDA(cudaMemcpyAsync(&cnt, h->counts.as<long long>() + C_CI, 8, cudaMemcpyDeviceToHost, h->stream));
   VO_CUDA(cudaStreamSynchronize(h->stream));
-  if (corr_host && cnt > 0) {
-    VO_CUDA(cudaMemcpyAsync(corr_host, h->corr_imgs.p, (size_t)cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+  const long long take = cnt < corr_capacity ? cnt : corr_capacity;
+  if (take > 0) {
+    VO_CUDA(cudaMemcpyAsync(corr_host, h->corr_imgs.p, (size_t)take * 8, cudaMemcpyDeviceToHost, h->stream));
     VO_CUDA(cudaStreamSynchronize(h->stream));
   }
   *n_corr = cnt;

@@ -227,7 +227,7 @@ int run_pipeline(int n_landmarks, int n_frames, unsigned seed, int rounds, const
   IntPairVector corr(std::min(reference.pc.size(), current.pc.size()) + 1);
   int64_t n_corr = 0;
   vo_b200::check(vo_pipe_second_frame(pipe, pts(current), app(current), (int64_t)current.pc.size(),
-                                      &corr[0].first, &n_corr),
+                                      &corr[0].first, (int64_t)corr.size(), &n_corr),
                  "vo_pipe_second_frame");
   corr.resize((size_t)n_corr);
   const Eigen::Isometry3f X0 = estimate_transform(k, corr, reference.pc.points(), current.pc.points());
