@@ -459,15 +459,16 @@ picp_resident_kernel(const PicpParams p, const int rounds) {
       // warp w sums rows w, w+W, ... (all loads in flight at once), warp 0 then sums the W results
       const float* part = p.partials + (int64_t)(round & 1) * csize * PICP_NACC;
       float acc = 0.f;
-      for (int r0 = warp; r0 < csize; r0 += W * 4) {
-        float x[4];
+      constexpr int INFLIGHT = 10;  // 148 rows / 16 warps: every row of a warp in one round-trip
+      for (int r0 = warp; r0 < csize; r0 += W * INFLIGHT) {
+        float x[INFLIGHT];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < INFLIGHT; ++q) {
           const int r = r0 + q * W;
           x[q] = r < csize ? __ldcg(part + (int64_t)r * PICP_NACC + lane) : 0.f;
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc += x[q];
+        for (int q = 0; q < INFLIGHT; ++q) acc += x[q];
       }
       __syncthreads();  // s_red is about to be reused
       s_red[warp][lane] = acc;
