@@ -91,6 +91,11 @@ int vo_nn_best_match_device(vo_nn_t h, const float* queries_dev, int64_t n_queri
                             int query_stride, float norm, int32_t* best_idx_dev,
                             float* best_d2_dev);
 
+/* Introspection for tests and profiles: the filter-kernel launches the LAST best_match call on this
+ * handle issued, four int32 per launch = (queries per thread, threads per block, query tiles, map
+ * splits).  *n_launches = how many there were; at most `capacity` of them are written to out.    */
+int vo_nn_last_launches(vo_nn_t h, int32_t* out, int capacity, int* n_launches);
+
 /* bruteForceSearch for a batch of queries: counts[q] = number of rows with d2 < norm^2.
  * If idx_out != NULL, the matching row indices of query q are written in ascending row
  * order to idx_out[q*max_per_query ...], at most max_per_query of them.                    */

@@ -52,30 +52,55 @@ def test_planted_random_vs_oracle(vo, oracle, synth, M, Q):
     assert np.array_equal(idx[exact], target[exact])
 
 
-@pytest.mark.parametrize("Q", [9216 + 1, 9216 + 212, 9216 + 600, 9216 + 1500, 9216 + 2000,
-                               9216 + 3000, 12500])
-def test_remainder_launch_variants_vs_oracle(vo, oracle, synth, Q):
-    """Batches above 8192 queries run whole 3072-query tiles plus ONE remainder launch whose
-    register tile depends on the remainder size; every variant must give the oracle's answers."""
+# remainder size -> the (queries per thread, threads) instantiation nn_launch_filter picks for it
+WIDE_REMAINDERS = [(1, (2, 256)), (300, (2, 256)), (600, (2, 384)), (1200, (4, 384)), (2000, (6, 384)),
+                   (2800, (8, 384)), (3600, (10, 384)), (4400, (12, 384))]
+WIDE_M = 38_000  # 297 tiles of 128 rows >= 2 x 148 SMs: large enough for the wide register tile
+
+
+@pytest.mark.parametrize("rem,variant", WIDE_REMAINDERS)
+def test_wide_kernel_and_every_remainder_variant_vs_oracle(vo, oracle, synth, rem, variant):
+    """The headline path: batches above 8192 queries against a map of >= 2 tiles per SM run whole
+    4608-query tiles through nn_filter_kernel<12,384> plus ONE remainder launch whose register tile
+    depends on the remainder size.  The launch log proves which instantiations answered; indices
+    and d2 must equal the oracle's (brute_force_search.h:22-41)."""
+    Q = 2 * 4608 + rem
+    m = synth.nn_map_rows_np(0, WIDE_M)
+    q, target = synth.nn_queries_np(Q, WIDE_M)
+    nn = vo.NNIndex(0)
+    nn.set_map(m)
+    idx, d2 = nn.best_match(q, 0.1, want_d2=True)
+    launches = nn.last_launches()
+    nn.close()
+    assert [l[:2] for l in launches] == [(12, 384), variant], launches
+    assert launches[0][2] == 2  # two full query tiles
+    oi, od = oracle.nn_best_match(m, q, 0.1)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(d2[oi >= 0], od[oi >= 0])
+    exact = (np.arange(Q) % 4) < 2
+    assert np.array_equal(idx[exact], target[exact])
+
+
+@pytest.mark.parametrize("Q,variant", [(3000, (2, 256)), (5000, (4, 256)), (700, (2, 64)),
+                                       (9216 + 212, (4, 256))])
+def test_small_map_routing_vs_oracle(vo, oracle, synth, Q, variant):
+    """Maps of fewer than 2 tiles per SM (frame-to-frame association) take the narrow register
+    tiles whatever the query count."""
     M = 4099
     m = synth.nn_map_rows_np(0, M)
     q, _ = synth.nn_queries_np(Q, M)
     nn = vo.NNIndex(0)
     nn.set_map(m)
     idx, d2 = nn.best_match(q, 0.1, want_d2=True)
+    launches = nn.last_launches()
     nn.close()
+    assert [l[:2] for l in launches] == [variant], launches
     oi, od = oracle.nn_best_match(m, q, 0.1)
     assert np.array_equal(idx, oi)
     assert np.array_equal(d2[oi >= 0], od[oi >= 0])
 
 
-@pytest.mark.parametrize("kind", ["constant_prefix", "clustered"])
-def test_partial_filter_worst_cases_stay_exact(vo, oracle, kind):
-    """The streaming filter only looks at the first 5 of the 10 dimensions (a lower bound of the
-    distance); data on which that bound prunes nothing — every row equal to the query in those
-    dimensions, or all rows in one tight cluster — must only cost re-scans, never exactness."""
-    rng = np.random.RandomState(11)
-    M, Q = 6000, 900
+def _worst_case(kind, rng, M, Q):
     m = rng.uniform(-1, 1, (M, 11)).astype(np.float32)
     q = rng.uniform(-1, 1, (Q, 11)).astype(np.float32)
     if kind == "constant_prefix":
@@ -86,6 +111,37 @@ def test_partial_filter_worst_cases_stay_exact(vo, oracle, kind):
         centre = rng.uniform(-1, 1, 11).astype(np.float32)
         m = (centre + rng.uniform(-0.03, 0.03, (M, 11))).astype(np.float32)
         q = (centre + rng.uniform(-0.03, 0.03, (Q, 11))).astype(np.float32)
+    return m, q
+
+
+@pytest.mark.parametrize("kind", ["constant_prefix", "clustered"])
+def test_wide_kernel_worst_case_data_stays_exact(vo, oracle, kind):
+    """No-pruning data (every row passes the partial-distance filter, every tile is re-scanned for
+    every query) through the WIDE kernel and a remainder variant: only the number of re-scans may
+    change, never the answers."""
+    rng = np.random.RandomState(13)
+    M, Q = WIDE_M, 2 * 4608 + 600
+    m, q = _worst_case(kind, rng, M, Q)
+    nn = vo.NNIndex(0)
+    nn.set_map(m)
+    idx, d2 = nn.best_match(q, 0.1, want_d2=True)
+    launches = nn.last_launches()
+    nn.close()
+    assert [l[:2] for l in launches] == [(12, 384), (2, 384)], launches
+    oi, od = oracle.nn_best_match(m, q, 0.1)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(d2[oi >= 0], od[oi >= 0])
+    assert (oi >= 0).sum() > Q // 3
+
+
+@pytest.mark.parametrize("kind", ["constant_prefix", "clustered"])
+def test_partial_filter_worst_cases_stay_exact(vo, oracle, kind):
+    """The streaming filter only looks at the first 5 of the 10 dimensions (a lower bound of the
+    distance); data on which that bound prunes nothing — every row equal to the query in those
+    dimensions, or all rows in one tight cluster — must only cost re-scans, never exactness."""
+    rng = np.random.RandomState(11)
+    M, Q = 6000, 900
+    m, q = _worst_case(kind, rng, M, Q)
     nn = vo.NNIndex(0)
     nn.set_map(m)
     idx, d2 = nn.best_match(q, 0.1, want_d2=True)

@@ -1,18 +1,49 @@
-"""GPU parity: vo_picp_* vs the oracle's PICPSolver.  FP32; tolerance 1e-5 relative (to the
-largest entry of each quantity) against the float64 truth, and the float oracle's own error
-against that truth is asserted to be of the same order (SURVEY.md §7 hard part 6)."""
+"""GPU parity: vo_picp_* vs the oracle's PICPSolver (picp_solver.cpp:25-112).  FP32.
+
+Tolerances (north_star: "PICP poses, H/b ... within 1e-5 relative in FP32"):
+  * H and b of a linearisation: every 3x3 block of H and each half of b, relative to the largest
+    entry OF THAT BLOCK, <= 1e-5 against the float64 truth of the same linearisation point
+    (rel_blocks) — an error confined to the small cross terms cannot hide behind the large ones;
+  * the FINAL pose (after 10 and after 100 rounds): rotation block and translation, each relative to
+    its own largest entry, <= 1e-5 against the float64 solver's final pose;
+  * mid-trajectory poses are only required to stay within MID_TOL = 2e-4: before convergence the
+    three solvers (GPU, sequential-float oracle, float64) linearise at slightly different poses and
+    Gauss-Newton amplifies that difference by the step length; it contracts again at convergence,
+    which is what the final-pose assertion checks;
+  * chi statistics: CHI_TOL = 1e-4 (sums of squared FP32 pixel residuals: each residual carries the
+    ~3e-5 px rounding of a ~300 px coordinate).
+The float oracle's own error against the float64 truth is asserted to be of the same order
+(hard part 6)."""
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
 
-TOL = 1e-5      # H, b, pose (north_star: 1e-5 relative in FP32)
-CHI_TOL = 1e-4  # chi statistics (sums of squared FP32 residuals, see below)
+TOL = 1e-5      # H, b, final pose
+MID_TOL = 2e-4  # poses before convergence (see above)
+CHI_TOL = 1e-4  # chi statistics
 
 
 def rel(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def rel_blocks(H, H64, b=None, b64=None):
+    """largest per-block relative error: the four 3x3 blocks of H (translation/translation,
+    translation/rotation, rotation/translation, rotation/rotation) and the two halves of b."""
+    H, H64 = np.asarray(H, np.float64), np.asarray(H64, np.float64)
+    errs = [rel(H[i:i + 3, j:j + 3], H64[i:i + 3, j:j + 3]) for i in (0, 3) for j in (0, 3)]
+    if b is not None:
+        b, b64 = np.asarray(b, np.float64), np.asarray(b64, np.float64)
+        errs += [rel(b[:3], b64[:3]), rel(b[3:], b64[3:])]
+    return max(errs)
+
+
+def rel_pose(T, T64):
+    """rotation block and translation, each relative to its own largest entry"""
+    T, T64 = np.asarray(T, np.float64), np.asarray(T64, np.float64)
+    return max(rel(T[:3, :3], T64[:3, :3]), rel(T[:3, 3], T64[:3, 3]))
 
 
 def _mk(vo, oracle, pr, thr):
@@ -38,21 +69,101 @@ def test_rounds_match_oracle(vo, oracle, synth, n, dist, shuffle):
             st = s.state()
             assert st.num_inliers == o.st.num_inliers == int(o.stats64[2])
             H = np.array(st.H[:]).reshape(6, 6).T
-            assert rel(H, o.H64m()) <= TOL, "H vs float64 truth"
-            if r == 0:  # at convergence b is pure rounding noise around 0: only round 0 is meaningful
-                assert rel(st.b[:], o.b64) <= TOL
-                # chi is a sum of squared FP32 pixel residuals: each residual carries the ~3e-5 px
-                # rounding of a ~300 px coordinate, so chi agrees to ~1e-5..1e-4, not better, and
-                # at convergence (residual ~ rounding) it is not comparable at all
+            if r == 0:
+                # all three linearise at the SAME pose (identity): the strict per-block bound
+                assert rel_blocks(H, o.H64m(), st.b[:], o.b64) <= TOL, "H/b blocks vs float64 truth"
                 assert rel(st.chi_inliers, o.stats64[0]) <= CHI_TOL
                 assert rel(st.chi_inliers, o.st.chi_inliers) <= CHI_TOL
+            else:
+                # round 9 linearises at each solver's own (converged) pose; b is rounding noise
+                # around 0 there and is not comparable
+                assert rel_blocks(H, o.H64m()) <= TOL, "H blocks vs float64 truth"
             assert rel(H, o.H()) <= 10 * TOL + rel(o.H(), o.H64m())
-        # keep the three solvers on the same trajectory: tiny differences are fine
-        assert rel(s.pose(), o.pose64()) <= 20 * TOL
-    assert rel(s.pose(), o.pose()) <= 20 * TOL
+        assert rel_pose(s.pose(), o.pose64()) <= MID_TOL
+    assert rel_pose(s.pose(), o.pose64()) <= TOL, "final pose vs float64 solver"
+    assert rel_pose(s.pose(), o.pose()) <= TOL + rel_pose(o.pose(), o.pose64())
     assert np.allclose(s.pose(), pr["T_gt"], atol=5e-4)
     assert s.state().rounds_done == 10
     s.close()
+
+
+@pytest.mark.parametrize("n,rounds", [(1000, 10), (1000, 100), (10000, 10), (10000, 100),
+                                      (200000, 10), (200000, 100), (2000000, 10)])
+def test_final_pose_within_1e5_of_f64(vo, oracle, synth, n, rounds):
+    """north_star's pose bound at every size class (cluster-resident, grid-resident, streaming):
+    all rounds in ONE vo_picp_compute call, final pose <= 1e-5 (per block) from the float64
+    solver's, and the last linearisation's H within 1e-5 per block."""
+    pr = synth.picp_problem(n, seed=31)
+    s, o = _mk(vo, oracle, pr, 10000.0)
+    s.set_correspondences(pr["pairs"])
+    s.compute(False, rounds)
+    for _ in range(rounds):
+        o.one_round_f64(pr["pairs"], False)
+    st = s.state()
+    assert st.rounds_done == rounds
+    err = rel_pose(s.pose(), o.pose64())
+    print(f"n={n} rounds={rounds}: final pose err vs f64 = {err:.2e}")
+    assert err <= TOL
+    assert rel_blocks(np.array(st.H[:]).reshape(6, 6).T, o.H64m()) <= TOL
+    assert st.num_inliers == int(o.stats64[2])
+    s.close()
+
+
+def test_streaming_kernel_final_pose(vo, oracle, synth, monkeypatch):
+    """the same bound with the streaming kernel forced on a mid-sized problem"""
+    monkeypatch.setenv("VO_PICP_FORCE_STREAM", "1")
+    pr = synth.picp_problem(200000, seed=32)
+    s, o = _mk(vo, oracle, pr, 10000.0)
+    s.set_correspondences(pr["pairs"])
+    s.compute(False, 1)
+    o.one_round_f64(pr["pairs"], False)
+    st = s.state()
+    assert rel_blocks(np.array(st.H[:]).reshape(6, 6).T, o.H64m(), st.b[:], o.b64) <= TOL
+    s.compute(False, 9)
+    for _ in range(9):
+        o.one_round_f64(pr["pairs"], False)
+    assert rel_pose(s.pose(), o.pose64()) <= TOL
+    s.close()
+
+
+def test_degenerate_points_do_not_poison_the_sums(vo, oracle, synth):
+    """rejected points must be skipped, not multiplied by a zero weight.
+      * a world point ON the camera plane (camera z == 0, legal with z_near == 0): the reference gets
+        1/0 = Inf, u = +-Inf and rejects it (camera.h:31-35);
+      * an off-image point paired with a NaN / Inf measurement (0 * NaN);
+      * an off-image point whose tiny depth overflows the Jacobian.
+    H, b and the pose must stay finite and equal to the oracle's over the remaining points.
+    (Not covered on purpose: a point exactly AT the camera centre gives 0 * Inf = NaN in the
+    reference, whose negated bounds test then ACCEPTS it and poisons its own H; this build rejects
+    it — DESIGN.md, divergences.)"""
+    pr = synth.picp_problem(3000, seed=33)
+    world, image = pr["world"].copy(), pr["image"].copy()
+    pairs = pr["pairs"].copy()
+    n0 = len(world)
+    extra_w = np.array([[0.3, -0.2, 0.0],        # exactly on the camera plane of the identity pose
+                        [50.0, 0.1, 1.0],        # off-image, finite
+                        [1.0, 1.0, 1e-30],       # tiny depth: projection overflows
+                        [-2.0, 3.0, 1e-38]], np.float32)
+    extra_i = np.array([[10.0, 10.0], [np.nan, np.inf], [5.0, 5.0], [np.nan, 1.0]], np.float32)
+    world = np.concatenate([world, extra_w])
+    image = np.concatenate([image, extra_i])
+    add = np.stack([np.arange(n0, n0 + 4), np.arange(n0, n0 + 4)], 1).astype(np.int32)
+    pairs = np.concatenate([pairs[:1000], add, pairs[1000:]])
+    pr2 = dict(pr, world=world, image=image)
+    for keep in (False, True):
+        s, o = _mk(vo, oracle, pr2, 10000.0)
+        for r in range(5):
+            s.oneRound(pairs, keep)
+            o.one_round(pairs, keep)
+            o.one_round_f64(pairs, keep)
+            st = s.state()
+            H = np.array(st.H[:]).reshape(6, 6).T
+            assert np.all(np.isfinite(H)) and np.all(np.isfinite(st.b[:])) and np.all(np.isfinite(st.T[:]))
+            assert st.num_inliers == o.st.num_inliers == int(o.stats64[2])
+            if r == 0:
+                assert rel_blocks(H, o.H64m(), st.b[:], o.b64) <= TOL
+        assert rel_pose(s.pose(), o.pose64()) <= TOL
+        s.close()
 
 
 def test_compute_many_rounds_equals_one_round_loop(vo, synth):
@@ -140,7 +251,7 @@ def test_outliers_and_robust_kernel(vo, oracle, synth, keep):
         assert st.num_inliers == int(o.stats64[2])
         assert rel(st.chi_outliers, o.stats64[1]) <= CHI_TOL
         assert rel(st.chi_inliers, o.stats64[0]) <= CHI_TOL
-        assert rel(np.array(st.H[:]).reshape(6, 6).T, o.H64m()) <= TOL
+        assert rel_blocks(np.array(st.H[:]).reshape(6, 6).T, o.H64m()) <= TOL
     s.close()
 
 
@@ -174,7 +285,7 @@ def test_large_n_vs_f64_truth(vo, oracle, synth):
     o.one_round(pr["pairs"], False)
     o.one_round_f64(pr["pairs"], False)
     H = s.H()
-    assert rel(H, o.H64m()) <= TOL
+    assert rel_blocks(H, o.H64m(), s.b(), o.b64) <= TOL
     assert rel(np.diag(H), np.diag(o.H64m())) <= TOL
     assert s.numInliers() == int(o.stats64[2])
     print("oracle(float,sequential) vs f64:", rel(o.H(), o.H64m()), " gpu vs f64:", rel(H, o.H64m()))
@@ -224,8 +335,8 @@ def test_general_camera_matrix(vo, oracle, synth):
         s.oneRound(pairs, False)
         o.one_round_f64(pairs, False)
         if r == 0:
-            assert rel(s.H(), o.H64m()) <= TOL
-            assert rel(s.b(), o.b64) <= TOL
-        assert rel(s.pose(), o.pose64()) <= 20 * TOL
+            assert rel_blocks(s.H(), o.H64m(), s.b(), o.b64) <= TOL
+        assert rel_pose(s.pose(), o.pose64()) <= MID_TOL
+    assert rel_pose(s.pose(), o.pose64()) <= TOL
     assert np.allclose(s.pose(), pr["T_gt"], atol=5e-4)
     s.close()

@@ -146,6 +146,13 @@ class NNIndex:
                                             C.c_void_p(d2_ptr) if d2_ptr else None),
               "vo_nn_best_match_device")
 
+    def last_launches(self):
+        """[(queries per thread, threads, query tiles, map splits), ...] of the last best_match."""
+        n = C.c_int(0)
+        buf = np.zeros((16, 4), dtype=np.int32)
+        check(lib().vo_nn_last_launches(self._h, _ptr(buf), 16, C.byref(n)), "vo_nn_last_launches")
+        return [tuple(int(x) for x in row) for row in buf[: min(n.value, 16)]]
+
     def radius_search(self, queries, norm, max_per_query=0):
         q = _f32(queries)
         counts = np.empty(q.shape[0], dtype=np.int32)

@@ -33,6 +33,7 @@
 
 #include <algorithm>
 #include <map>
+#include <vector>
 
 #include "common.cuh"
 
@@ -551,6 +552,9 @@ struct vo_nn_s {
   DevBuf keys;
   DevBuf q_stage, idx_stage, d2_stage, cnt_stage, list_stage;
   std::map<int, int> occupancy;  // (TQ, THREADS) -> resident CTAs per SM of that filter variant
+  // filter launches of the last best_match call: (TQ, THREADS, query tiles, map splits) each, so a
+  // test can PROVE which instantiation answered it (vo_nn_last_launches)
+  std::vector<int32_t> last_launches;
 };
 
 static int nn_launch_filter(vo_nn_s* h, const float* queries_dev, int64_t nq, int qstride,
@@ -605,6 +609,7 @@ static int nn_launch_filter(vo_nn_s* h, const float* queries_dev, int64_t nq, in
     dim3 grid((unsigned)nsplit, (unsigned)qtiles);
     kernel<<<grid, threads, smem, h->stream>>>(r);
     VO_LAUNCH_CHECK();
+    h->last_launches.insert(h->last_launches.end(), {tq, threads, (int32_t)qtiles, (int32_t)nsplit});
     return VO_OK;
   };
   // a batch too small for the wide register tile
@@ -669,6 +674,7 @@ static int nn_set_map_common(vo_nn_s* h, const float* rows_dev, int64_t n_rows, 
 static int nn_best_match_common(vo_nn_s* h, const float* queries_dev, int64_t nq, int qstride,
                                 float norm, int32_t* idx_dev, float* d2_dev) {
   const float bound = norm * norm;  // brute_force_search.h:31
+  h->last_launches.clear();
   if (nq == 0) return VO_OK;
   int rc = h->keys.reserve((size_t)nq * sizeof(unsigned long long));
   if (rc) return rc;
@@ -840,6 +846,16 @@ int vo_nn_best_match(vo_nn_t h, const float* queries_host, int64_t n_queries, in
     VO_CUDA(cudaMemcpyAsync(best_d2_host, h->d2_stage.p, (size_t)n_queries * sizeof(float),
                             cudaMemcpyDeviceToHost, h->stream));
   VO_CUDA(cudaStreamSynchronize(h->stream));
+  return VO_OK;
+}
+
+int vo_nn_last_launches(vo_nn_t h, int32_t* out, int capacity, int* n_launches) {
+  VO_REQUIRE(h != nullptr && n_launches != nullptr, VO_ERR_ARG, "null pointer");
+  VO_REQUIRE(capacity >= 0 && (out != nullptr || capacity == 0), VO_ERR_ARG, "bad output buffer");
+  const int n = (int)(h->last_launches.size() / 4);
+  *n_launches = n;
+  for (int i = 0; i < n && i < capacity; ++i)
+    for (int k = 0; k < 4; ++k) out[4 * i + k] = h->last_launches[4 * i + k];
   return VO_OK;
 }
 

@@ -58,8 +58,9 @@ struct PicpParams {
 };
 
 // Two correspondences at a time: errorAndJacobian (:25-53) + the body of linearize's loop (:62-95).
-// Branch-free: a rejected point runs the same instructions with weight 0, so a warp never
-// diverges on the data.
+// Branch-free: a rejected point runs the same instructions on zeroed operands (selected, not
+// multiplied by a zero weight), so a warp never diverges on the data and nothing non-finite that
+// a rejected point produced can reach the sums.
 //
 // Packed arithmetic.  At 28 B per point the kernel is HBM-bound only if its instruction stream
 // stays well under the issue rate 6.5 TB/s implies; the scalar formulation (136 instructions per
@@ -121,10 +122,6 @@ __device__ __forceinline__ void picp_point2(const PicpParams& p, const PicpConst
   f2_unpack(pz, pz0, pz1);
   bool valid0 = !(pz0 > p.z_far || pz0 < p.z_near);  // camera.h:28
   bool valid1 = have1 && !(pz1 > p.z_far || pz1 < p.z_near);
-  // a rejected point continues as the harmless dummy (0,0,1) so that nothing overflows
-  px = f2_sel(valid0, valid1, px, 0ull);
-  py = f2_sel(valid0, valid1, py, 0ull);
-  pz = f2_sel(valid0, valid1, pz, f2_bc(1.f));
   // phom = K * camera_point  (camera.h:30, picp_solver.cpp:43)
   f2_t hx, hy, hz;
   if (PINHOLE) {
@@ -136,14 +133,26 @@ __device__ __forceinline__ void picp_point2(const PicpParams& p, const PicpConst
     hy = f2_fma(f2_bc(p.K[7]), pz, f2_fma(f2_bc(p.K[4]), py, f2_mul(f2_bc(p.K[1]), px)));
     hz = f2_fma(f2_bc(p.K[8]), pz, f2_fma(f2_bc(p.K[5]), py, f2_mul(f2_bc(p.K[2]), px)));
   }
-  const f2_t iz = picp_rcp2(hz);  // camera.h:31 / picp_solver.cpp:44
-  const f2_t u = f2_mul(hx, iz), v = f2_mul(hy, iz);
+  const f2_t iz_raw = picp_rcp2(hz);  // camera.h:31 / picp_solver.cpp:44
+  const f2_t u_raw = f2_mul(hx, iz_raw), v_raw = f2_mul(hy, iz_raw);
   float u0, u1, v0, v1;
-  f2_unpack(u, u0, u1);
-  f2_unpack(v, v0, v1);
-  valid0 = valid0 && !(u0 < 0.f || u0 > p.max_u) && !(v0 < 0.f || v0 > p.max_v);  // camera.h:32-35
-  valid1 = valid1 && !(u1 < 0.f || u1 > p.max_u) && !(v1 < 0.f || v1 > p.max_v);
-  const f2_t e0 = f2_fma(mu, neg1, u), e1 = f2_fma(mv, neg1, v);  // e = proj - meas (:35)
+  f2_unpack(u_raw, u0, u1);
+  f2_unpack(v_raw, v0, v1);
+  // camera.h:32-35, written so that a NaN projection is rejected as well: a point ON the camera
+  // plane (hz == 0, legal with z_near == 0) gives 1/0 = Inf in the reference, u = +-Inf, rejected;
+  // here the Newton step of picp_rcp2 turns that Inf into NaN, which the negated form would accept.
+  valid0 = valid0 && (u0 >= 0.f && u0 <= p.max_u) && (v0 >= 0.f && v0 <= p.max_v);
+  valid1 = valid1 && (u1 >= 0.f && u1 <= p.max_u) && (v1 >= 0.f && v1 <= p.max_v);
+  // A rejected point is masked by SELECTION, not by a zero weight: 0 * Inf = NaN would poison H and
+  // b for every later round, while the reference simply skips the point (picp_solver.cpp:72).  With
+  // pc = iz = u = v = e = 0 every Jacobian entry and every product below is an exact zero.
+  px = f2_sel(valid0, valid1, px, 0ull);
+  py = f2_sel(valid0, valid1, py, 0ull);
+  pz = f2_sel(valid0, valid1, pz, 0ull);
+  const f2_t iz = f2_sel(valid0, valid1, iz_raw, 0ull);
+  const f2_t u = f2_sel(valid0, valid1, u_raw, 0ull), v = f2_sel(valid0, valid1, v_raw, 0ull);
+  const f2_t e0 = f2_sel(valid0, valid1, f2_fma(mu, neg1, u_raw), 0ull);  // e = proj - meas (:35)
+  const f2_t e1 = f2_sel(valid0, valid1, f2_fma(mv, neg1, v_raw), 0ull);
   // A = Jp*K with Jp = [iz 0 -hx*iz^2; 0 iz -hy*iz^2]  ==  iz * (K_row{0,1} - {u,v} * K_row2)
   // J = [A | A*skew(-pc)],  skew(-pc) = [0 pz -py; -pz 0 px; py -px 0]   (:39-41, utils.h:96-102)
   const f2_t npx = f2_mul(px, neg1), npy = f2_mul(py, neg1), npz = f2_mul(pz, neg1);
