@@ -6,7 +6,7 @@ CSRC := $(PKG)/csrc
 LIB := $(PKG)/lib/libvo_b200.so
 NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
              -Xcompiler -fPIC,-Wall,-ffp-contract=off --expt-relaxed-constexpr
-SRCS := $(CSRC)/lib.cu $(CSRC)/nn.cu $(CSRC)/picp.cu $(CSRC)/triangulate.cu $(CSRC)/pipeline.cu
+SRCS := $(CSRC)/lib.cu $(CSRC)/stage.cu $(CSRC)/nn.cu $(CSRC)/nn_tc.cu $(CSRC)/picp.cu $(CSRC)/triangulate.cu $(CSRC)/pipeline.cu
 OBJS := $(SRCS:$(CSRC)/%.cu=build/%.o)
 HDRS := $(wildcard $(CSRC)/*.cuh) include/vo_b200.h
 

@@ -64,6 +64,12 @@ int vo_measure_ffma2_peak(int device, double* tflops_out);
  * the dim trailing floats, evaluated in the reference's FP32 order;
  * a row matches when d2 < norm*norm (strict); the best match is the strict minimum, the
  * lowest row index winning ties; -1 when no row matches.
+ *
+ * Two filters feed the exact re-rank (same answers, chosen per call): the FP32 FFMA2
+ * partial-distance filter (csrc/nn.cu; small maps, small batches, data whose norms do not fit
+ * f16) and the tcgen05 f16 tensor-core filter (csrc/nn_tc.cu; maps >= 32768 rows and batches
+ * >= 2048 queries).  The launch log (queries per thread == 0) marks the tensor-core filter.
+ * VO_NN_FORCE_PATH=ffma|tc in the environment at vo_nn_create pins one of them (tests, bench).
  */
 typedef struct vo_nn_s* vo_nn_t;
 
@@ -95,6 +101,9 @@ int vo_nn_best_match_device(vo_nn_t h, const float* queries_dev, int64_t n_queri
  * handle issued, four int32 per launch = (queries per thread, threads per block, query tiles, map
  * splits).  *n_launches = how many there were; at most `capacity` of them are written to out.    */
 int vo_nn_last_launches(vo_nn_t h, int32_t* out, int capacity, int* n_launches);
+/* (query, 128-row block) pairs the tensor-core filter of the last best_match call handed to the
+ * exact re-rank; -1 when that call ran the FP32 filter.  Synchronises.                            */
+int vo_nn_last_rescans(vo_nn_t h, int64_t* n_rescans);
 
 /* bruteForceSearch for a batch of queries: counts[q] = number of rows with d2 < norm^2.
  * If idx_out != NULL, the matching row indices of query q are written in ascending row

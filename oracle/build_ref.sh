@@ -29,4 +29,6 @@ $CXX $FLAGS "$REF/src/apps/evaluate.cpp" "$REF/src/evaluation_utils.cpp" $OBJS -
 # objects (it only uses declarations both header sets share), i.e. the reference implementation of
 # every stage on the synthetic frames
 $CXX $FLAGS "$HERE/../visual-odometry_b200/host/apps/vo_sequence.cpp" $OBJS -o "$OUT/bin/vo_sequence"
+# config 2 on the CPU: the seeded whole_test driver, same arrangement
+$CXX $FLAGS "$HERE/../visual-odometry_b200/host/apps/whole_synthetic.cpp" $OBJS -o "$OUT/bin/whole_synthetic"
 echo "built $OUT/libvo_ref.so and $OUT/bin/{vo_complete,picp_test,whole_test,evaluation}"

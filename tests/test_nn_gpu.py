@@ -59,11 +59,13 @@ WIDE_M = 38_000  # 297 tiles of 128 rows >= 2 x 148 SMs: large enough for the wi
 
 
 @pytest.mark.parametrize("rem,variant", WIDE_REMAINDERS)
-def test_wide_kernel_and_every_remainder_variant_vs_oracle(vo, oracle, synth, rem, variant):
-    """The headline path: batches above 8192 queries against a map of >= 2 tiles per SM run whole
-    4608-query tiles through nn_filter_kernel<12,384> plus ONE remainder launch whose register tile
-    depends on the remainder size.  The launch log proves which instantiations answered; indices
-    and d2 must equal the oracle's (brute_force_search.h:22-41)."""
+def test_wide_kernel_and_every_remainder_variant_vs_oracle(vo, oracle, synth, monkeypatch, rem, variant):
+    """The FP32 filter at headline shape (VO_NN_FORCE_PATH=ffma; by default a map this large goes
+    to the tensor-core filter): batches above 8192 queries against a map of >= 2 tiles per SM run
+    whole 4608-query tiles through nn_filter_kernel<12,384> plus ONE remainder launch whose register
+    tile depends on the remainder size.  The launch log proves which instantiations answered;
+    indices and d2 must equal the oracle's (brute_force_search.h:22-41)."""
+    monkeypatch.setenv("VO_NN_FORCE_PATH", "ffma")
     Q = 2 * 4608 + rem
     m = synth.nn_map_rows_np(0, WIDE_M)
     q, target = synth.nn_queries_np(Q, WIDE_M)
@@ -115,10 +117,11 @@ def _worst_case(kind, rng, M, Q):
 
 
 @pytest.mark.parametrize("kind", ["constant_prefix", "clustered"])
-def test_wide_kernel_worst_case_data_stays_exact(vo, oracle, kind):
-    """No-pruning data (every row passes the partial-distance filter, every tile is re-scanned for
+def test_wide_kernel_worst_case_data_stays_exact(vo, oracle, monkeypatch, kind):
+    """FP32 filter (forced).  No-pruning data (every row passes the partial-distance filter, every tile is re-scanned for
     every query) through the WIDE kernel and a remainder variant: only the number of re-scans may
     change, never the answers."""
+    monkeypatch.setenv("VO_NN_FORCE_PATH", "ffma")
     rng = np.random.RandomState(13)
     M, Q = WIDE_M, 2 * 4608 + 600
     m, q = _worst_case(kind, rng, M, Q)
@@ -150,6 +153,139 @@ def test_partial_filter_worst_cases_stay_exact(vo, oracle, kind):
     assert np.array_equal(idx, oi)
     assert np.array_equal(d2[oi >= 0], od[oi >= 0])
     assert (oi >= 0).sum() > Q // 3
+
+
+# ---- the tensor-core filter (csrc/nn_tc.cu): maps >= 32768 rows, batches >= 2048 queries ------------
+def _is_tc(launches):
+    return len(launches) == 1 and launches[0][0] == 0  # queries per thread == 0 marks nn_tc_filter_kernel
+
+
+@pytest.mark.parametrize("M,Q", [(32768, 2048), (38000, 2049), (38000, 5000), (50001, 12500),
+                                 (33000, 30000), (70000, 2 * 4608 + 600)])
+def test_tensor_core_filter_vs_oracle(vo, oracle, synth, M, Q):
+    """tcgen05 f16 filter + exact FP32 re-rank: indices AND d2 equal to the oracle's; the launch log
+    proves the tensor-core kernel answered.  Sizes cover 1..N query groups, ragged last query tiles
+    and ragged last map tiles."""
+    m = synth.nn_map_rows_np(0, M)
+    q, target = synth.nn_queries_np(Q, M)
+    nn = vo.NNIndex(0)
+    nn.set_map(m)
+    idx, d2 = nn.best_match(q, 0.1, want_d2=True)
+    launches, rescans = nn.last_launches(), nn.last_rescans()
+    nn.close()
+    assert _is_tc(launches), launches
+    oi, od = oracle.nn_best_match(m, q, 0.1)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(d2[oi >= 0], od[oi >= 0])
+    exact = (np.arange(Q) % 4) < 2
+    assert np.array_equal(idx[exact], target[exact])
+    # the 10-D filter is sharp: little beyond the true matches is ever re-ranked
+    assert (oi >= 0).sum() <= rescans <= 3 * Q
+
+
+@pytest.mark.parametrize("kind", ["constant_prefix", "clustered"])
+def test_tensor_core_filter_worst_case_data_stays_exact(vo, oracle, kind):
+    """data on which the FP32 partial-distance filter prunes nothing; the full-distance tensor-core
+    filter must stay exact on it as well (and re-scan only what is close in all ten dimensions)"""
+    rng = np.random.RandomState(17)
+    M, Q = WIDE_M, 2 * 4608 + 600
+    m, q = _worst_case(kind, rng, M, Q)
+    nn = vo.NNIndex(0)
+    nn.set_map(m)
+    idx, d2 = nn.best_match(q, 0.1, want_d2=True)
+    launches = nn.last_launches()
+    nn.close()
+    assert _is_tc(launches), launches
+    oi, od = oracle.nn_best_match(m, q, 0.1)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(d2[oi >= 0], od[oi >= 0])
+    assert (oi >= 0).sum() > Q // 3
+
+
+def test_tensor_core_filter_matches_at_the_edge_of_the_radius(vo, oracle):
+    """every query has exactly one row at a distance within a few ulp of the radius (inside or
+    outside), in a random direction: the f16 filter's margin must never hide an acceptable row, and
+    the strict `<` of brute_force_search.h:35 must be decided by the reference-order distance."""
+    rng = np.random.RandomState(19)
+    M, Q = 40000, 4096
+    m = rng.uniform(-1, 1, (M, 11)).astype(np.float32)
+    q = rng.uniform(-1, 1, (Q, 11)).astype(np.float32)
+    rows = rng.choice(M, Q, replace=False)
+    d = rng.normal(size=(Q, 10))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    scale = 0.1 * (1.0 + rng.randint(-8, 9, Q) * 2.0 ** -22)
+    q[:, 1:] = (m[rows, 1:].astype(np.float64) + d * scale[:, None]).astype(np.float32)
+    nn = vo.NNIndex(0)
+    nn.set_map(m)
+    idx, d2 = nn.best_match(q, 0.1, want_d2=True)
+    assert _is_tc(nn.last_launches())
+    nn.close()
+    oi, od = oracle.nn_best_match(m, q, 0.1)
+    assert 0.2 * Q < (oi >= 0).sum() < 0.8 * Q  # both sides of the edge are populated
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(d2[oi >= 0], od[oi >= 0])
+
+
+def test_tensor_core_filter_ties_large_radius_and_odd_queries(vo, oracle, monkeypatch):
+    rng = np.random.RandomState(23)
+    M = 33000
+    m = rng.uniform(-1, 1, (M, 11)).astype(np.float32)
+    dup = rng.choice(20000, 64, replace=False)
+    m[20000 + np.arange(64)] = m[dup]            # duplicate rows: the lowest index must win
+    m[32990:33000] = m[dup[0]]                   # and an 11-way tie ending in the ragged last tile
+    q = rng.uniform(-1, 1, (2100, 11)).astype(np.float32)
+    q[:64] = m[dup]
+    q[64] = m[dup[0]]
+    q[65, 1:] = np.nan                           # non-finite query: no row can match
+    q[66, 3] = np.inf
+    q[67, 1:] = 300.0                            # |q|^2 too large for f16: exact re-scan of every block
+    q[68, 1:] = 0.0
+    nn = vo.NNIndex(0)
+    nn.set_map(m)
+    for norm in (0.1, 0.8):                      # 0.8: hundreds of candidates per query, bound tightening
+        idx, d2 = nn.best_match(q, norm, want_d2=True)
+        assert _is_tc(nn.last_launches())
+        oi, od = oracle.nn_best_match(m, q, norm)
+        assert np.array_equal(idx, oi)
+        assert np.array_equal(d2[oi >= 0], od[oi >= 0])
+        assert np.array_equal(idx[:64], dup) and idx[64] == dup[0]
+        assert idx[65] == idx[66] == idx[67] == -1
+    nn.close()
+    # a radius for which the f16 margin would swamp the bound falls back to the FP32 filter
+    nn = vo.NNIndex(0)
+    nn.set_map(m)
+    idx = nn.best_match(q, 0.01)
+    assert not _is_tc(nn.last_launches())
+    assert np.array_equal(idx, oracle.nn_best_match(m, q, 0.01)[0])
+    nn.close()
+
+
+def test_both_filters_agree_at_scale(vo, synth, monkeypatch):
+    """1e5 queries x 1e6 rows through the tensor-core filter and through the FP32 filter: identical
+    indices and d2 (both are decided by the same exact re-rank)."""
+    import torch
+
+    M, Q = 1_000_000, 100_000
+    dev = torch.device("cuda:0")
+    m = synth.nn_map_torch(M, dev)
+    qn, _ = synth.nn_queries_np(Q, M)
+    q = torch.from_numpy(qn).to(dev)
+    out = {}
+    for path in ("tc", "ffma"):
+        monkeypatch.setenv("VO_NN_FORCE_PATH", path)
+        idx = torch.empty(Q, dtype=torch.int32, device=dev)
+        d2 = torch.empty(Q, dtype=torch.float32, device=dev)
+        nn = vo.NNIndex(0)
+        nn.set_stream(torch.cuda.current_stream().cuda_stream)
+        nn.set_map_device(m.data_ptr(), M, 11, 1)
+        nn.best_match_device(q.data_ptr(), Q, 11, 0.1, idx.data_ptr(), d2.data_ptr())
+        torch.cuda.synchronize()
+        assert _is_tc(nn.last_launches()) == (path == "tc")
+        out[path] = (idx.cpu().numpy(), d2.cpu().numpy())
+        nn.close()
+    assert np.array_equal(out["tc"][0], out["ffma"][0])
+    hit = out["tc"][0] >= 0
+    assert np.array_equal(out["tc"][1][hit], out["ffma"][1][hit])
 
 
 def test_large_radius_true_argmin(vo, oracle):

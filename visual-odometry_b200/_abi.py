@@ -60,6 +60,7 @@ PROTOTYPES = {
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p],
     ),
+    "vo_nn_last_rescans": (C.c_int, [C.c_void_p, c_i64p]),
     "vo_nn_last_launches": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "vo_nn_radius_search": (
         C.c_int,

@@ -153,6 +153,13 @@ class NNIndex:
         check(lib().vo_nn_last_launches(self._h, _ptr(buf), 16, C.byref(n)), "vo_nn_last_launches")
         return [tuple(int(x) for x in row) for row in buf[: min(n.value, 16)]]
 
+    def last_rescans(self):
+        """blocks the tensor-core filter handed to the exact re-rank in the last best_match (-1: the
+        FP32 filter ran)"""
+        n = C.c_int64(0)
+        check(lib().vo_nn_last_rescans(self._h, C.byref(n)), "vo_nn_last_rescans")
+        return int(n.value)
+
     def radius_search(self, queries, norm, max_per_query=0):
         q = _f32(queries)
         counts = np.empty(q.shape[0], dtype=np.int32)

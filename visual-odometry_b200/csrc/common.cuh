@@ -93,6 +93,16 @@ inline bool host_source_still_in_use(const void* host_ptr) {
   return a.type != cudaMemoryTypeUnregistered;
 }
 
+inline bool host_source_is_pageable(const void* host_ptr) { return !host_source_still_in_use(host_ptr); }
+
+// Pinned, chunked staging between pageable host memory and the device (stage.cu): a pool of
+// host threads copies through a ring of pinned chunks while the DMA engine moves the previous
+// one.  stage_h2d returns as soon as the caller's buffer is no longer referenced (the tail may
+// still be in flight on `s`); stage_d2h returns with the data in dst_host.  Transfers below
+// 1 MB, and pinned / managed host memory, take a plain cudaMemcpyAsync.
+int stage_h2d(int device, void* dst_dev, const void* src_host, size_t bytes, cudaStream_t s);
+int stage_d2h(int device, void* dst_host, const void* src_dev, size_t bytes, cudaStream_t s);
+
 // ---- device-side PTX wrappers (TMA bulk copy + mbarrier) ----------------------------------
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

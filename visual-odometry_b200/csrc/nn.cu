@@ -28,126 +28,29 @@
 //     (all but ~1.6e-6 of the rows for uniform appearances and radius 0.1) only decides how often
 //     the re-scan runs.
 //   * no float atomics, no data-dependent result: indices are bit-exact vs the oracle.
-#include <float.h>
-#include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
-#include <map>
-#include <vector>
 
-#include "common.cuh"
+#include "nn.cuh"
 
 namespace vo {
 
-constexpr int NN_DIM = 10;            // fast-path dimension (Vector11f minus the id column)
-constexpr int NN_FDIM = 5;            // leading dimensions the streaming filter looks at (<= 6)
-constexpr int NN_TM = 128;            // map rows per shared-memory tile
-constexpr int NN_STAGES = 4;          // TMA stages in flight
-constexpr int NN_ROW_BYTES = 48;      // packed row: 3 x float4
-constexpr uint32_t NN_TILE_BYTES = NN_TM * NN_ROW_BYTES;
-constexpr unsigned long long NN_KEY_NONE = 0xFFFFFFFFFFFFFFFFull;
-
-// ---- the reference's distance, one rounding per operation ---------------------------------
-// (p-q).tail(n).squaredNorm() under Eigen's SSE2 linear-vectorised redux; see oracle_sqdist.
-template <int DIM>
-__device__ __forceinline__ float ref_sqdist(const float (&m)[DIM], const float (&q)[DIM]) {
-  float s[DIM];
-#pragma unroll
-  for (int i = 0; i < DIM; ++i) {
-    const float d = __fsub_rn(m[i], q[i]);
-    s[i] = __fmul_rn(d, d);
-  }
-  constexpr int n4 = (DIM / 4) * 4, n8 = (DIM / 8) * 8;
-  float r;
-  if (n4 > 0) {
-    float a[4] = {s[0], s[1], s[2], s[3]};
-    if (n4 > 4) {
-      float c[4] = {s[4], s[5], s[6], s[7]};
-#pragma unroll
-      for (int i = 8; i < n8; i += 8)
-#pragma unroll
-        for (int l = 0; l < 4; ++l) {
-          a[l] = __fadd_rn(a[l], s[i + l]);
-          c[l] = __fadd_rn(c[l], s[i + 4 + l]);
-        }
-#pragma unroll
-      for (int l = 0; l < 4; ++l) a[l] = __fadd_rn(a[l], c[l]);
-      if (n4 > n8)
-#pragma unroll
-        for (int l = 0; l < 4; ++l) a[l] = __fadd_rn(a[l], s[n8 + l]);
-    }
-    r = __fadd_rn(__fadd_rn(a[0], a[2]), __fadd_rn(a[1], a[3]));
-#pragma unroll
-    for (int i = n4; i < DIM; ++i) r = __fadd_rn(r, s[i]);
-  } else {
-    r = s[0];
-#pragma unroll
-    for (int i = 1; i < DIM; ++i) r = __fadd_rn(r, s[i]);
-  }
-  return r;
-}
-
-// run-time dimension version (general kernel)
-__device__ __forceinline__ float ref_sqdist_dyn(const float* __restrict__ m,
-                                                const float* __restrict__ q, int dim) {
-  const int n4 = (dim / 4) * 4, n8 = (dim / 8) * 8;
-  auto sq = [&](int i) {
-    const float d = __fsub_rn(m[i], q[i]);
-    return __fmul_rn(d, d);
-  };
-  float r;
-  if (n4 > 0) {
-    float a0 = sq(0), a1 = sq(1), a2 = sq(2), a3 = sq(3);
-    if (n4 > 4) {
-      float c0 = sq(4), c1 = sq(5), c2 = sq(6), c3 = sq(7);
-      for (int i = 8; i < n8; i += 8) {
-        a0 = __fadd_rn(a0, sq(i));
-        a1 = __fadd_rn(a1, sq(i + 1));
-        a2 = __fadd_rn(a2, sq(i + 2));
-        a3 = __fadd_rn(a3, sq(i + 3));
-        c0 = __fadd_rn(c0, sq(i + 4));
-        c1 = __fadd_rn(c1, sq(i + 5));
-        c2 = __fadd_rn(c2, sq(i + 6));
-        c3 = __fadd_rn(c3, sq(i + 7));
-      }
-      a0 = __fadd_rn(a0, c0);
-      a1 = __fadd_rn(a1, c1);
-      a2 = __fadd_rn(a2, c2);
-      a3 = __fadd_rn(a3, c3);
-      if (n4 > n8) {
-        a0 = __fadd_rn(a0, sq(n8));
-        a1 = __fadd_rn(a1, sq(n8 + 1));
-        a2 = __fadd_rn(a2, sq(n8 + 2));
-        a3 = __fadd_rn(a3, sq(n8 + 3));
-      }
-    }
-    r = __fadd_rn(__fadd_rn(a0, a2), __fadd_rn(a1, a3));
-    for (int i = n4; i < dim; ++i) r = __fadd_rn(r, sq(i));
-  } else {
-    r = sq(0);
-    for (int i = 1; i < dim; ++i) r = __fadd_rn(r, sq(i));
-  }
-  return r;
-}
-
-__device__ __forceinline__ unsigned long long nn_pack_key(float d2, uint32_t row) {
-  // d2 >= 0, so its bit pattern is monotone as an unsigned integer
-  return (static_cast<unsigned long long>(__float_as_uint(d2)) << 32) | row;
-}
-
 // ---- map re-pack ------------------------------------------------------------------------------
-// one thread per padded row; rows >= n_rows are neutral ( |m|^2 = +inf never passes the filter )
+// one thread per row of [r_begin, r_end); `rows` points at row r_begin of the caller's layout (the
+// map may arrive in chunks); rows >= n_rows are neutral ( |m|^2 = +inf never passes the filter )
 __global__ void __launch_bounds__(256)
-nn_repack_kernel(const float* __restrict__ rows, int64_t n_rows, int64_t n_rows_padded,
+nn_repack_kernel(const float* __restrict__ rows, int64_t r_begin, int64_t r_end, int64_t n_rows,
                  int row_stride, int skip, float4* __restrict__ packed,
                  unsigned int* __restrict__ mm_max_bits) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = r_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   float mm_for_max = 0.f;
-  if (r < n_rows_padded) {
+  if (r < r_end) {
     float v[NN_DIM];
     float mm, mm6;
     if (r < n_rows) {
-      const float* src = rows + r * (int64_t)row_stride + skip;
+      const float* src = rows + (r - r_begin) * (int64_t)row_stride + skip;
 #pragma unroll
       for (int k = 0; k < NN_DIM; ++k) v[k] = __ldg(src + k);
       mm6 = 0.f;
@@ -189,38 +92,6 @@ struct NNParams {
   const float* mm_max;      // device scalar written by the re-pack
   unsigned long long* keys; // per query, pre-set to NN_KEY_NONE
 };
-
-// Filter thresholds for one query.  With u = 2^-24, d2_ref < bound implies
-//   full:     acc10 = |m|^2   + sum_{k<10} (-2 q_k) m_k  <  (bound - |q|^2)   + eps
-//   partial:  acc6  = |m|^2_6 + sum_{k<6}  (-2 q_k) m_k  <  (bound - |q|^2_6) + eps
-// (the partial squared distance over the first NN_FDIM dimensions is a lower bound of the full
-// one), where eps = 64u(|q|^2 + max|m|^2) + 32u|bound| covers the FMA chains and the roundings of
-// |m|^2, |q|^2 and of the reference's own d2.  `qn` is the query scaled by -2.
-__device__ __forceinline__ float nn_eps(float qq, float bound, float mm_max) {
-  const float u64 = 64.f * 5.9604645e-8f;  // 64 * 2^-24
-  return u64 * (qq + mm_max) + 0.5f * u64 * fabsf(bound);
-}
-__device__ __forceinline__ void nn_query_norms(const float (&qn)[NN_DIM], float* qq6, float* qq) {
-  float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < NN_FDIM; ++k) {
-    const float q = -0.5f * qn[k];
-    s = fmaf(q, q, s);
-  }
-  *qq6 = s;
-#pragma unroll
-  for (int k = NN_FDIM; k < NN_DIM; ++k) {
-    const float q = -0.5f * qn[k];
-    s = fmaf(q, q, s);
-  }
-  *qq = s;
-}
-__device__ __forceinline__ float nn_threshold_partial(float qq6, float qq, float bound, float mm_max) {
-  return (bound - qq6) + nn_eps(qq, bound, mm_max);
-}
-__device__ __forceinline__ float nn_threshold_full(float qq, float bound, float mm_max) {
-  return (bound - qq) + nn_eps(qq, bound, mm_max);
-}
 
 // Slow path: re-scan one tile for ONE query with the full distance, exact arithmetic for the
 // candidates — executed by the whole warp (lane l takes rows l, l+32, ...), because in
@@ -534,29 +405,6 @@ nn_radius_kernel(const float* __restrict__ rows, int64_t n_rows, int row_stride,
 // =================================================================================================
 using namespace vo;
 
-struct vo_nn_s {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  bool own_stream = false;
-  int64_t n_rows = 0;
-  int row_stride = 0, skip = 0, dim = 0;
-  bool fast = false;          // packed layout valid (dim == NN_DIM)
-  int64_t n_tiles = 0;
-  DevBuf raw;                 // staging copy of the caller's rows (host variant / general path)
-  // rows as seen by the general + radius kernels: the packed buffer (stride 12, skip 0) on the
-  // fast path, the private raw copy otherwise
-  const float* rows_dev = nullptr;
-  int map_stride = 0, map_skip = 0;
-  DevBuf packed;
-  DevBuf scalars;             // [0] = mm_max
-  DevBuf keys;
-  DevBuf q_stage, idx_stage, d2_stage, cnt_stage, list_stage;
-  std::map<int, int> occupancy;  // (TQ, THREADS) -> resident CTAs per SM of that filter variant
-  // filter launches of the last best_match call: (TQ, THREADS, query tiles, map splits) each, so a
-  // test can PROVE which instantiation answered it (vo_nn_last_launches)
-  std::vector<int32_t> last_launches;
-};
-
 static int nn_launch_filter(vo_nn_s* h, const float* queries_dev, int64_t nq, int qstride,
                             float bound) {
   NNParams p;
@@ -640,8 +488,11 @@ static int nn_launch_filter(vo_nn_s* h, const float* queries_dev, int64_t nq, in
   return launch(nn_filter_kernel<12, 384>, 12, 384, full, rem);
 }
 
-static int nn_set_map_common(vo_nn_s* h, const float* rows_dev, int64_t n_rows, int row_stride,
-                             int skip) {
+// set_map in three steps so that a host map can arrive in chunks: begin (sizes, buffers), one
+// repack per row range, end (f16 tiles for the tensor-core filter)
+static int nn_set_map_begin(vo_nn_s* h, const float* rows_dev, int64_t n_rows, int row_stride, int skip) {
+  h->have_mm_max = false;
+  h->tc_ready = false;
   h->n_rows = n_rows;
   h->row_stride = row_stride;
   h->skip = skip;
@@ -652,22 +503,63 @@ static int nn_set_map_common(vo_nn_s* h, const float* rows_dev, int64_t n_rows, 
   h->fast = (h->dim == NN_DIM);
   if (!h->fast || n_rows == 0) return VO_OK;
   h->n_tiles = (n_rows + NN_TM - 1) / NN_TM;
-  const int64_t padded = h->n_tiles * NN_TM;
-  int rc = h->packed.reserve((size_t)padded * NN_ROW_BYTES);
+  int rc = h->packed.reserve((size_t)h->n_tiles * NN_TM * NN_ROW_BYTES);
   if (rc) return rc;
   rc = h->scalars.reserve(64);
   if (rc) return rc;
   VO_CUDA(cudaMemsetAsync(h->scalars.p, 0, 64, h->stream));
+  return VO_OK;
+}
+
+// rows [r_begin, r_end) of the caller's layout, `rows_dev` pointing at row r_begin; the last range
+// also writes the neutral padding rows of the last tile
+static int nn_repack_range(vo_nn_s* h, const float* rows_dev, int64_t r_begin, int64_t r_end) {
+  if (r_end >= h->n_rows) r_end = h->n_tiles * NN_TM;
+  if (r_end <= r_begin) return VO_OK;
   const int threads = 256;
-  const int64_t blocks = (padded + threads - 1) / threads;
+  const int64_t blocks = (r_end - r_begin + threads - 1) / threads;
   nn_repack_kernel<<<(unsigned)blocks, threads, 0, h->stream>>>(
-      rows_dev, n_rows, padded, row_stride, skip, h->packed.as<float4>(),
+      rows_dev, r_begin, r_end, h->n_rows, h->row_stride, h->skip, h->packed.as<float4>(),
       h->scalars.as<unsigned int>());
   VO_LAUNCH_CHECK();
+  return VO_OK;
+}
+
+static int nn_set_map_end(vo_nn_s* h) {
+  if (!h->fast || h->n_rows == 0) return VO_OK;
   // from here on the caller's rows are not needed: the packed rows are [a0..a9 |a|^2 0]
   h->rows_dev = h->packed.as<float>();
   h->map_stride = NN_ROW_BYTES / (int)sizeof(float);
   h->map_skip = 0;
+  // f16 operand tiles for the tensor-core filter (large maps only; +32 B per row)
+  if (h->force_path != 1 && (h->n_rows >= NN_TC_MIN_ROWS || h->force_path == 2)) {
+    int rc = nn_tc_pack(h);
+    if (rc) return rc;
+    h->tc_ready = true;
+  }
+  return VO_OK;
+}
+
+static int nn_set_map_common(vo_nn_s* h, const float* rows_dev, int64_t n_rows, int row_stride,
+                             int skip) {
+  int rc = nn_set_map_begin(h, rows_dev, n_rows, row_stride, skip);
+  if (rc || !h->fast || n_rows == 0) return rc;
+  rc = nn_repack_range(h, rows_dev, 0, n_rows);
+  if (rc) return rc;
+  return nn_set_map_end(h);
+}
+
+// The tensor-core filter needs every |m|^2 to fit f16 arithmetic, and its margin (~2^-9 |q||m|)
+// to be of the order of the radius, otherwise it passes everything and the FFMA filter (margin
+// ~2^-18) is the better tool.  max|m|^2 lives on the device; it is read back once per map.
+static int nn_tc_usable(vo_nn_s* h, float bound, bool* ok) {
+  if (!h->have_mm_max) {
+    VO_CUDA(cudaMemcpyAsync(&h->mm_max_host, h->scalars.p, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    VO_CUDA(cudaStreamSynchronize(h->stream));
+    h->have_mm_max = true;
+  }
+  const float mm = h->mm_max_host;
+  *ok = mm <= 30000.f && 4.01f * 4.8828125e-4f * mm <= 8.f * bound;
   return VO_OK;
 }
 
@@ -679,10 +571,18 @@ static int nn_best_match_common(vo_nn_s* h, const float* queries_dev, int64_t nq
   int rc = h->keys.reserve((size_t)nq * sizeof(unsigned long long));
   if (rc) return rc;
   VO_CUDA(cudaMemsetAsync(h->keys.p, 0xFF, (size_t)nq * sizeof(unsigned long long), h->stream));
+  h->last_was_tc = false;
   if (h->n_rows > 0) {
     if (h->fast) {
-      rc = nn_launch_filter(h, queries_dev, nq, qstride, bound);
+      bool tc = h->tc_ready && (h->force_path == 2 || nq >= NN_TC_MIN_QUERIES);
+      if (tc && h->force_path != 2) {
+        rc = nn_tc_usable(h, bound, &tc);
+        if (rc) return rc;
+      }
+      rc = tc ? nn_tc_launch(h, queries_dev, nq, qstride, bound)
+              : nn_launch_filter(h, queries_dev, nq, qstride, bound);
       if (rc) return rc;
+      h->last_was_tc = tc;
     } else {
       const int threads = 128;
       const int64_t qblocks = (nq + threads - 1) / threads;
@@ -722,6 +622,10 @@ int vo_nn_create(vo_nn_t* out, int device) {
     return VO_ERR_CUDA;
   }
   h->own_stream = true;
+  if (const char* fp = getenv("VO_NN_FORCE_PATH")) {
+    if (!strcmp(fp, "ffma")) h->force_path = 1;
+    else if (!strcmp(fp, "tc")) h->force_path = 2;
+  }
   *out = h;
   return VO_OK;
 }
@@ -739,6 +643,8 @@ int vo_nn_destroy(vo_nn_t h) {
   h->d2_stage.release();
   h->cnt_stage.release();
   h->list_stage.release();
+  h->tiles16.release();
+  h->tc_stats.release();
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return VO_OK;
@@ -777,16 +683,32 @@ int vo_nn_set_map(vo_nn_t h, const float* rows_host, int64_t n_rows, int row_str
   if (rc) return rc;
   VO_REQUIRE(rows_host != nullptr || n_rows == 0, VO_ERR_ARG, "null rows");
   DeviceGuard g(h->device);
-  const size_t bytes = (size_t)n_rows * row_stride * sizeof(float);
-  rc = h->raw.reserve(bytes ? bytes : 16);
+  const size_t row_bytes = (size_t)row_stride * sizeof(float);
+  if (row_stride - skip_cols != NN_DIM || n_rows == 0) {
+    // general path: the kernels read the caller's layout at query time, keep a device copy
+    const size_t bytes = (size_t)n_rows * row_bytes;
+    rc = h->raw.reserve(bytes ? bytes : 16);
+    if (rc) return rc;
+    if ((rc = stage_h2d(h->device, h->raw.p, rows_host, bytes, h->stream))) return rc;
+    return nn_set_map_common(h, h->raw.as<float>(), n_rows, row_stride, skip_cols);
+  }
+  // fast path: the map arrives in chunks of <= 32 MB through the pinned staging ring and each
+  // chunk is re-packed as soon as it has landed (stream order), so the host copy of chunk k+1
+  // overlaps the DMA and the re-pack of chunk k and the raw rows never exist on the device as a
+  // whole (a 1e8-row map is 4.4 GB on the host, 4.8 + 3.2 GB packed)
+  const int64_t chunk_rows = std::max<int64_t>(1, ((int64_t)32 << 20) / (int64_t)row_bytes);
+  rc = h->raw.reserve((size_t)std::min(chunk_rows, n_rows) * row_bytes);
   if (rc) return rc;
-  if (bytes)
-    VO_CUDA(cudaMemcpyAsync(h->raw.p, rows_host, bytes, cudaMemcpyHostToDevice, h->stream));
-  rc = nn_set_map_common(h, h->raw.as<float>(), n_rows, row_stride, skip_cols);
+  rc = nn_set_map_begin(h, h->raw.as<float>(), n_rows, row_stride, skip_cols);
   if (rc) return rc;
-  // the host buffer may be freed by the caller as soon as we return
-  if (bytes && host_source_still_in_use(rows_host)) VO_CUDA(cudaStreamSynchronize(h->stream));
-  return VO_OK;
+  for (int64_t r0 = 0; r0 < n_rows; r0 += chunk_rows) {
+    const int64_t r1 = std::min(n_rows, r0 + chunk_rows);
+    rc = stage_h2d(h->device, h->raw.p, rows_host + r0 * (int64_t)row_stride, (size_t)(r1 - r0) * row_bytes,
+                   h->stream);
+    if (rc) return rc;
+    if ((rc = nn_repack_range(h, h->raw.as<float>(), r0, r1))) return rc;
+  }
+  return nn_set_map_end(h);
 }
 
 int vo_nn_set_map_device(vo_nn_t h, const float* rows_dev, int64_t n_rows, int row_stride,
@@ -836,16 +758,25 @@ int vo_nn_best_match(vo_nn_t h, const float* queries_host, int64_t n_queries, in
   if (rc) return rc;
   rc = h->d2_stage.reserve((size_t)n_queries * sizeof(float));
   if (rc) return rc;
-  VO_CUDA(cudaMemcpyAsync(h->q_stage.p, queries_host, qbytes, cudaMemcpyHostToDevice, h->stream));
+  if ((rc = stage_h2d(h->device, h->q_stage.p, queries_host, qbytes, h->stream))) return rc;
   rc = nn_best_match_common(h, h->q_stage.as<float>(), n_queries, query_stride, norm,
                             h->idx_stage.as<int32_t>(), h->d2_stage.as<float>());
   if (rc) return rc;
-  VO_CUDA(cudaMemcpyAsync(best_idx_host, h->idx_stage.p, (size_t)n_queries * sizeof(int32_t),
-                          cudaMemcpyDeviceToHost, h->stream));
-  if (best_d2_host)
-    VO_CUDA(cudaMemcpyAsync(best_d2_host, h->d2_stage.p, (size_t)n_queries * sizeof(float),
-                            cudaMemcpyDeviceToHost, h->stream));
+  if (best_d2_host &&
+      (rc = stage_d2h(h->device, best_d2_host, h->d2_stage.p, (size_t)n_queries * sizeof(float), h->stream)))
+    return rc;
+  return stage_d2h(h->device, best_idx_host, h->idx_stage.p, (size_t)n_queries * sizeof(int32_t), h->stream);
+}
+
+int vo_nn_last_rescans(vo_nn_t h, int64_t* n_rescans) {
+  VO_REQUIRE(h != nullptr && n_rescans != nullptr, VO_ERR_ARG, "null pointer");
+  *n_rescans = -1;
+  if (!h->last_was_tc) return VO_OK;
+  DeviceGuard g(h->device);
+  unsigned long long v = 0;
+  VO_CUDA(cudaMemcpyAsync(&v, h->tc_stats.p, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
   VO_CUDA(cudaStreamSynchronize(h->stream));
+  *n_rescans = (int64_t)v;
   return VO_OK;
 }
 

@@ -1,0 +1,499 @@
+// nn_tc.cu — the tensor-core filter of the exact appearance nearest neighbour (sm_100a, tcgen05).
+//
+// Same contract as nn.cu (bruteForceBestMatch, reference include/brute_force_search.h:22-41): the
+// answer is decided by an exact re-rank in the reference's own FP32 rounding order; what changes is
+// the FILTER that finds the few (query,row) pairs worth re-ranking.  nn.cu tests a 5-of-10-dimension
+// partial distance with FP32 FMAs (10 executed flop per pair, data-dependent pruning).  Here the
+// full 10-D distance of 128 queries x 128 rows is ONE tcgen05.mma:
+//
+//     A (queries, K-major f16)   a_i = [ -2q_0 .. -2q_9 | 1 | 1 | |q|^2_hi | |q|^2_lo | 0 0 ]
+//     B (map rows, K-major f16)  b_j = [  m_0 ..  m_9   | |m|^2_hi | |m|^2_lo | 1 | 1 | 0 0 ]
+//     D = A B^T  (FP32, in TMEM)  d_ij = |m_j|^2 - 2 q_i.m_j + |q_i|^2  ~  |q_i - m_j|^2
+//
+// (K = 16 is one kind::f16 instruction; the norms travel as hi+lo f16 pairs so that only the
+// rounding of the COORDINATES to f16, u = 2^-11, matters.)  The accumulator never leaves the chip
+// as data: 16 epilogue warps read it back with tcgen05.ld (thread = TMEM lane = query), fold their
+// 128 columns into one minimum with 3-input mins and compare it with the query's threshold
+//     thr_i = best_i + eps_i ,   eps_i = 4.01 u |q_i| max|m| + (accumulation / norm slack) ,
+// which is an upper bound of d_ij for every row the reference could accept (derivation: DESIGN.md
+// §4.1b).  A warp with a flagged query re-scans those 128 rows from the FP32 rows in global memory
+// exactly as nn.cu does (full FMA test, then the reference-order distance, 64-bit atomicMin key).
+// In ten dimensions the margin costs nothing: for uniform appearances the filter passes ~3e-10 of
+// the pairs, and clustered descriptors only add re-scans, never a cliff.
+//
+// Pipeline per CTA (one per SM, persistent): a TMA warp streams 256-row f16 tiles (8 KB, 1-D bulk
+// copies) into a 4-stage ring; one thread issues two N=128 MMAs per (query tile, map tile) into
+// four 128-column TMEM buffers; four warpgroups drain one buffer each.  Measured limits
+// (profiles/r02a_tc_probe.md): the f16 MMA takes 64 cycles per 128x128 tile, the TMEM read of the
+// epilogue 160 — the kernel is bound by tcgen05.ld throughput (~410 B/clk/SM).
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "nn.cuh"
+
+namespace vo {
+
+constexpr int TC_BN = 256;                  // map rows per smem tile
+constexpr int TC_SUB = 128;                 // rows per MMA (N) and per TMEM buffer
+constexpr int TC_ROW_BYTES = 32;            // 16 halves
+constexpr uint32_t TC_TILE_BYTES = TC_BN * TC_ROW_BYTES;   // 8 KB
+constexpr int TC_RESCAN = 64;                // rows one epilogue warp answers for (its column half)
+constexpr int TC_STAGES = 4;
+constexpr int TC_QT_MAX = 16;               // query tiles (of 128) resident per CTA
+constexpr uint32_t TC_A_BYTES = 128 * TC_ROW_BYTES;        // 4 KB per query tile
+constexpr int TC_EPI_WARPS = 16;
+constexpr int TC_PIPES = TC_BN / TC_SUB;    // 2 independent MMA->epilogue pipelines (halves of a map tile)
+constexpr int TC_PIPE_WARPS = TC_EPI_WARPS / TC_PIPES;     // 8 epilogue warps per pipeline
+constexpr int TC_THREADS = (TC_EPI_WARPS + 1 + TC_PIPES) * 32;  // + TMA warp + one MMA warp per pipeline
+constexpr int TC_BUFS = 4;                  // TMEM accumulator buffers of TC_SUB columns; pipeline p owns p, p+2
+constexpr float TC_U16 = 4.8828125e-4f;     // 2^-11, unit roundoff of f16 (round to nearest)
+constexpr float TC_PAD_NORM = 60000.f;      // |m|^2 of a padding row: never under any threshold
+constexpr float TC_MAX_NORM = 30000.f;      // |m|^2, |q|^2 above this do not fit f16 arithmetic
+
+constexpr size_t TC_SMEM_A = (size_t)TC_QT_MAX * TC_A_BYTES;            // 64 KB
+constexpr size_t TC_SMEM_B = (size_t)TC_STAGES * TC_TILE_BYTES;         // 32 KB
+constexpr size_t TC_SMEM_THR = (size_t)TC_QT_MAX * 128 * sizeof(float); // 8 KB (x2: thr, eps)
+constexpr size_t TC_SMEM_BYTES = TC_SMEM_A + TC_SMEM_B + 2 * TC_SMEM_THR + 256;
+
+struct NNTCParams {
+  const unsigned char* tiles16;  // f16 map tiles, TC_TILE_BYTES each, 8-row interleaved
+  const float4* packed;          // FP32 rows (48 B) for the exact re-rank
+  int64_t n_rows;
+  int64_t n_rows_packed;         // rows the FP32 buffer holds (padding included)
+  int64_t n_tiles16;
+  const float* queries;
+  int64_t n_queries;
+  int query_stride;
+  int skip;
+  float bound;                   // norm*norm
+  const float* mm_max;
+  unsigned long long* keys;
+  int qt;                        // query tiles per group (<= TC_QT_MAX)
+  int n_groups;
+  unsigned long long* stats;     // [0] = re-scans (flagged (query, 128-row block) pairs)
+};
+
+// ---- tcgen05 / TMEM wrappers ------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// mbarrier arrive when every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, 0, 0;\n"  // p = false: D = A*B (no accumulation)
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float tc_min3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));  // SASS FMNMX3
+  return r;
+}
+// minimum of 32 accumulator columns, folded into four independent chains (a single chain of
+// dependent 3-input mins would leave the warp waiting on its own latency)
+__device__ __forceinline__ void tc_fold(float (&mn)[4], const uint32_t (&r)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      mn[c] = tc_min3(mn[c], __uint_as_float(r[j + 2 * c]), __uint_as_float(r[j + 2 * c + 1]));
+  }
+}
+
+// Shared-memory matrix descriptor: K-major, no swizzle.  A core matrix is 8 rows x 16 bytes stored
+// as 128 contiguous bytes; the two 16-byte K chunks of one instruction are `lbo` bytes apart,
+// consecutive 8-row groups `sbo` bytes (layout verified on hardware by tools/tc_probe.cu).
+__device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr) {
+  constexpr uint64_t lbo = 128, sbo = 256;
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((lbo >> 4) << 16) | ((sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ uint64_t tc_desc_hi() {  // everything but the start address
+  return ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor: D = F32 (bits 4-5 = 1), A = B = F16 (0), both K-major, N>>3 at bit 17,
+// M>>4 at bit 24
+constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(TC_SUB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+// byte offset of (row r, K chunk c) inside an interleaved operand tile
+__host__ __device__ __forceinline__ uint32_t tc_row_off(int r, int c) {
+  return (uint32_t)((r >> 3) * 256 + c * 128 + (r & 7) * 16);
+}
+
+// x = hi + lo with hi, lo representable in f16 (|x - hi - lo| <= 2^-22 |x| + 2^-25)
+__device__ __forceinline__ void tc_split(float x, __half* hi, __half* lo) {
+  const __half h = __float2half_rn(x);
+  *hi = h;
+  *lo = __float2half_rn(x - __half2float(h));
+}
+
+// ---- map tiles: FP32 packed rows -> interleaved f16 operand tiles -----------------------------------
+__global__ void __launch_bounds__(256)
+nn_tc_pack_kernel(const float4* __restrict__ packed, int64_t n_rows, int64_t n_rows_tc,
+                  unsigned char* __restrict__ tiles16) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows_tc) return;
+  __align__(16) __half v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = __float2half_rn(0.f);
+  if (r < n_rows) {
+    const float4 a = packed[r * 3 + 0], b = packed[r * 3 + 1], c = packed[r * 3 + 2];
+    const float m[NN_DIM] = {a.x, a.y, a.z, a.w, b.x, b.y, c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int k = 0; k < NN_DIM; ++k) v[k] = __float2half_rn(m[k]);
+    tc_split(b.w, &v[10], &v[11]);  // |m|^2 as computed by the FP32 re-pack
+  } else {
+    v[10] = __float2half_rn(TC_PAD_NORM);
+  }
+  v[12] = v[13] = __float2half_rn(1.f);  // multiply |q|^2_hi, |q|^2_lo
+  unsigned char* tile = tiles16 + (r / TC_BN) * (int64_t)TC_TILE_BYTES;
+  const int rr = (int)(r % TC_BN);
+  *reinterpret_cast<uint4*>(tile + tc_row_off(rr, 0)) = *reinterpret_cast<const uint4*>(&v[0]);
+  *reinterpret_cast<uint4*>(tile + tc_row_off(rr, 1)) = *reinterpret_cast<const uint4*>(&v[8]);
+}
+
+// Soundness margin of the f16 tensor-core distance for one query:
+//   |d_tc - d2_ref| <= 2 * (2u + u^2) |q||m|          coordinates rounded to f16, u = 2^-11
+//                    + 2^-18 (|q|^2 + |m|^2 + 2|q||m|)  norms' hi/lo residual, their FP32 rounding
+//                                                       and the tensor core's FP32 accumulation
+//                    + 2^-21 (|q| + |m|)                 f16 underflow of tiny coordinates
+//                    + nn_eps                            the reference's own rounding of d2
+__device__ __forceinline__ float tc_eps(float qq, float bound, float mm_max) {
+  const float qm = sqrtf(qq * mm_max) * 1.0000002f;
+  return 4.01f * TC_U16 * qm + 3.8146973e-6f * (qq + mm_max + 2.f * qm) +
+         4.7683716e-7f * (sqrtf(qq) + sqrtf(mm_max)) + nn_eps(qq, bound, mm_max);
+}
+
+// Exact re-rank of ONE query against TC_RESCAN consecutive rows, executed by the whole warp (lane l takes
+// rows l, l+32, ...) from the FP32 rows in global memory: the full 10-D FMA test first, then the
+// candidates in the REFERENCE order, merged into the query's 64-bit key (strict minimum, lowest row
+// on ties — brute_force_search.h:30-40).  Returns the best exact d2 known for the query.
+__device__ __forceinline__ float tc_rescan_warp(const float4* __restrict__ packed, int64_t row0,
+                                                int64_t n_rows, const float* __restrict__ query,
+                                                float radius2, float mm_max, unsigned long long* key) {
+  const int lane = threadIdx.x & 31;
+  float q[NN_DIM], qn[NN_DIM];
+#pragma unroll
+  for (int k = 0; k < NN_DIM; ++k) {
+    q[k] = __ldg(query + k);
+    qn[k] = -2.f * q[k];
+  }
+  float qq6, qq;
+  nn_query_norms(qn, &qq6, &qq);
+  const unsigned long long k0 = *reinterpret_cast<volatile unsigned long long*>(key);
+  const float best = (k0 == NN_KEY_NONE) ? radius2 : __uint_as_float(static_cast<unsigned int>(k0 >> 32));
+  const float tq = nn_threshold_full(qq, best, mm_max);
+  float found = best;
+#pragma unroll
+  for (int r = lane; r < TC_RESCAN; r += 32) {
+    const int64_t row = row0 + r;
+    if (row < n_rows) {
+      const float4 a = __ldg(packed + row * 3 + 0), b = __ldg(packed + row * 3 + 1),
+                   c = __ldg(packed + row * 3 + 2);
+      float acc = b.w;
+      acc = fmaf(qn[0], a.x, acc);
+      acc = fmaf(qn[1], a.y, acc);
+      acc = fmaf(qn[2], a.z, acc);
+      acc = fmaf(qn[3], a.w, acc);
+      acc = fmaf(qn[4], b.x, acc);
+      acc = fmaf(qn[5], b.y, acc);
+      acc = fmaf(qn[6], c.x, acc);
+      acc = fmaf(qn[7], c.y, acc);
+      acc = fmaf(qn[8], c.z, acc);
+      acc = fmaf(qn[9], c.w, acc);
+      if (acc < tq) {
+        const float m[NN_DIM] = {a.x, a.y, a.z, a.w, b.x, b.y, c.x, c.y, c.z, c.w};
+        const float d2 = ref_sqdist<NN_DIM>(m, q);
+        if (d2 < radius2 && d2 <= best) {
+          found = fminf(found, d2);
+          atomicMin(key, nn_pack_key(d2, static_cast<uint32_t>(row)));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) found = fminf(found, __shfl_xor_sync(0xffffffffu, found, o));
+  return found;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCParams p) {
+  extern __shared__ __align__(1024) unsigned char tc_smem[];
+  unsigned char* sA = tc_smem;
+  unsigned char* sB = tc_smem + TC_SMEM_A;
+  float* thr_s = reinterpret_cast<float*>(tc_smem + TC_SMEM_A + TC_SMEM_B);  // [qt][128]
+  float* eps_s = thr_s + TC_QT_MAX * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(eps_s + TC_QT_MAX * 128);
+  uint64_t* full = bars;                       // [TC_STAGES]  TMA bytes landed
+  uint64_t* empty = full + TC_STAGES;          // [TC_STAGES]  every MMA reading the stage is done
+  uint64_t* tfull = empty + TC_STAGES;         // [TC_BUFS]    accumulator written
+  uint64_t* tempty = tfull + TC_BUFS;          // [TC_BUFS]    accumulator drained (the 4 warps of a warpgroup)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + TC_BUFS);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qt = p.qt;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], TC_PIPES);  // one commit per MMA warp
+    }
+#pragma unroll
+    for (int b = 0; b < TC_BUFS; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], TC_PIPE_WARPS);
+    }
+    mbar_fence_init();
+  }
+  if (warp == TC_EPI_WARPS + 1) tmem_alloc(tmem_slot, 512);  // the whole tensor memory of the SM
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  // 512 columns is all of it, so the allocation starts at column 0 / lane 0: addresses below are
+  // plain constants (and the issuing warp keeps them in uniform registers)
+  const uint32_t tmem_base = *tmem_slot;
+  if (tmem_base != 0u) __trap();
+  const float mm_max = __ldg(p.mm_max);
+
+  // this CTA's share of the (query group, map tile) units, group-major
+  const int64_t units = (int64_t)p.n_groups * p.n_tiles16;
+  int64_t u = units * blockIdx.x / gridDim.x;
+  const int64_t u_end = units * (blockIdx.x + 1) / gridDim.x;
+
+  // running counters, identical in every role
+  uint32_t unit_n = 0;   // map tiles streamed so far (position in the smem ring)
+  uint32_t acc_n = 0;    // accumulator tiles each pipeline has produced so far (= unit_n * qt)
+
+  while (u < u_end) {
+    const int g = (int)(u / p.n_tiles16);
+    const int64_t t0 = u % p.n_tiles16;
+    const int64_t nt = min(p.n_tiles16 - t0, u_end - u);  // tiles of this segment
+    u += nt;
+
+    // ---- segment prologue: this group's queries -> f16 A tiles + thresholds -------------------------
+    __syncthreads();  // every accumulator of the previous segment has been drained
+    const int64_t qbase = (int64_t)g * qt * 128;
+    if (warp < TC_EPI_WARPS) {
+      for (int i = tid; i < qt * 128; i += TC_EPI_WARPS * 32) {
+        const int64_t qi = qbase + i;
+        __align__(16) __half v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = __float2half_rn(0.f);
+        float thr = -INFINITY, eps = 0.f;
+        if (qi < p.n_queries) {
+          const float* src = p.queries + qi * (int64_t)p.query_stride + p.skip;
+          float qn[NN_DIM];
+#pragma unroll
+          for (int k = 0; k < NN_DIM; ++k) qn[k] = -2.f * __ldg(src + k);
+          float qq6, qq;
+          nn_query_norms(qn, &qq6, &qq);
+          if (qq <= TC_MAX_NORM) {
+#pragma unroll
+            for (int k = 0; k < NN_DIM; ++k) v[k] = __float2half_rn(qn[k]);
+            v[10] = v[11] = __float2half_rn(1.f);  // multiply |m|^2_hi, |m|^2_lo
+            tc_split(qq, &v[12], &v[13]);
+            eps = tc_eps(qq, p.bound, mm_max);
+            thr = p.bound + eps;
+          } else if (qq < INFINITY) {
+            thr = INFINITY;  // too large for f16: every block is re-scanned exactly (A row stays 0)
+          }                  // non-finite query: no row can satisfy d2 < norm^2, nothing to do
+        }
+        unsigned char* dst = sA + (i >> 7) * TC_A_BYTES;
+        *reinterpret_cast<uint4*>(dst + tc_row_off(i & 127, 0)) = *reinterpret_cast<const uint4*>(&v[0]);
+        *reinterpret_cast<uint4*>(dst + tc_row_off(i & 127, 1)) = *reinterpret_cast<const uint4*>(&v[8]);
+        thr_s[i] = thr;
+        eps_s[i] = eps;
+      }
+      // the tensor core reads shared memory through the async proxy
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == TC_EPI_WARPS) {
+      // ===== TMA producer ==========================================================================
+      if (lane == 0) {
+        for (int64_t i = 0; i < nt; ++i) {
+          const uint32_t n = unit_n + (uint32_t)i;
+          const int s = (int)(n % TC_STAGES);
+          mbar_wait(&empty[s], ((n / TC_STAGES) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&full[s], TC_TILE_BYTES);
+          tma_load_1d(sB + s * TC_TILE_BYTES, p.tiles16 + (t0 + i) * (int64_t)TC_TILE_BYTES, TC_TILE_BYTES,
+                      &full[s]);
+        }
+      }
+      __syncwarp();
+    } else if (warp > TC_EPI_WARPS) {
+      // ===== MMA issuer of pipeline `pipe`: rows [pipe*128, +128) of every map tile ==================
+      // The loop is warp-uniform (all lanes track the same counters); one lane issues.  A single
+      // thread needs ~100 cycles of instruction latency per MMA + commit + barrier wait, which is
+      // why each pipeline has its own issuing warp (profiles/r02d_ncu_nn_tc.md).
+      const int pipe = warp - (TC_EPI_WARPS + 1);
+      const uint32_t a_desc0 = (uint32_t)((smem_u32(sA) >> 4) & 0x3FFF);
+      uint32_t n_acc = acc_n;
+      for (int64_t i = 0; i < nt; ++i) {
+        const uint32_t n = unit_n + (uint32_t)i;
+        const int s = (int)(n % TC_STAGES);
+        mbar_wait(&full[s], (n / TC_STAGES) & 1u);
+        tc_fence_after();
+        const uint64_t bdesc = tc_desc(smem_u32(sB + s * TC_TILE_BYTES) + pipe * (TC_SUB * TC_ROW_BYTES));
+        for (int a = 0; a < qt; ++a) {
+          const int buf = pipe + TC_PIPES * (int)(n_acc & 1u);
+          mbar_wait(&tempty[buf], ((n_acc >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          if (lane == 0) {
+            tc_mma_f16((uint32_t)buf * TC_SUB, tc_desc_hi() | (uint64_t)(a_desc0 + a * (TC_A_BYTES >> 4)), bdesc,
+                       TC_IDESC);
+            tc_commit(&tfull[buf]);
+          }
+          __syncwarp();
+          ++n_acc;
+        }
+        if (lane == 0) tc_commit(&empty[s]);  // the stage is free once every MMA above has read it
+        __syncwarp();
+      }
+    } else {
+      // ===== epilogue of pipeline `pipe` (8 warps): drains buffers pipe and pipe+2 in turn, one being
+      // refilled by the tensor core while the other is read; thread = TMEM lane = query, and the two
+      // warps of a lane quadrant split the 128 columns ============================================
+      const int pipe = warp / TC_PIPE_WARPS, w8 = warp % TC_PIPE_WARPS;
+      const int quad = w8 & 3, half = w8 >> 2;
+      const uint32_t tlane = ((uint32_t)(quad * 32) << 16) + (uint32_t)half * 64;
+      uint32_t n_acc = acc_n;
+      for (int64_t unit = 0; unit < nt; ++unit) {
+        for (int a = 0; a < qt; ++a, ++n_acc) {
+          const int buf = pipe + TC_PIPES * (int)(n_acc & 1u);
+          mbar_wait(&tfull[buf], (n_acc >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t taddr = tlane + (uint32_t)buf * TC_SUB;
+          uint32_t r0[32], r1[32];
+          tc_ld32(taddr, r0);
+          tc_ld32(taddr + 32, r1);
+          tc_wait_ld();
+          // the buffer may be overwritten as soon as all eight warps have read it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[buf]);
+          float m4[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+          tc_fold(m4, r0);
+          tc_fold(m4, r1);
+          const float mn = fminf(tc_min3(m4[0], m4[1], m4[2]), m4[3]);
+
+          const int ql = a * 128 + quad * 32 + lane;
+          // `<=`: a query whose threshold is +inf (norm too large for f16) is always re-scanned
+          unsigned pending = __ballot_sync(0xffffffffu, mn <= thr_s[ql]);
+          while (pending) {
+            const int src = __ffs(pending) - 1;
+            pending &= pending - 1;
+            const int qs = a * 128 + quad * 32 + src;
+            const int64_t qi = qbase + qs;
+            const int64_t row0 = (t0 + unit) * TC_BN + pipe * TC_SUB + half * 64;
+            const float found = tc_rescan_warp(p.packed, row0, p.n_rows,
+                                               p.queries + qi * (int64_t)p.query_stride + p.skip, p.bound,
+                                               mm_max, p.keys + qi);
+            if (lane == 0) {
+              // later rows only matter if they can reach d2 <= found.  Four warps share a query's
+              // threshold; a lost update only leaves it higher than necessary (more re-scans).
+              const float nt_thr = found + eps_s[qs];
+              if (nt_thr < thr_s[qs]) thr_s[qs] = nt_thr;
+              atomicAdd(p.stats, 1ull);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+    unit_n += (uint32_t)nt;
+    acc_n += (uint32_t)(nt * qt);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_EPI_WARPS + 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace vo
+
+using namespace vo;
+
+// ---- host side (called from nn.cu) ----------------------------------------------------------------
+int nn_tc_pack(vo_nn_s* h) {
+  h->n_tiles16 = (h->n_rows + TC_BN - 1) / TC_BN;
+  const int64_t rows_tc = h->n_tiles16 * TC_BN;
+  int rc = h->tiles16.reserve((size_t)h->n_tiles16 * TC_TILE_BYTES);
+  if (rc) return rc;
+  rc = h->tc_stats.reserve(64);
+  if (rc) return rc;
+  const int threads = 256;
+  nn_tc_pack_kernel<<<(unsigned)((rows_tc + threads - 1) / threads), threads, 0, h->stream>>>(
+      h->packed.as<float4>(), h->n_rows, rows_tc, h->tiles16.as<unsigned char>());
+  VO_LAUNCH_CHECK();
+  return VO_OK;
+}
+
+// query tiles per group: as many as fit (fewer passes over the map), trimmed so that the last group
+// is not mostly padding (a sharded batch of 12 500 queries = 98 tiles runs as 7 groups of 14)
+static int tc_pick_qt(int64_t n_qtiles) {
+  const int64_t groups = (n_qtiles + TC_QT_MAX - 1) / TC_QT_MAX;
+  return (int)((n_qtiles + groups - 1) / groups);
+}
+
+int nn_tc_launch(vo_nn_s* h, const float* queries_dev, int64_t nq, int qstride, float bound) {
+  NNTCParams p;
+  p.tiles16 = h->tiles16.as<unsigned char>();
+  p.packed = h->packed.as<float4>();
+  p.n_rows = h->n_rows;
+  p.n_rows_packed = h->n_tiles * NN_TM;
+  p.n_tiles16 = h->n_tiles16;
+  p.queries = queries_dev;
+  p.n_queries = nq;
+  p.query_stride = qstride;
+  p.skip = h->skip;
+  p.bound = bound;
+  p.mm_max = h->scalars.as<float>();
+  p.keys = h->keys.as<unsigned long long>();
+  const int64_t n_qtiles = (nq + 127) / 128;
+  p.qt = tc_pick_qt(n_qtiles);
+  p.n_groups = (int)((n_qtiles + p.qt - 1) / p.qt);
+  p.stats = h->tc_stats.as<unsigned long long>();
+  if (!h->tc_opted_in) {
+    VO_CUDA(cudaFuncSetAttribute(nn_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)TC_SMEM_BYTES));
+    h->tc_opted_in = true;
+  }
+  VO_CUDA(cudaMemsetAsync(h->tc_stats.p, 0, 64, h->stream));
+  const int sms = num_sms(h->device);
+  const int64_t units = (int64_t)p.n_groups * p.n_tiles16;
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(sms, units));
+  nn_tc_filter_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(p);
+  VO_LAUNCH_CHECK();
+  // (queries per thread = 0 marks the tensor-core filter, threads, query groups, CTAs)
+  h->last_launches.insert(h->last_launches.end(), {0, TC_THREADS, (int32_t)p.n_groups, (int32_t)grid});
+  return VO_OK;
+}

@@ -23,6 +23,8 @@
 #include <string.h>
 
 
+#include <algorithm>
+
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -763,6 +765,17 @@ picp_stream_kernel(const PicpParams p, const int rounds) {
   }
 }
 
+// lowest position of a pair whose indices fall outside the two point sets (all ones = none)
+__global__ void __launch_bounds__(256)
+picp_check_pairs_kernel(const int2* __restrict__ pairs, int64_t n, int n_image, int n_world,
+                        unsigned long long* __restrict__ bad) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int2 p = __ldg(pairs + i);
+    if ((unsigned)p.x >= (unsigned)n_image || (unsigned)p.y >= (unsigned)n_world)
+      atomicMin(bad, (unsigned long long)i);
+  }
+}
+
 }  // namespace vo
 
 // =================================================================================================
@@ -781,7 +794,7 @@ struct vo_picp_s {
   bool force_stream = false;          // VO_PICP_FORCE_STREAM=1: never use the resident kernel
   bool force_general = false;         // VO_PICP_FORCE_GENERAL=1: never use the pinhole kernel
   int32_t min_inliers = 0;
-  DevBuf world_buf, image_buf, pairs_buf, state_buf, partials_buf;
+  DevBuf world_buf, image_buf, pairs_buf, state_buf, partials_buf, check_buf;
   const float* world = nullptr;
   const float* image = nullptr;
   const int32_t* pairs = nullptr;
@@ -875,6 +888,7 @@ int vo_picp_destroy(vo_picp_t h) {
   h->pairs_buf.release();
   h->state_buf.release();
   h->partials_buf.release();
+  h->check_buf.release();
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return VO_OK;
@@ -927,20 +941,13 @@ int vo_picp_init(vo_picp_t h, const vo_camera* cam, const float* world_host, int
   if (rc) return rc;
   rc = h->image_buf.reserve((size_t)n_image * 8 + 16);
   if (rc) return rc;
-  if (n_world)
-    VO_CUDA(cudaMemcpyAsync(h->world_buf.p, world_host, (size_t)n_world * 12,
-                            cudaMemcpyHostToDevice, h->stream));
-  if (n_image)
-    VO_CUDA(cudaMemcpyAsync(h->image_buf.p, image_host, (size_t)n_image * 8,
-                            cudaMemcpyHostToDevice, h->stream));
+  // through the pinned staging ring; the caller's vectors are free again when this returns (the
+  // reference borrows them, picp_solver.cpp:21-22 — we own a copy)
+  if ((rc = stage_h2d(h->device, h->world_buf.p, world_host, (size_t)n_world * 12, h->stream))) return rc;
+  if ((rc = stage_h2d(h->device, h->image_buf.p, image_host, (size_t)n_image * 8, h->stream))) return rc;
   h->world = h->world_buf.as<float>();
   h->image = h->image_buf.as<float>();
-  rc = picp_init_common(h, cam, n_world, n_image);
-  if (rc) return rc;
-  // the reference borrows the vectors; we own a copy, so the caller may reuse them right away
-  if ((n_world && host_source_still_in_use(world_host)) || (n_image && host_source_still_in_use(image_host)))
-    VO_CUDA(cudaStreamSynchronize(h->stream));
-  return VO_OK;
+  return picp_init_common(h, cam, n_world, n_image);
 }
 
 int vo_picp_init_device(vo_picp_t h, const vo_camera* cam, const float* world_dev, int64_t n_world,
@@ -961,21 +968,43 @@ int vo_picp_set_correspondences(vo_picp_t h, const int32_t* pairs_host, int64_t 
   VO_REQUIRE(n_pairs >= 0 && n_pairs < (1LL << 31) && (pairs_host || n_pairs == 0), VO_ERR_ARG,
              "bad pairs");
   DeviceGuard g(h->device);
-  // bounds check on the host: the reference indexes with operator[] (UB when out of range);
-  // we refuse instead of reading out of bounds on the device.
-  for (int64_t i = 0; i < n_pairs; ++i) {
-    const int32_t a = pairs_host[2 * i], b = pairs_host[2 * i + 1];
-    if (a < 0 || a >= h->n_image || b < 0 || b >= h->n_world) {
-      set_error("vo_picp_set_correspondences: pair %lld = (%d,%d) out of range", (long long)i, a, b);
+  int rc = h->pairs_buf.reserve((size_t)n_pairs * 8 + 16);
+  if (rc) return rc;
+  h->n_pairs = 0;
+  // The reference indexes with operator[] (UB when out of range, picp_solver.cpp:66-71); we refuse
+  // instead of reading out of bounds on the device.  Frame-sized lists are checked on the host
+  // before the upload; large ones by a kernel over the uploaded copy (an O(n) host loop cost as
+  // much as the whole transfer).
+  constexpr int64_t HOST_CHECK_MAX = 1 << 16;
+  if (n_pairs <= HOST_CHECK_MAX) {
+    for (int64_t i = 0; i < n_pairs; ++i) {
+      const int32_t a = pairs_host[2 * i], b = pairs_host[2 * i + 1];
+      if (a < 0 || a >= h->n_image || b < 0 || b >= h->n_world) {
+        set_error("vo_picp_set_correspondences: pair %lld = (%d,%d) out of range", (long long)i, a, b);
+        return VO_ERR_ARG;
+      }
+    }
+  }
+  if ((rc = stage_h2d(h->device, h->pairs_buf.p, pairs_host, (size_t)n_pairs * 8, h->stream))) return rc;
+  if (n_pairs > HOST_CHECK_MAX) {
+    rc = h->check_buf.reserve(16);
+    if (rc) return rc;
+    VO_CUDA(cudaMemsetAsync(h->check_buf.p, 0xFF, 8, h->stream));
+    const int threads = 256;
+    const int blocks = (int)std::min<int64_t>((n_pairs + threads - 1) / threads, 8LL * num_sms(h->device));
+    picp_check_pairs_kernel<<<blocks, threads, 0, h->stream>>>(
+        h->pairs_buf.as<int2>(), n_pairs, (int)std::min<int64_t>(h->n_image, INT32_MAX),
+        (int)std::min<int64_t>(h->n_world, INT32_MAX), h->check_buf.as<unsigned long long>());
+    VO_LAUNCH_CHECK();
+    long long bad = -1;
+    VO_CUDA(cudaMemcpyAsync(&bad, h->check_buf.p, sizeof(bad), cudaMemcpyDeviceToHost, h->stream));
+    VO_CUDA(cudaStreamSynchronize(h->stream));
+    if (bad != -1) {
+      set_error("vo_picp_set_correspondences: pair %lld = (%d,%d) out of range", bad, pairs_host[2 * bad],
+                pairs_host[2 * bad + 1]);
       return VO_ERR_ARG;
     }
   }
-  int rc = h->pairs_buf.reserve((size_t)n_pairs * 8 + 16);
-  if (rc) return rc;
-  if (n_pairs)
-    VO_CUDA(cudaMemcpyAsync(h->pairs_buf.p, pairs_host, (size_t)n_pairs * 8,
-                            cudaMemcpyHostToDevice, h->stream));
-  if (n_pairs && host_source_still_in_use(pairs_host)) VO_CUDA(cudaStreamSynchronize(h->stream));
   h->pairs = h->pairs_buf.as<int32_t>();
   h->n_pairs = n_pairs;
   return VO_OK;

@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "common.cuh"
@@ -43,6 +44,12 @@ struct TriParams {
   long long* n_success;            // device int64
   ScanWorkspace ws;
   int num_tiles;
+  // bounds of the two point sets (INT_MAX when the caller vouches for the indices) and where an
+  // out-of-range pair is reported: *bad = lowest offending position (all ones = none).  The reference's
+  // PointCloud overload throws through .at() (utils.cpp:119-127); here the item is dropped and the
+  // host-pointer entry point turns the report into VO_ERR_ARG.
+  int n_p1, n_p2;
+  unsigned long long* bad;
 };
 
 // triangulate_point (utils.cpp:36-49) for TWO correspondences at once: the two lanes of sm_100a's
@@ -192,6 +199,11 @@ __global__ void __launch_bounds__(THREADS) triangulate_kernel(const TriParams q)
       const int64_t i = warp_base + j * 32 + lane;
       in[j] = i < n_corr;
       c[j] = __ldg(q.corr + (in[j] ? i : n_corr - 1));
+      if ((unsigned)c[j].x >= (unsigned)q.n_p1 || (unsigned)c[j].y >= (unsigned)q.n_p2) {
+        if (in[j] && q.bad) atomicMin(q.bad, (unsigned long long)i);
+        in[j] = false;
+        c[j] = make_int2(0, 0);
+      }
     }
     float2 a[ITEMS], b[ITEMS];
 #pragma unroll
@@ -385,7 +397,8 @@ static void tri_precompute(const float K[9], const float X[16], TriParams* q) {
 static int tri_launch(cudaStream_t stream, const float K[9], const float X[16], const int32_t* corr,
                       int64_t n, const float* p1, const float* p2, const float* app2, float* out_pts,
                       int32_t* out_corr_new, float* out_app, int32_t* out_src, int64_t* n_success,
-                      void* workspace, const int32_t* n_corr_dev = nullptr) {
+                      void* workspace, const int32_t* n_corr_dev = nullptr, int64_t n_p1 = INT32_MAX,
+                      int64_t n_p2 = INT32_MAX, unsigned long long* bad = nullptr) {
   const int tile_items = TRI_TILE;
   const int64_t tiles = (n + tile_items - 1) / tile_items;
   VO_REQUIRE(tiles < (1LL << 31), VO_ERR_UNSUPPORTED, "too many correspondences");
@@ -409,6 +422,9 @@ static int tri_launch(cudaStream_t stream, const float K[9], const float X[16], 
   q.n_success = reinterpret_cast<long long*>(n_success);
   q.ws = scan_workspace_at(workspace, tiles);
   q.num_tiles = (int)tiles;
+  q.n_p1 = (int)std::min<int64_t>(n_p1, INT32_MAX);
+  q.n_p2 = (int)std::min<int64_t>(n_p2, INT32_MAX);
+  q.bad = bad;
   // persistent blocks: as many as can be resident, each loops over dynamically claimed tiles
   static int resident = 0;
   if (resident == 0) {
@@ -486,15 +502,6 @@ int vo_triangulate(int device, const float K[9], const float X[16], const int32_
   *n_success = 0;
   if (n_corr == 0) return VO_OK;
   VO_REQUIRE(corr_host && p1_host && p2_host && out_points_host, VO_ERR_ARG, "null pointer");
-  // the PointCloud overload indexes with .at() (utils.cpp:119-127): out-of-range is an error,
-  // never a device fault
-  for (int64_t i = 0; i < n_corr; ++i) {
-    const int32_t a = corr_host[2 * i], b = corr_host[2 * i + 1];
-    if (a < 0 || a >= n_p1 || b < 0 || b >= n_p2) {
-      set_error("vo_triangulate: correspondence %lld = (%d,%d) out of range", (long long)i, a, b);
-      return VO_ERR_ARG;
-    }
-  }
   int ndev = 0;
   VO_CUDA(cudaGetDeviceCount(&ndev));
   VO_REQUIRE(device >= 0 && device < ndev && device < 64, VO_ERR_ARG, "bad device ordinal");
@@ -515,31 +522,37 @@ int vo_triangulate(int device, const float K[9], const float X[16], const int32_
   if (out_src_host && (rc = cx->out_d.reserve((size_t)n_corr * 4))) return rc;
   if ((rc = cx->ws.reserve((size_t)vo_triangulate_workspace_bytes(n_corr)))) return rc;
   if ((rc = cx->cnt.reserve(64))) return rc;
-  VO_CUDA(cudaMemcpyAsync(cx->in_a.p, corr_host, (size_t)n_corr * 8, cudaMemcpyHostToDevice, s));
-  VO_CUDA(cudaMemcpyAsync(cx->in_b.p, p1_host, (size_t)n_p1 * 8, cudaMemcpyHostToDevice, s));
-  VO_CUDA(cudaMemcpyAsync(cx->in_c.p, p2_host, (size_t)n_p2 * 8, cudaMemcpyHostToDevice, s));
-  if (with_app)
-    VO_CUDA(cudaMemcpyAsync(cx->in_d.p, app2_host, (size_t)n_p2 * 40, cudaMemcpyHostToDevice, s));
+  // inputs through the pinned staging ring (the host copy of chunk k+1 overlaps the DMA of chunk k)
+  if ((rc = stage_h2d(device, cx->in_a.p, corr_host, (size_t)n_corr * 8, s))) return rc;
+  if ((rc = stage_h2d(device, cx->in_b.p, p1_host, (size_t)n_p1 * 8, s))) return rc;
+  if ((rc = stage_h2d(device, cx->in_c.p, p2_host, (size_t)n_p2 * 8, s))) return rc;
+  if (with_app && (rc = stage_h2d(device, cx->in_d.p, app2_host, (size_t)n_p2 * 40, s))) return rc;
+  // cnt[0] = number of successes, cnt[1] = lowest out-of-range position (all ones = none): the
+  // PointCloud overload indexes with .at() (utils.cpp:119-127), so out of range is an error, never
+  // a device fault — checked by the kernel itself instead of an O(n) host loop
+  VO_CUDA(cudaMemsetAsync(cx->cnt.p, 0xFF, 16, s));
   rc = tri_launch(s, K, X, cx->in_a.as<int32_t>(), n_corr, cx->in_b.as<float>(),
                   cx->in_c.as<float>(), with_app ? cx->in_d.as<float>() : nullptr,
                   cx->out_a.as<float>(), out_corr_new_host ? cx->out_b.as<int32_t>() : nullptr,
                   with_app ? cx->out_c.as<float>() : nullptr,
                   out_src_host ? cx->out_d.as<int32_t>() : nullptr, cx->cnt.as<int64_t>(),
-                  cx->ws.p);
+                  cx->ws.p, nullptr, n_p1, n_p2, cx->cnt.as<unsigned long long>() + 1);
   if (rc) return rc;
-  int64_t ns = 0;
-  VO_CUDA(cudaMemcpyAsync(&ns, cx->cnt.p, sizeof(ns), cudaMemcpyDeviceToHost, s));
+  long long res[2] = {0, 0};
+  VO_CUDA(cudaMemcpyAsync(res, cx->cnt.p, sizeof(res), cudaMemcpyDeviceToHost, s));
   VO_CUDA(cudaStreamSynchronize(s));
+  if (res[1] != -1) {
+    const long long i = res[1];
+    set_error("vo_triangulate: correspondence %lld = (%d,%d) out of range", i, corr_host[2 * i],
+              corr_host[2 * i + 1]);
+    return VO_ERR_ARG;
+  }
+  const int64_t ns = res[0];
   if (ns > 0) {
-    VO_CUDA(cudaMemcpyAsync(out_points_host, cx->out_a.p, (size_t)ns * 12, cudaMemcpyDeviceToHost, s));
-    if (out_corr_new_host)
-      VO_CUDA(cudaMemcpyAsync(out_corr_new_host, cx->out_b.p, (size_t)ns * 8,
-                              cudaMemcpyDeviceToHost, s));
-    if (with_app)
-      VO_CUDA(cudaMemcpyAsync(out_app_host, cx->out_c.p, (size_t)ns * 40, cudaMemcpyDeviceToHost, s));
-    if (out_src_host)
-      VO_CUDA(cudaMemcpyAsync(out_src_host, cx->out_d.p, (size_t)ns * 4, cudaMemcpyDeviceToHost, s));
-    VO_CUDA(cudaStreamSynchronize(s));
+    if ((rc = stage_d2h(device, out_points_host, cx->out_a.p, (size_t)ns * 12, s))) return rc;
+    if (out_corr_new_host && (rc = stage_d2h(device, out_corr_new_host, cx->out_b.p, (size_t)ns * 8, s))) return rc;
+    if (with_app && (rc = stage_d2h(device, out_app_host, cx->out_c.p, (size_t)ns * 40, s))) return rc;
+    if (out_src_host && (rc = stage_d2h(device, out_src_host, cx->out_d.p, (size_t)ns * 4, s))) return rc;
   }
   *n_success = ns;
   return VO_OK;
@@ -568,7 +581,7 @@ int vo_project_points(int device, const vo_camera* cam, const float* world_host,
   if ((rc = cx->out_a.reserve((size_t)n_points * 12))) return rc;
   if ((rc = cx->ws.reserve((size_t)scan_workspace_bytes(tiles)))) return rc;
   if ((rc = cx->cnt.reserve(64))) return rc;
-  VO_CUDA(cudaMemcpyAsync(cx->in_a.p, world_host, (size_t)n_points * 12, cudaMemcpyHostToDevice, s));
+  if ((rc = stage_h2d(device, cx->in_a.p, world_host, (size_t)n_points * 12, s))) return rc;
   VO_CUDA(cudaMemsetAsync(cx->ws.p, 0, (size_t)scan_workspace_bytes(tiles), s));
   ProjParams q;
   for (int j = 0; j < 4; ++j)
@@ -590,11 +603,8 @@ int vo_project_points(int device, const vo_camera* cam, const float* world_host,
   long long counts[2] = {0, 0};
   VO_CUDA(cudaMemcpyAsync(counts, cx->cnt.p, sizeof(counts), cudaMemcpyDeviceToHost, s));
   VO_CUDA(cudaStreamSynchronize(s));
-  if (counts[0] > 0) {
-    VO_CUDA(cudaMemcpyAsync(out_image_host, cx->out_a.p, (size_t)counts[0] * 8,
-                            cudaMemcpyDeviceToHost, s));
-    VO_CUDA(cudaStreamSynchronize(s));
-  }
+  if (counts[0] > 0 && (rc = stage_d2h(device, out_image_host, cx->out_a.p, (size_t)counts[0] * 8, s)))
+    return rc;
   *n_out = counts[0];
   *n_inside = counts[1];
   return VO_OK;

@@ -31,6 +31,11 @@
 #include "camera.h"
 #include "picp_solver.h"
 #include "epipolar_utils.h"
+#if defined(__has_include)
+#if __has_include("vo_b200_host.h")
+#include "vo_b200_host.h"  // drop-in build only: defines VO_B200_DROPIN
+#endif
+#endif
 
 namespace {
 using Clock = std::chrono::steady_clock;

@@ -24,4 +24,6 @@ $CXX $FLAGS "$REF/src/tests/picp_solver_test.cpp" $OBJS $LINK -o "$HERE/bin/picp
 $CXX $FLAGS "$REF/src/tests/essential_picp_test.cpp" $OBJS $LINK -o "$HERE/bin/whole_test"
 # the synthetic-sequence driver (config 5): our own source, the same file the CPU reference build uses
 $CXX $FLAGS "$HERE/apps/vo_sequence.cpp" $OBJS $LINK -o "$HERE/bin/vo_sequence"
+# the seeded whole_test driver (config 2), same arrangement
+$CXX $FLAGS "$HERE/apps/whole_synthetic.cpp" $OBJS $LINK -o "$HERE/bin/whole_synthetic"
 echo "built $HERE/bin/{vo_complete,picp_test,whole_test,vo_sequence} against libvo_b200.so"

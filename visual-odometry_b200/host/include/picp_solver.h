@@ -59,4 +59,9 @@ class PICPSolver {
   mutable bool _dirty;            // rounds were queued since the last refresh
   mutable float _chi_inliers, _chi_outliers;
   mutable int _num_inliers;
+  // host mirrors of the last linearisation (damping included), refreshed with the accessors above;
+  // protected members of the same names exist in the reference (picp_solver.h:70-71) and its
+  // subclasses read them
+  mutable Matrix6f _H;
+  mutable Vector6f _b;
 };

@@ -17,6 +17,8 @@ PICPSolver::PICPSolver()
       _chi_inliers(0.f),
       _chi_outliers(0.f),
       _num_inliers(0) {
+  _H.setZero();
+  _b.setZero();
   check(vo_picp_create(&_handle, vo_b200::device()), "vo_picp_create");
 }
 
@@ -90,6 +92,9 @@ void PICPSolver::refresh() const {
   _chi_inliers = st.chi_inliers;
   _chi_outliers = st.chi_outliers;
   _num_inliers = st.num_inliers;
+  for (int j = 0; j < 6; ++j)
+    for (int i = 0; i < 6; ++i) _H(i, j) = st.H[j * 6 + i];
+  for (int i = 0; i < 6; ++i) _b(i) = st.b[i];
   _dirty = false;
 }
 
