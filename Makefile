@@ -19,6 +19,10 @@ $(LIB): $(OBJS)
 # triangulate.cu mirrors the oracle's operation order exactly, so it is compiled without FMA
 # contraction (-fmad=false): its results are then bit-identical to the CPU restatement.
 build/triangulate.o: EXTRA := -fmad=false
+# make TC_PROFILE=1: cycle counters inside nn_tc_filter_kernel (see nn_tc.cu)
+ifdef TC_PROFILE
+build/nn_tc.o: EXTRA := -DNN_TC_PROFILE
+endif
 
 build/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p build

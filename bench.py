@@ -8,11 +8,17 @@ Primary line (BASELINE.json config 4, the only config that shards across GPUs):
   e2e     the same through the host-pointer C-ABI call (vo_nn_best_match): queries cross PCIe
           host->device and indices device->host inside the timed region; the map is resident
           (it is the database, uploaded once like the reference builds its kd-tree once per map).
-  roofline  FP32 CUDA-core bound: 30 algorithmic flop per (query,row) pair.
-  cpu_baseline  the oracle port of bruteForceBestMatch on the host cores, on a query sample.
-Extra objects on the same line: "picp" (config 3 at 1e7 correspondences, HBM-bound) and
-"triangulate" (1e7 correspondences, HBM-bound), each with its own roofline and CPU sample (N=1
-only), and "vo" (config 5: one synthetic 1000-frame x 1e5-landmark sequence per GPU, frames/s).
+  roofline  the tensor-core filter (csrc/nn_tc.cu): executed tensor flop (2 x 16 per pair) against
+            the measured dense bf16/f16 peak, with the algorithmic 30 flop per pair and
+            the TMEM-read fraction (the kernel's real limiter) beside it.
+  cpu_baseline  the REFERENCE's own bruteForceBestMatch (oracle/_ref, built from its sources) on
+            all host cores, on a query sample against the full map.
+Extra objects on the same line (N=1 only): "nn_ffma" (the FP32 FFMA2 filter on the same config,
+fraction of FP32 peak), "nn_sweep" (M = 1e6, 1e7), "nn_clustered" (1e3 Gaussian clusters: data on
+which a partial-distance filter prunes nothing), "picp" (config 3 at 1e7 correspondences, HBM-bound),
+"triangulate" (1e7 correspondences, HBM-bound), "whole" (config 2: 3 views x 1e4 points, GPU vs the
+CPU reference per correspondence id), and "vo" (config 5: one synthetic 1000-frame x 1e5-landmark
+sequence per GPU, frames/s; every N).  Floats are rounded to 6 significant digits to keep the line short.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
   torchrun --nproc-per-node N bench.py --gpus N ...      (queries sharded, map replicated)
@@ -38,6 +44,28 @@ PICP_BYTES_PER_CORR = 28.0  # 8 pair + 12 world + 8 image
 TRI_BYTES_PER_CORR = 44.0   # 8 pair + 8 + 8 in, 12 + 8 out
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 RADIUS = 0.1
+NN_TC_FLOP_PER_PAIR = 32.0  # what the tensor-core filter executes: K = 16 (10 + norm terms, padded) x 2
+TMEM_READ_B_PER_CLK_SM = 410.0  # measured tcgen05.ld ceiling with 16 warps (profiles/r02a_tc_probe.md)
+
+
+def nn_workload(Q, M):
+    """identical in both arms (the driver compares config strings)"""
+    return f"appearance NN: {Q} queries x {M}-row 10-D map, radius {RADIUS}, queries sharded, map replicated"
+
+
+def compact(x):
+    """round every float to 6 significant digits (the driver keeps only the tail of a long line)"""
+    if isinstance(x, float):
+        return float(f"{x:.6g}") if np.isfinite(x) else None
+    if isinstance(x, dict):
+        return {k: compact(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [compact(v) for v in x]
+    if isinstance(x, (np.floating,)):
+        return compact(float(x))
+    if isinstance(x, (np.integer,)):
+        return int(x)
+    return x
 
 
 def host_cores():
@@ -235,8 +263,7 @@ def reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"appearance NN: {Q} queries x {M}-row 10-D map, radius {RADIUS}",
-                   "map_rows": M, "queries": Q},
+        "config": {"workload": nn_workload(Q, M), "map_rows": M, "queries": Q},
         "cpu_baseline": {"value": val, "unit": "queries/s", "cores": cores, "kind": cpu_kind(),
                          "sample": f"{per_step} queries x full {M}-row map per step, "
                                    f"{cores} threads over queries"},
@@ -244,7 +271,7 @@ def reference_arm(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(compact(line)), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -320,21 +347,48 @@ def bench_picp(torch, vo, synth, args, cores):
     for _ in range(max(1, args.steps)):
         step_e2e()
     e2e_s = (time.perf_counter() - t0) / max(1, args.steps)
-    # parity on the same inputs: float64 truth for the first round on a bounded subset
+    # parity on the same inputs: float64 truth for the first round on a bounded subset; CPU baseline
+    # = the reference's own PICPSolver::oneRound (oracle/_ref) when it travelled, else the C port
+    import ref_lib
+
     sub = pr["pairs"][: min(n_corr, 1_000_000)]
     ocam = oracle.make_camera(pr["rows"], pr["cols"], pr["z_near"], pr["z_far"], pr["K"], np.eye(4))
     o = oracle.PicpOracle(ocam, pr["world"], pr["image"], thr=10000.0)
-    t0 = time.perf_counter()
-    o.one_round(sub, False)
-    cpu_dt = time.perf_counter() - t0
+    if ref_lib.available():
+        rp = ref_lib.Picp(pr["rows"], pr["cols"], pr["z_near"], pr["z_far"], pr["K"], np.eye(4),
+                          pr["world"], pr["image"], 10000.0)
+        t0 = time.perf_counter()
+        rp.one_round(sub, False)
+        cpu_dt, cpu_kind_ = time.perf_counter() - t0, "reference"
+        o.one_round(sub, False)
+    else:
+        t0 = time.perf_counter()
+        o.one_round(sub, False)
+        cpu_dt, cpu_kind_ = time.perf_counter() - t0, "port"
     o.one_round_f64(sub, False)
     s3 = vo.PICPSolver(0)
     s3.setKernelThreshold(10000.0)
     s3.init(cam, pr["world"], pr["image"])
     s3.oneRound(sub, False)
     H = s3.H().astype(np.float64)
-    err_gpu = float(np.max(np.abs(H - o.H64m())) / np.max(np.abs(o.H64m())))
-    err_cpu = float(np.max(np.abs(o.H().astype(np.float64) - o.H64m())) / np.max(np.abs(o.H64m())))
+    H64 = o.H64m()
+
+    def blocks(a, b):
+        return max(float(np.max(np.abs(a[i:i + 3, j:j + 3] - b[i:i + 3, j:j + 3])) /
+                         np.max(np.abs(b[i:i + 3, j:j + 3]))) for i in (0, 3) for j in (0, 3))
+
+    err_gpu = blocks(H, H64)
+    err_cpu = blocks(o.H().astype(np.float64), H64)
+    # final pose of the 10-round solve against the float64 solver on the same bounded subset
+    s3.init(cam, pr["world"], pr["image"])
+    s3.set_correspondences(sub)
+    s3.compute(False, rounds)
+    o2 = oracle.PicpOracle(ocam, pr["world"], pr["image"], thr=10000.0)
+    for _ in range(rounds):
+        o2.one_round_f64(sub, False)
+    Tg, T64 = s3.pose().astype(np.float64), o2.pose64()
+    pose_rel = max(float(np.max(np.abs(Tg[:3, :3] - T64[:3, :3]))),
+                   float(np.max(np.abs(Tg[:3, 3] - T64[:3, 3])) / max(np.max(np.abs(T64[:3, 3])), 1e-30)))
     for x in (s, s2, s3):
         x.close()
     peaks = measured_peaks()
@@ -379,9 +433,11 @@ def bench_picp(torch, vo, synth, args, cores):
                      "algorithmic_bytes_per_launch": PICP_BYTES_PER_CORR * n_corr * rounds,
                      "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         "cpu_baseline": {"value": len(sub) / cpu_dt, "unit": "point-iters/s", "cores": 1,
-                         "kind": "port", "sample": f"1 round over {len(sub)} correspondences"},
-        "parity": {"tolerance_rel": 1e-5, "H_gpu_vs_f64": err_gpu, "H_cpu_oracle_vs_f64": err_cpu,
-                   "pose_err_vs_gt": float(np.max(np.abs(pose - pr["T_gt"])))},
+                         "kind": cpu_kind_, "sample": f"1 round over {len(sub)} correspondences"},
+        "parity": {"tolerance_rel": 1e-5, "H_blocks_gpu_vs_f64": err_gpu,
+                   "H_blocks_cpu_float_vs_f64": err_cpu, "final_pose_rel_vs_f64_solver": pose_rel,
+                   "pose_err_vs_gt": float(np.max(np.abs(pose - pr["T_gt"]))),
+                   "rule": "per 3x3 block of H; pose per block (R, t); sample = first 1e6 correspondences"},
     }
 
 
@@ -417,17 +473,45 @@ def bench_triangulate(torch, vo, synth, args, cores):
 
     ms = timed_steps(torch, step, args.steps, args.warmup)
     ns = int(nsucc.item())
+    # end to end through the host-pointer ABI (what the drop-in triangulate_points calls): pageable
+    # host vectors in, pageable host vectors out.  The output arrays are allocated and touched once,
+    # as a caller that re-uses its std::vectors would have them.
+    h_pts = np.zeros((nc, 3), np.float32)
+    h_cn = np.zeros((nc, 2), np.int32)
+    nsh = C.c_int64(0)
+    p1h, p2h = np.ascontiguousarray(tv["p1"]), np.ascontiguousarray(tv["p2"])
+
+    def e2e_step():
+        rc = lib.vo_triangulate(0, K.ctypes.data_as(f32p), X.ctypes.data_as(f32p),
+                                corr_np.ctypes.data_as(C.c_void_p), nc, p1h.ctypes.data_as(C.c_void_p),
+                                len(p1h), p2h.ctypes.data_as(C.c_void_p), len(p2h), None,
+                                h_pts.ctypes.data_as(C.c_void_p), h_cn.ctypes.data_as(C.c_void_p), None,
+                                None, C.byref(nsh))
+        assert rc == 0, lib.vo_last_error()
+
+    e2e_step()
     t0 = time.perf_counter()
     for _ in range(max(1, args.steps)):
-        pts, cn = vo.triangulate_points(tv["K"], tv["X"], corr_np, tv["p1"], tv["p2"])
+        e2e_step()
     e2e_s = (time.perf_counter() - t0) / max(1, args.steps)
+    import ref_lib
+
     sub = corr_np[: min(nc, 1_000_000)]
-    t0 = time.perf_counter()
     opts, ocn, _, osrc = oracle.triangulate_points(tv["K"], tv["X"], sub, tv["p1"], tv["p2"])
-    cpu_dt = time.perf_counter() - t0
+    if ref_lib.available():
+        t0 = time.perf_counter()
+        rpts, rcn, _ = ref_lib.triangulate_points(tv["K"], tv["X"], sub, tv["p1"], tv["p2"])
+        cpu_dt, cpu_kind_ = time.perf_counter() - t0, "reference"
+    else:
+        t0 = time.perf_counter()
+        oracle.triangulate_points(tv["K"], tv["X"], sub, tv["p1"], tv["p2"])
+        cpu_dt, cpu_kind_ = time.perf_counter() - t0, "port"
     gp, gcn, gsrc = vo.triangulate_points(tv["K"], tv["X"], sub, tv["p1"], tv["p2"], want_src=True)
     same = np.array_equal(gsrc, osrc)
     perr = float(np.max(np.abs(gp - opts)) / max(1.0, np.abs(opts).max())) if same else None
+    if ref_lib.available() and same:
+        same = bool(np.array_equal(gcn, rcn))
+        perr = max(perr, float(np.max(np.abs(gp - rpts)) / max(1.0, np.abs(rpts).max())))
     peaks = measured_peaks()
     hbm = peaks.get("hbm_gbs", 6650.0)
     achieved = TRI_BYTES_PER_CORR * nc / (ms * 1e-3) / 1e9
@@ -437,13 +521,15 @@ def bench_triangulate(torch, vo, synth, args, cores):
         "config": {"workload": f"triangulate_points: {nc} correspondences, {ns} successes"},
         "e2e": {"value": nc / e2e_s, "unit": "correspondences/s",
                 "h2d_bytes_per_step": int(8 * nc + 16 * len(tv["p1"])),
-                "d2h_bytes_per_step": int(20 * ns + 8)},
+                "d2h_bytes_per_step": int(20 * ns + 16), "ms_per_step": e2e_s * 1e3,
+                "pcie_gbs_each_way": [(8 * nc + 16 * len(tv["p1"])) / e2e_s / 1e9, 20 * ns / e2e_s / 1e9],
+                "note": "pageable host memory both ways through the pinned staging ring"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                      "frac": achieved / hbm, **traffic_fields("tri", n == 10_000_000),
                      "algorithmic_bytes_per_launch": TRI_BYTES_PER_CORR * nc,
                      "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         "cpu_baseline": {"value": len(sub) / cpu_dt, "unit": "correspondences/s", "cores": 1,
-                         "kind": "port", "sample": f"{len(sub)} correspondences"},
+                         "kind": cpu_kind_, "sample": f"{len(sub)} correspondences"},
         "parity": {"tolerance_rel": 1e-5, "flags_equal": bool(same), "points_rel_err": perr},
     }
 

@@ -13,6 +13,36 @@ dev = torch.device("cuda:0")
 m = synth.nn_map_torch(M, dev)
 qn, target = synth.nn_queries_np(Q, M)
 q = torch.from_numpy(qn).to(dev)
+import threading
+class Sampler:
+    """SM clock, power and throttle reasons every 20 ms while a filter runs"""
+    def __init__(self):
+        import pynvml
+        pynvml.nvmlInit()
+        self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(0)
+        self.clk, self.pw, self.reasons = [], [], set()
+        self.stop = threading.Event()
+    def run(self):
+        nv = self.nv
+        while not self.stop.is_set():
+            self.clk.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.pw.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for name, bit in (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal", 0x20), ("hw_thermal", 0x40)):
+                if r & bit:
+                    self.reasons.add(name)
+            self.stop.wait(0.02)
+    def __enter__(self):
+        self.t = threading.Thread(target=self.run, daemon=True); self.t.start(); return self
+    def __exit__(self, *a):
+        self.stop.set(); self.t.join()
+    def summary(self):
+        return {"sm_mhz_median": float(np.median(self.clk)), "sm_mhz_min": int(min(self.clk)),
+                "power_w_median": float(np.median(self.pw)), "power_w_max": float(max(self.pw)),
+                "reasons": sorted(self.reasons), "samples": len(self.clk)}
 res = {}
 for path in paths:
     os.environ["VO_NN_FORCE_PATH"] = path
@@ -22,6 +52,8 @@ for path in paths:
     idx = torch.empty(Q, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
     ts = []
+    smp = Sampler()
+    smp.__enter__()
     for it in range(4):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -29,10 +61,11 @@ for path in paths:
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
+    smp.__exit__()
     got = idx.cpu().numpy()
     cls = np.arange(Q) % 4
     ok = bool(np.array_equal(got[cls < 3], target[cls < 3]) and np.all(got[cls == 3] == -1))
     res[path] = {"ms": ts, "planted_ok": ok, "launches": nn.last_launches(), "rescans": nn.last_rescans(),
-                 "queries_per_s": Q / (min(ts[1:]) * 1e-3)}
+                 "queries_per_s": Q / (min(ts[1:]) * 1e-3), "clocks": smp.summary()}
     print(json.dumps({path: res[path]}), flush=True)
     nn.close()

@@ -271,6 +271,111 @@ __global__ void __launch_bounds__(256) mma_rate_kernel(int n_mma, float* sink, l
   if (warp == 0) tmem_dealloc(tb, 512);
 }
 
+// ---- (4) dependent latency: issue one MMA, commit, wait for the barrier, repeat --------------------
+template <int N>
+__global__ void __launch_bounds__(128) mma_latency_kernel(int iters, long long* cycles, int* status) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 24576 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base;
+  if (tid == 0) {
+    const uint64_t ad = make_desc(smem_u32(smem), 128, 256), bd = make_desc(smem_u32(smem + 8192), 128, 256);
+    const uint32_t idesc = make_idesc(0, 128, N);
+    bool ok = true;
+    const long long t0 = clock64();
+    for (int i = 0; i < iters && ok; ++i) {
+      tc_mma_f16(tb, ad, bd, idesc, 0);
+      tc_commit(&bar);
+      ok = mbar_wait_bounded(&bar, (uint32_t)(i & 1), 100000000LL);
+      tc_fence_after();
+    }
+    const long long t1 = clock64();
+    cycles[blockIdx.x] = t1 - t0;
+    if (blockIdx.x == 0) *status = ok ? 1 : -1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
+// ---- (5) dependent latency of one tcgen05.ld.x32 + wait::ld, single warp ---------------------------
+__global__ void __launch_bounds__(32) ldtm_latency_kernel(int iters, float* sink, long long* cycles) {
+  __shared__ uint32_t tmem_base;
+  tmem_alloc(&tmem_base, 512);
+  tc_fence_before();
+  __syncwarp();
+  tc_fence_after();
+  const uint32_t tb = tmem_base;
+  float mn = INFINITY;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    uint32_t r[32];
+    tc_ld32(tb + ((it * 32) & 511), r);
+    tc_wait_ld();
+    mn = f_min3(mn, __uint_as_float(r[0]), __uint_as_float(r[31]));
+  }
+  const long long t1 = clock64();
+  if (mn == 123.456f) sink[0] = mn;
+  if (threadIdx.x == 0) cycles[0] = t1 - t0;
+  tc_fence_before();
+  __syncwarp();
+  tmem_dealloc(tb, 512);
+}
+
+// ---- (6) issue cost: back-to-back MMAs of width N, optionally one commit per MMA, from 1 or 2 warps ----
+template <int N>
+__global__ void __launch_bounds__(128) mma_issue_kernel(int n_mma, int commit_each, int n_issuers, long long* cycles,
+                                                        int* status) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar[4];
+  __shared__ uint64_t done_bar[2];
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 24576 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1 << 20);  // never completes: commits just arrive
+    mbar_init(&done_bar[0], 1);
+    mbar_init(&done_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base;
+  if (warp < n_issuers && lane == 0) {
+    const uint64_t ad = make_desc(smem_u32(smem), 128, 256), bd = make_desc(smem_u32(smem + 8192), 128, 256);
+    const uint32_t idesc = make_idesc(0, 128, N);
+    const long long t0 = clock64();
+    for (int i = 0; i < n_mma; ++i) {
+      tc_mma_f16(tb + (uint32_t)(((i & 1) * 2 + warp) * 128) % 512, ad, bd, idesc, 0);
+      if (commit_each) tc_commit(&bar[(i & 1) * 2 + warp]);
+    }
+    const long long t_issue = clock64() - t0;
+    tc_commit(&done_bar[warp]);
+    const bool ok = mbar_wait_bounded(&done_bar[warp], 0, 2000000000LL);
+    const long long t_all = clock64() - t0;
+    cycles[(blockIdx.x * 2 + warp) * 2] = t_issue;
+    cycles[(blockIdx.x * 2 + warp) * 2 + 1] = t_all;
+    if (blockIdx.x == 0 && warp == 0) *status = ok ? 1 : -1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
 int main() {
   int dev = 0, sms = 0, khz = 0;
   CK(cudaSetDevice(dev));
@@ -379,5 +484,53 @@ int main() {
            "\"cycles_per_128x256x16_tile\": %.1f}\n",
            variant >= 2 ? "tf32" : "f16", variant & 1, s, (double)mx / n);
   }
+  // (4) dependent MMA latency
+  for (int variant = 0; variant < 3; ++variant) {
+    const int iters = 2000;
+    CK(cudaMemset(st, 0, 4));
+    for (int rep = 0; rep < 2; ++rep) {
+      if (variant == 0) mma_latency_kernel<64><<<sms, 128, 24576>>>(iters, cyc, st);
+      else if (variant == 1) mma_latency_kernel<128><<<sms, 128, 24576>>>(iters, cyc, st);
+      else mma_latency_kernel<256><<<sms, 128, 24576>>>(iters, cyc, st);
+      CK(cudaDeviceSynchronize());
+    }
+    int sflag = 0;
+    CK(cudaMemcpy(&sflag, st, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h.data(), cyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+    long long mx = 0;
+    for (int i = 0; i < sms; ++i) mx = h[i] > mx ? h[i] : mx;
+    printf("{\"probe\": \"mma_dependent_latency\", \"N\": %d, \"status\": %d, \"cycles_issue_to_barrier\": %.1f}\n",
+           variant == 0 ? 64 : (variant == 1 ? 128 : 256), sflag, (double)mx / iters);
+  }
+  // (5) dependent tcgen05.ld latency
+  {
+    const int iters = 20000;
+    for (int rep = 0; rep < 2; ++rep) {
+      ldtm_latency_kernel<<<1, 32>>>(iters, sink, cyc);
+      CK(cudaDeviceSynchronize());
+    }
+    CK(cudaMemcpy(h.data(), cyc, sizeof(long long), cudaMemcpyDeviceToHost));
+    printf("{\"probe\": \"ldtm_dependent_latency\", \"cycles_per_x32_load\": %.1f}\n", (double)h[0] / iters);
+  }
+  // (6) issue cost
+  for (int nsel = 0; nsel < 3; ++nsel)
+    for (int commit_each = 0; commit_each < 2; ++commit_each)
+      for (int issuers = 1; issuers <= 2; ++issuers) {
+        const int n = 2000;
+        CK(cudaMemset(st, 0, 4));
+        CK(cudaMemset(cyc, 0, sizeof(long long) * 1024));
+        for (int rep = 0; rep < 2; ++rep) {
+          if (nsel == 0) mma_issue_kernel<64><<<sms, 128, 24576>>>(n, commit_each, issuers, cyc, st);
+          else if (nsel == 1) mma_issue_kernel<128><<<sms, 128, 24576>>>(n, commit_each, issuers, cyc, st);
+          else mma_issue_kernel<256><<<sms, 128, 24576>>>(n, commit_each, issuers, cyc, st);
+          CK(cudaDeviceSynchronize());
+        }
+        int sflag = 0;
+        CK(cudaMemcpy(&sflag, st, 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(h.data(), cyc, sizeof(long long) * 4, cudaMemcpyDeviceToHost));
+        printf("{\"probe\": \"mma_issue\", \"N\": %d, \"commit_each\": %d, \"issuers\": %d, \"status\": %d, "
+               "\"issue_cycles_per_mma\": %.1f, \"total_cycles_per_mma\": %.1f}\n",
+               nsel == 0 ? 64 : (nsel == 1 ? 128 : 256), commit_each, issuers, sflag, (double)h[0] / n, (double)h[1] / n);
+      }
   return 0;
 }

@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "lib", "libvo_b200.so")
+# VO_B200_LIB: another build of the same library (kernel experiments, tools/build_variants.sh)
+_LIB_PATH = os.environ.get("VO_B200_LIB") or os.path.join(_HERE, "lib", "libvo_b200.so")
 
 c_f32p = C.POINTER(C.c_float)
 c_i32p = C.POINTER(C.c_int32)

@@ -773,10 +773,13 @@ int vo_nn_last_rescans(vo_nn_t h, int64_t* n_rescans) {
   *n_rescans = -1;
   if (!h->last_was_tc) return VO_OK;
   DeviceGuard g(h->device);
-  unsigned long long v = 0;
-  VO_CUDA(cudaMemcpyAsync(&v, h->tc_stats.p, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+  unsigned long long v[16] = {};
+  VO_CUDA(cudaMemcpyAsync(v, h->tc_stats.p, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
   VO_CUDA(cudaStreamSynchronize(h->stream));
-  *n_rescans = (int64_t)v;
+  *n_rescans = (int64_t)v[0];
+  if (getenv("VO_NN_TC_PROFILE"))  // only meaningful in a -DNN_TC_PROFILE build
+    fprintf(stderr, "nn_tc profile (cycles, CTA 0): epi wait_acc %llu  ld %llu  fold+test %llu | mma wait_tile %llu  wait_free %llu  fence %llu  mma %llu  commit %llu  syncwarp %llu\n",
+            v[1], v[2], v[3], v[8 + 4], v[8 + 5], v[8 + 6], v[8 + 7], v[8 + 3], v[8 + 2]);
   return VO_OK;
 }
 

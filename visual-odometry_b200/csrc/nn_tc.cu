@@ -21,16 +21,36 @@
 // In ten dimensions the margin costs nothing: for uniform appearances the filter passes ~3e-10 of
 // the pairs, and clustered descriptors only add re-scans, never a cliff.
 //
-// Pipeline per CTA (one per SM, persistent): a TMA warp streams 256-row f16 tiles (8 KB, 1-D bulk
-// copies) into a 4-stage ring; one thread issues two N=128 MMAs per (query tile, map tile) into
-// four 128-column TMEM buffers; four warpgroups drain one buffer each.  Measured limits
-// (profiles/r02a_tc_probe.md): the f16 MMA takes 64 cycles per 128x128 tile, the TMEM read of the
-// epilogue 160 — the kernel is bound by tcgen05.ld throughput (~410 B/clk/SM).
+// Pipeline per CTA (one per SM, persistent, 19 warps):
+//   * a TMA warp streams 256-row f16 map tiles (8 KB, 1-D bulk copies) into a 4-stage ring;
+//   * the tile is split into two 128-row halves, each the start of an independent pipeline: its own
+//     MMA-issuing warp (one N=128 tcgen05.mma per resident query tile, each committed to an mbarrier),
+//     its own two 128-column TMEM buffers (all 512 columns are in use) and its own eight epilogue
+//     warps (lane quadrant x column half: thread = TMEM lane = query, 64 columns per thread);
+//   * an epilogue warp waits for the accumulator, reads its 64 columns with two tcgen05.ld.x32,
+//     releases the buffer, folds the 64 values into a minimum with 3-input mins and tests it.
+// Measured on hardware (tools/tc_probe.cu, profiles/r02a_tc_probe.md): one thread issues at most one
+// tcgen05.mma per 114 cycles whatever its width, several threads issue in parallel, issue-to-
+// barrier latency is 288 cycles, the f16 MMA itself takes N/2 cycles, and 16 warps read TMEM at
+// 410 B/clk/SM.  The last figure is the kernel's ceiling (4 B per pair: 0.34 s for 1e13 pairs); the
+// kernel reaches 48 % of it (0.70 s) — each warp serialises barrier wait, load latency, fold and
+// test, and 64 data registers per thread leave no room to overlap them.
 #include <cuda_fp16.h>
 
 #include <algorithm>
 
 #include "nn.cuh"
+
+// -DNN_TC_PROFILE: cycle counters of one epilogue warp and one MMA warp of CTA 0 in stats[1..6]
+// (tools/nn_tc_time.py prints them): 1 wait accumulator, 2 tcgen05.ld, 3 fold + threshold,
+// 4 MMA warp waits for the map tile, 5 waits for a free accumulator, 6 issues.
+#ifdef NN_TC_PROFILE
+#define TC_PROF_T(v) const long long v = clock64()
+#define TC_PROF_ADD(slot, v) prof[slot] += clock64() - (v)
+#else
+#define TC_PROF_T(v)
+#define TC_PROF_ADD(slot, v)
+#endif
 
 namespace vo {
 
@@ -287,6 +307,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
   int64_t u = units * blockIdx.x / gridDim.x;
   const int64_t u_end = units * (blockIdx.x + 1) / gridDim.x;
 
+#ifdef NN_TC_PROFILE
+  long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
   // running counters, identical in every role
   uint32_t unit_n = 0;   // map tiles streamed so far (position in the smem ring)
   uint32_t acc_n = 0;    // accumulator tiles each pipeline has produced so far (= unit_n * qt)
@@ -360,19 +383,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
       for (int64_t i = 0; i < nt; ++i) {
         const uint32_t n = unit_n + (uint32_t)i;
         const int s = (int)(n % TC_STAGES);
+        TC_PROF_T(pa);
         mbar_wait(&full[s], (n / TC_STAGES) & 1u);
+        TC_PROF_ADD(4, pa);
         tc_fence_after();
         const uint64_t bdesc = tc_desc(smem_u32(sB + s * TC_TILE_BYTES) + pipe * (TC_SUB * TC_ROW_BYTES));
         for (int a = 0; a < qt; ++a) {
           const int buf = pipe + TC_PIPES * (int)(n_acc & 1u);
+          TC_PROF_T(pb);
           mbar_wait(&tempty[buf], ((n_acc >> 1) & 1u) ^ 1u);
+          TC_PROF_ADD(5, pb);
+          TC_PROF_T(pc);
           tc_fence_after();
+          TC_PROF_ADD(6, pc);
           if (lane == 0) {
+            TC_PROF_T(pd);
             tc_mma_f16((uint32_t)buf * TC_SUB, tc_desc_hi() | (uint64_t)(a_desc0 + a * (TC_A_BYTES >> 4)), bdesc,
                        TC_IDESC);
+            TC_PROF_ADD(7, pd);
+            TC_PROF_T(pe);
             tc_commit(&tfull[buf]);
+            TC_PROF_ADD(3, pe);
           }
+          TC_PROF_T(pf);
           __syncwarp();
+          TC_PROF_ADD(2, pf);
           ++n_acc;
         }
         if (lane == 0) tc_commit(&empty[s]);  // the stage is free once every MMA above has read it
@@ -389,7 +424,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
       for (int64_t unit = 0; unit < nt; ++unit) {
         for (int a = 0; a < qt; ++a, ++n_acc) {
           const int buf = pipe + TC_PIPES * (int)(n_acc & 1u);
+          TC_PROF_T(pa);
+          const int ql = a * 128 + quad * 32 + lane;
+          const float my_thr = thr_s[ql];  // read before the wait: its latency hides behind it
           mbar_wait(&tfull[buf], (n_acc >> 1) & 1u);
+          TC_PROF_ADD(1, pa);
+          TC_PROF_T(pb);
           tc_fence_after();
           const uint32_t taddr = tlane + (uint32_t)buf * TC_SUB;
           uint32_t r0[32], r1[32];
@@ -400,14 +440,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[buf]);
+          TC_PROF_ADD(2, pb);
+          TC_PROF_T(pc);
           float m4[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
           tc_fold(m4, r0);
           tc_fold(m4, r1);
           const float mn = fminf(tc_min3(m4[0], m4[1], m4[2]), m4[3]);
 
-          const int ql = a * 128 + quad * 32 + lane;
           // `<=`: a query whose threshold is +inf (norm too large for f16) is always re-scanned
-          unsigned pending = __ballot_sync(0xffffffffu, mn <= thr_s[ql]);
+          unsigned pending = __ballot_sync(0xffffffffu, mn <= my_thr);
           while (pending) {
             const int src = __ffs(pending) - 1;
             pending &= pending - 1;
@@ -426,6 +467,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
             }
           }
           __syncwarp();
+          TC_PROF_ADD(3, pc);
         }
       }
     }
@@ -433,6 +475,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
     acc_n += (uint32_t)(nt * qt);
   }
 
+#ifdef NN_TC_PROFILE
+  if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == TC_EPI_WARPS + 1))
+    for (int i = 1; i < 8; ++i)
+      if (prof[i]) atomicAdd(p.stats + (warp == 0 ? 0 : 8) + i, (unsigned long long)prof[i]);
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == TC_EPI_WARPS + 1) tmem_dealloc(tmem_base, 512);
@@ -448,7 +495,7 @@ int nn_tc_pack(vo_nn_s* h) {
   const int64_t rows_tc = h->n_tiles16 * TC_BN;
   int rc = h->tiles16.reserve((size_t)h->n_tiles16 * TC_TILE_BYTES);
   if (rc) return rc;
-  rc = h->tc_stats.reserve(64);
+  rc = h->tc_stats.reserve(128);
   if (rc) return rc;
   const int threads = 256;
   nn_tc_pack_kernel<<<(unsigned)((rows_tc + threads - 1) / threads), threads, 0, h->stream>>>(
@@ -487,7 +534,7 @@ int nn_tc_launch(vo_nn_s* h, const float* queries_dev, int64_t nq, int qstride, 
                                  (int)TC_SMEM_BYTES));
     h->tc_opted_in = true;
   }
-  VO_CUDA(cudaMemsetAsync(h->tc_stats.p, 0, 64, h->stream));
+  VO_CUDA(cudaMemsetAsync(h->tc_stats.p, 0, 128, h->stream));
   const int sms = num_sms(h->device);
   const int64_t units = (int64_t)p.n_groups * p.n_tiles16;
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(sms, units));
