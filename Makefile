@@ -6,11 +6,18 @@ CSRC := $(PKG)/csrc
 LIB := $(PKG)/lib/libvo_b200.so
 NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
              -Xcompiler -fPIC,-Wall,-ffp-contract=off --expt-relaxed-constexpr
-SRCS := $(CSRC)/lib.cu $(CSRC)/stage.cu $(CSRC)/nn.cu $(CSRC)/nn_tc.cu $(CSRC)/picp.cu $(CSRC)/triangulate.cu $(CSRC)/pipeline.cu
+SRCS := $(CSRC)/lib.cu $(CSRC)/stage.cu $(CSRC)/nn.cu $(CSRC)/nn_tc.cu $(CSRC)/comm.cu $(CSRC)/picp.cu $(CSRC)/triangulate.cu $(CSRC)/pipeline.cu
 OBJS := $(SRCS:$(CSRC)/%.cu=build/%.o)
 HDRS := $(wildcard $(CSRC)/*.cuh) include/vo_b200.h
 
-all: $(LIB) oracle
+APPS := $(PKG)/host/bin/nn_sharded
+
+all: $(LIB) oracle $(APPS)
+
+# a plain C++ caller of the multi-GPU C ABI (no Eigen, no reference sources needed)
+$(PKG)/host/bin/nn_sharded: $(PKG)/host/apps/nn_sharded.cpp $(LIB) include/vo_b200.h
+	@mkdir -p $(dir $@)
+	$(CXX) -std=c++17 -O2 -I include $< -L $(PKG)/lib -lvo_b200 -Wl,-rpath,'$$ORIGIN/../../lib' -o $@
 
 $(LIB): $(OBJS)
 	@mkdir -p $(dir $@)

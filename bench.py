@@ -618,18 +618,23 @@ def bench_vo(torch, args, dist, rank, local, world):
         except Exception:  # noqa: BLE001
             rc = None
     frames, sec = float(r["frames"]), max(r["loop_ms"] * 1e-3, 1e-9)
+    per_rank = [{"rank": 0, "frames_per_s": frames / sec, "loop_s": sec}]
     if dist is not None:
-        t = torch.tensor([frames, sec], dtype=torch.float64, device="cuda")
-        tot = t.clone()
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        frames, sec = float(tot[0].item()), float(t[1].item())
+        mine = torch.tensor([frames, sec], dtype=torch.float64, device="cuda")
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        per_rank = [{"rank": i, "frames_per_s": float(t[0] / max(t[1], 1e-9)), "loop_s": float(t[1])}
+                    for i, t in enumerate(every)]
+        frames = float(sum(t[0] for t in every))
+        sec = float(max(t[1] for t in every))
+    slowest = max(per_rank, key=lambda x: x["loop_s"])["rank"]
     res = {
         "metric": "vo_frames_per_s", "value": frames / sec, "unit": "frames/s", "n_gpus": world,
         "scaling": "weak",
         "config": {"workload": f"batched vo_complete: {world} independent synthetic sequence(s) x "
                                f"{args.vo_frames} frames x {args.vo_landmarks} landmarks, one per GPU, "
                                "100 PICP rounds/frame; the first 20 loop frames are untimed warm-up"},
+        "per_rank": per_rank, "slowest_rank": slowest,
         "rank0": {k: r[k] for k in ("impl", "frames_per_s", "stage_ms_per_frame", "mean_measurements",
                                     "mean_correspondences", "map_points", "rot_err_mean_rad",
                                     "scale_first_pair", "scale_median")},
@@ -664,6 +669,142 @@ def bench_vo(torch, args, dist, rank, local, world):
         except Exception as e:  # noqa: BLE001
             res["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     return res
+
+
+def nn_clustered_np(M, Q, seed=77, clusters=1000, sigma=0.05):
+    """Clustered descriptors: `clusters` Gaussian blobs of std `sigma` in
+    [-1,1]^10, rows assigned to blobs at random; half of the queries are copies of map rows plus
+    N(0, 0.01^2) noise, half are fresh samples of the same mixture.  Every partial distance over a
+    few dimensions is small inside a blob, so a partial-distance filter prunes almost nothing."""
+    rng = np.random.RandomState(seed)
+    centres = rng.uniform(-1, 1, (clusters, 10)).astype(np.float32)
+    rows = np.empty((M, 11), np.float32)
+    rows[:, 0] = np.arange(M, dtype=np.float32)
+    step = 2_000_000
+    for r0 in range(0, M, step):
+        n = min(step, M - r0)
+        rows[r0:r0 + n, 1:] = centres[rng.randint(0, clusters, n)] + rng.normal(0, sigma, (n, 10)).astype(np.float32)
+    q = np.empty((Q, 11), np.float32)
+    q[:, 0] = np.arange(Q, dtype=np.float32)
+    src = rng.randint(0, M, Q)
+    q[:, 1:] = rows[src, 1:] + rng.normal(0, 0.01, (Q, 10)).astype(np.float32)
+    fresh = np.arange(Q) % 2 == 1
+    q[fresh, 1:] = centres[rng.randint(0, clusters, int(fresh.sum()))] + \
+        rng.normal(0, sigma, (int(fresh.sum()), 10)).astype(np.float32)
+    return rows, q
+
+
+def nn_extras(torch, vo, synth, args, local, cores, map_dev, fp32_peak):
+    """N=1 only: the FP32 filter on the headline config, the M sweep of config 4, and the clustered
+    data set through both filters.  Device-resident timing (CUDA events), bit-exact checks against
+    the reference on samples."""
+    import ref_lib
+
+    dev = torch.device("cuda", local)
+    M, Q = args.map_rows, args.queries
+    out = {}
+
+    def time_path(path, map_t, m_rows, q_t, nq, reps):
+        os.environ["VO_NN_FORCE_PATH"] = path
+        nn = vo.NNIndex(local)
+        os.environ.pop("VO_NN_FORCE_PATH", None)
+        nn.set_stream(torch.cuda.current_stream().cuda_stream)
+        nn.set_map_device(map_t.data_ptr(), m_rows, 11, 1)
+        idx = torch.empty(nq, dtype=torch.int32, device=dev)
+        ms = timed_steps(torch, lambda: nn.best_match_device(q_t.data_ptr(), nq, 11, RADIUS, idx.data_ptr()),
+                         reps, 1)
+        launches, rescans = nn.last_launches(), nn.last_rescans()
+        nn.close()
+        return ms, idx.cpu().numpy(), launches, rescans
+
+    # (a) the FP32 FFMA2 partial-distance filter (csrc/nn.cu) on the headline configuration
+    q_np, target = synth.nn_queries_np(Q, M)
+    q_t = torch.from_numpy(q_np).to(dev)
+    ms, got, launches, _ = time_path("ffma", map_dev, M, q_t, Q, 2)
+    cls = np.arange(Q) % 4
+    achieved = NN_FLOP_PER_PAIR * Q * M / (ms * 1e-3) / 1e12
+    out["nn_ffma"] = {
+        "value": Q / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms,
+        "planted_answers_equal": bool(np.array_equal(got[cls < 3], target[cls < 3]) and np.all(got[cls == 3] == -1)),
+        "launches": launches,
+        "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": achieved / fp32_peak, "algorithmic_flop_per_pair": NN_FLOP_PER_PAIR,
+                     "executed_flop_per_pair": 10.0, "executed_frac": achieved / 3.0 / fp32_peak,
+                     "kernel": "nn_filter_kernel<12,384>",
+                     "note": "frac counts the 30 algorithmic flop; the 5-of-10-dimension filter executes 10 "
+                             "(ncu sm__pipe_fma_cycles_active 69 %, profiles/r01e_ncu_nn.md)"}}
+    # (b) config 4's sweep: M = 1e6, 1e7 rows of the same map (default path = tensor-core filter)
+    sweep = []
+    for m_rows in (1_000_000, 10_000_000):
+        if m_rows >= M:
+            continue
+        qn, tg = synth.nn_queries_np(Q, m_rows)
+        qt = torch.from_numpy(qn).to(dev)
+        ms, got, launches, rescans = time_path("", map_dev, m_rows, qt, Q, 3)
+        sweep.append({"map_rows": m_rows, "queries_per_s": Q / (ms * 1e-3), "ms_per_step": ms,
+                      "filter": "tensor" if launches and launches[0][0] == 0 else "fp32",
+                      "planted_answers_equal": bool(np.array_equal(got[cls < 3], tg[cls < 3]) and
+                                                    np.all(got[cls == 3] == -1))})
+    sweep.append({"map_rows": M, "see": "primary line"})
+    out["nn_sweep"] = sweep
+    # (c) clustered descriptors, M = 1e7: both filters, sample checked against the reference
+    Mc = min(10_000_000, M)
+    rows, qc = nn_clustered_np(Mc, Q)
+    rows_t, qc_t = torch.from_numpy(rows).to(dev), torch.from_numpy(qc).to(dev)
+    res = {}
+    for path in ("tc", "ffma"):
+        ms, got, launches, rescans = time_path(path, rows_t, Mc, qc_t, Q, 2)
+        res[path] = (ms, got, rescans)
+    sel = np.linspace(0, Q - 1, max(cores, 64)).astype(np.int64)
+    if ref_lib.available():
+        ref_idx = np.concatenate(list(ThreadPoolExecutor(cores).map(
+            lambda ix: ref_lib.nn_best_match_inplace(rows, qc[ix], RADIUS), np.array_split(sel, cores))))
+        kind = "reference"
+    else:
+        import oracle_lib
+
+        ref_idx, kind = oracle_lib.nn_best_match(rows, qc[sel], RADIUS)[0], "port"
+    out["nn_clustered"] = {
+        "config": {"workload": f"{Q} queries x {Mc}-row map, 1000 Gaussian clusters (sigma 0.05), radius {RADIUS}"},
+        "tensor_filter": {"queries_per_s": Q / (res["tc"][0] * 1e-3), "ms_per_step": res["tc"][0],
+                          "rescans_per_query": res["tc"][2] / Q},
+        "fp32_filter": {"queries_per_s": Q / (res["ffma"][0] * 1e-3), "ms_per_step": res["ffma"][0]},
+        "match_rate": float(np.mean(res["tc"][1] >= 0)),
+        "parity": {"filters_agree": bool(np.array_equal(res["tc"][1], res["ffma"][1])),
+                   "sample": int(len(sel)), "sample_equal_" + kind: bool(np.array_equal(ref_idx, res["tc"][1][sel]))}}
+    return out
+
+
+def bench_whole(args):
+    """Config 2: whole_test at 1e4 points (3 views, epipolar init on the host, triangulation + 100
+    PICP rounds on the GPU) — the seeded driver built against the drop-in layer vs the same source
+    built against the reference (oracle/_ref), compared per original correspondence id."""
+    import tempfile
+
+    import test_whole_gpu as tw
+
+    if not (os.path.exists(tw.GPU_EXE) and os.path.exists(tw.REF_EXE)):
+        return {"unavailable": "whole_synthetic executables not built (need the reference checkout at build time)"}
+    out = {"config": {"workload": "whole_test synthetic: 3 views, 1e4 points, epipolar init (host) + "
+                                  "triangulation + 100 PICP rounds"}, "tolerance_rel": 1e-5, "runs": []}
+    with tempfile.TemporaryDirectory() as tmp:
+        for dist, seed in (("frustum", 11), ("ref", 11)):
+            gi, g = tw.run(tw.GPU_EXE, 10000, seed, dist, 100, os.path.join(tmp, "g.bin"))
+            ci, c = tw.run(tw.REF_EXE, 10000, seed, dist, 100, os.path.join(tmp, "c.bin"))
+            gpu_ms = gi["ms"]["triangulate"] + gi["ms"]["picp"] + gi["ms"]["project_2_views"] + gi["ms"]["project_view_2"]
+            cpu_ms = ci["ms"]["triangulate"] + ci["ms"]["picp"] + ci["ms"]["project_2_views"] + ci["ms"]["project_view_2"]
+            out["runs"].append({"dist": dist, "seed": seed, "n_correspondences": gi["n_correspondences"],
+                                "n_triangulated": gi["n_triangulated"], "parity": tw.compare(g, c),
+                                "b200_ms": gi["ms"], "reference_cpu_ms": ci["ms"],
+                                "hot_path_ms": {"b200": gpu_ms, "reference_cpu": cpu_ms}})
+    fr = out["runs"][0]
+    out["e2e"] = {"value": 1e3 / fr["hot_path_ms"]["b200"], "unit": "whole_test runs/s (hot path: 3 projections, "
+                  "triangulation, 100 PICP rounds; host vectors in and out through the drop-in classes)",
+                  "h2d_bytes_per_step": int(3 * 12e4 + 28 * fr["n_correspondences"]),
+                  "d2h_bytes_per_step": int(3 * 8e4 + 20 * fr["n_triangulated"] + 268 * 2)}
+    out["cpu_baseline"] = {"value": 1e3 / fr["hot_path_ms"]["reference_cpu"], "unit": "whole_test runs/s",
+                           "cores": 1, "kind": "reference", "sample": "the same run, frustum-dist"}
+    return out
 
 
 def ours_arm(args):
@@ -704,8 +845,10 @@ def ours_arm(args):
     nn.set_stream(torch.cuda.current_stream().cuda_stream)
     nn.set_map_device(map_dev.data_ptr(), M, 11, 1)
     torch.cuda.synchronize()
-    del map_dev  # the handle owns the re-packed tiles; the caller's rows are no longer needed
-    torch.cuda.empty_cache()
+    keep_map = rank == 0 and world == 1 and not args.nn_only
+    if not keep_map:
+        del map_dev  # the handle owns the re-packed tiles; the caller's rows are no longer needed
+        torch.cuda.empty_cache()
 
     def gather():
         if world > 1:
@@ -720,6 +863,8 @@ def ours_arm(args):
     ms = timed_steps(torch, step, args.steps, args.warmup, dist, sampler)
     launches = (vo.launch_count() - l0) // (args.steps + args.warmup) * args.steps
     value = Q / (ms * 1e-3)
+    nn_launches, nn_rescans = nn.last_launches(), nn.last_rescans()
+    tensor_path = bool(nn_launches) and nn_launches[0][0] == 0
 
     # kernel-only duration for the roofline (no collective), CUDA events on the launch stream
     def kstep():
@@ -749,7 +894,7 @@ def ours_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
 
-    # ---- parity: planted answers on all Q, oracle on a sample ----------------------------------
+    # ---- parity: planted answers on all Q, the reference on a sample ---------------------------
     torch.cuda.synchronize()
     got = idx_all.cpu().numpy()
     cls = np.arange(Q) % 4
@@ -766,8 +911,34 @@ def ours_arm(args):
                         f"({ffma:.1f}) and packed FFMA2 ({ffma2:.1f}) TFLOP/s")
         except Exception:
             fp32_peak, peak_src = NOMINAL_FP32_TFLOPS, "nominal 148x128x2x1.965GHz"
-        achieved = NN_FLOP_PER_PAIR * nq * M / (kms * 1e-3) / 1e12
-        # CPU baseline (oracle port) on a bounded sample against the full map
+        pairs = float(nq) * M
+        alg_tflops = NN_FLOP_PER_PAIR * pairs / (kms * 1e-3) / 1e12
+        if tensor_path:
+            tc_peak = peaks.get("bf16_tflops", 1590.0)
+            achieved = NN_TC_FLOP_PER_PAIR * pairs / (kms * 1e-3) / 1e12
+            sm_hz = (sampler.summary().get("sm_mhz") or 1965.0) * 1e6
+            tmem_bpc = 4.0 * pairs / (kms * 1e-3) / 148 / sm_hz
+            roof = {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
+                    "frac": achieved / tc_peak,
+                    **traffic_fields("nn_tc", M == 100_000_000 and Q == 100_000 and world == 1),
+                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst; f16 runs at the same rate)"
+                                    if peaks else "fallback 1590"),
+                    "kernel": "nn_tc_filter_kernel", "executed_flop_per_pair": NN_TC_FLOP_PER_PAIR,
+                    "algorithmic_flop_per_pair": NN_FLOP_PER_PAIR, "algorithmic_tflops": alg_tflops,
+                    "algorithmic_frac_of_fp32_peak": alg_tflops / fp32_peak, "fp32_peak": fp32_peak,
+                    "fp32_peak_source": peak_src,
+                    "limiter": "tcgen05.ld of the epilogue (4 B per pair)",
+                    "tmem_read_bytes_per_clk_per_sm": tmem_bpc,
+                    "tmem_read_frac": tmem_bpc / TMEM_READ_B_PER_CLK_SM,
+                    "tmem_read_peak_source": "410 B/clk/SM, tools/tc_probe.cu (profiles/r02a_tc_probe.md)",
+                    "rescans_per_query": nn_rescans / max(nq, 1), "kernel_ms": kms}
+        else:
+            roof = {"bound": "fp32", "achieved": alg_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+                    "frac": alg_tflops / fp32_peak, "traffic": None, "peak_source": peak_src,
+                    "kernel": "nn_filter_kernel", "algorithmic_flop_per_pair": NN_FLOP_PER_PAIR,
+                    "executed_flop_per_pair": 10.0, "executed_frac": alg_tflops / 3.0 / fp32_peak,
+                    "kernel_ms": kms}
+        # CPU baseline (the reference's own template) on a bounded sample against the full map
         sample_q = max(cores, min(Q, int(2.0 * 1.0e8 * cores / max(M, 1))))
         map_host = np.empty((M, 11), dtype=np.float32)
         slab = 2_000_000
@@ -784,28 +955,23 @@ def ours_arm(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"appearance NN: {Q} queries x {M}-row 10-D map, radius {RADIUS}"
-                                   f", queries sharded over {world} GPU(s), map replicated",
-                       "map_rows": M, "queries": Q, "l2": "inputs_larger_than_l2"
-                       if M * 48 > 126e6 else "map fits L2 (small config)",
-                       "collective": "all_gather(int32 indices) over NCCL" if world > 1 else "none"},
+            "config": {"workload": nn_workload(Q, M), "map_rows": M, "queries": Q,
+                       "l2": "inputs_larger_than_l2" if M * 32 > 126e6 else "map fits L2 (small config)",
+                       "collective": "all_gather(int32 indices) over NCCL" if world > 1 else "none",
+                       "filter": "tcgen05 f16 (nn_tc.cu) + exact FP32 re-rank" if tensor_path
+                       else "FP32 FFMA2 partial distance (nn.cu) + exact FP32 re-rank"},
             "e2e": {"value": Q / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(nq * 44),
                     "d2h_bytes_per_step": int(nq * 4), "note": "map resident; per-rank copies"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
-            "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak,
-                         "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                         **traffic_fields("nn", M == 100_000_000 and Q == 100_000 and world == 1),
-                         "peak_source": peak_src, "kernel": "nn_filter_kernel",
-                         "algorithmic_flop_per_pair": NN_FLOP_PER_PAIR,
-                         "nominal_fp32_tflops": NOMINAL_FP32_TFLOPS,
-                         "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS,
-                         "kernel_ms": kms},
+            "roofline": roof,
             "cpu_baseline": {"value": cpu_qps, "unit": "queries/s", "cores": cores,
                              "kind": cpu_kind(),
                              "sample": f"{sample_q} queries x full {M}-row map, {cores} threads"},
             "parity": {"planted_answers_equal": planted_ok, "oracle_sample_equal": oracle_equal,
-                       "oracle_sample": sample_q, "rule": "bit-exact indices",
+                       "oracle_sample": sample_q,
+                       "rule": "bit-exact indices vs the reference's bruteForceBestMatch compiled over "
+                               "third_party/mini_eigen (Eigen's summation order is mini_eigen's model of it)",
                        "kdtree": None if args.nn_only else kdtree_guard(vo, synth, local)},
         }
     nn.close()
@@ -819,15 +985,23 @@ def ours_arm(args):
             traceback.print_exc(file=sys.stderr)
             return {"error": f"{type(e).__name__}: {e}"[:400]}
 
-    if rank == 0 and world == 1 and not args.nn_only:
+    if keep_map:
+        ex = guarded(nn_extras, torch, vo, synth, args, local, cores, map_dev, line["roofline"].get("fp32_peak", NOMINAL_FP32_TFLOPS))
+        if "error" in ex:
+            line["nn_extras"] = ex
+        else:
+            line.update(ex)
+        del map_dev
+        torch.cuda.empty_cache()
         line["picp"] = guarded(bench_picp, torch, vo, synth, args, cores)
         line["triangulate"] = guarded(bench_triangulate, torch, vo, synth, args, cores)
+        line["whole"] = guarded(bench_whole, args)
     if not args.nn_only and args.vo_frames > 0:
         vo_res = guarded(bench_vo, torch, args, dist, rank, local, world)
         if rank == 0:
             line["vo"] = vo_res
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(compact(line)), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -112,6 +112,25 @@ int vo_nn_radius_search(vo_nn_t h, const float* queries_host, int64_t n_queries,
                         int query_stride, float norm, int32_t* counts_host,
                         int32_t* idx_out_host, int32_t max_per_query);
 
+/* ==== (1b) the same on several GPUs of one node ===========================================
+ * BASELINE config 4 / SURVEY.md 8e: the map is replicated on every GPU, a query batch is cut into
+ * contiguous blocks (GPU g answers [g*Q/G, (g+1)*Q/G)), and the int32 match indices are gathered
+ * with ONE ncclAllGather over NVLink — the only collective; no data-path exchange.  One process
+ * drives all GPUs (ncclCommInitAll over devices 0..n-1; NCCL is loaded at run time).  The reference
+ * has no counterpart: it answers one query at a time on one thread (src/apps/vo_complete.cpp:12-49).
+ */
+typedef struct vo_comm_s* vo_comm_t;
+
+int vo_comm_init_all(vo_comm_t* out, int n_gpus);
+int vo_comm_destroy(vo_comm_t c);
+int vo_comm_size(vo_comm_t c);
+/* vo_nn_set_map on GPU 0, then the re-packed map is broadcast to the other GPUs over NVLink      */
+int vo_nn_set_map_replicated(vo_comm_t c, const float* rows_host, int64_t n_rows, int row_stride,
+                             int skip_cols);
+/* vo_nn_best_match with the queries sharded over the communicator's GPUs                         */
+int vo_nn_best_match_sharded(vo_comm_t c, const float* queries_host, int64_t n_queries,
+                             int query_stride, float norm, int32_t* best_idx_host);
+
 /* ==== (2) projective ICP ===============================================================
  * replaces PICPSolver::{init,oneRound,linearize,errorAndJacobian}  src/picp_solver.cpp:16-112
  * and Camera::projectPoint                                        include/camera.h:25-37

@@ -17,6 +17,7 @@ from .api import (  # noqa: F401
     FramePipeline,
     NNIndex,
     PICPSolver,
+    ShardedNN,
     bruteForceBestMatch,
     bruteForceSearch,
     project_points,

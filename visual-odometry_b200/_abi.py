@@ -67,6 +67,11 @@ PROTOTYPES = {
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int32],
     ),
+    "vo_comm_init_all": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "vo_comm_destroy": (C.c_int, [C.c_void_p]),
+    "vo_comm_size": (C.c_int, [C.c_void_p]),
+    "vo_nn_set_map_replicated": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int]),
+    "vo_nn_best_match_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p]),
     "vo_picp_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "vo_picp_destroy": (C.c_int, [C.c_void_p]),
     "vo_picp_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -170,6 +170,41 @@ class NNIndex:
         return counts, lst
 
 
+class ShardedNN:
+    """bruteForceBestMatch on several GPUs of one node from ONE process (vo_comm_*): map replicated,
+    queries sharded in contiguous blocks, indices gathered with one ncclAllGather."""
+
+    def __init__(self, n_gpus):
+        self._c = C.c_void_p()
+        check(lib().vo_comm_init_all(C.byref(self._c), int(n_gpus)), "vo_comm_init_all")
+
+    def close(self):
+        if self._c:
+            lib().vo_comm_destroy(self._c)
+            self._c = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self):
+        return int(lib().vo_comm_size(self._c))
+
+    def set_map(self, rows, skip_cols=1):
+        rows = _f32(rows)
+        check(lib().vo_nn_set_map_replicated(self._c, _ptr(rows), rows.shape[0], rows.shape[1], skip_cols),
+              "vo_nn_set_map_replicated")
+
+    def best_match(self, queries, norm):
+        q = _f32(queries)
+        idx = np.empty(q.shape[0], dtype=np.int32)
+        check(lib().vo_nn_best_match_sharded(self._c, _ptr(q), q.shape[0], q.shape[1], float(norm), _ptr(idx)),
+              "vo_nn_best_match_sharded")
+        return idx
+
+
 def bruteForceBestMatch(points, query, norm, device=0):
     """brute_force_search.h:22-41 for one query (or a batch): index of the best row or -1."""
     points = _f32(points)
