@@ -606,7 +606,8 @@ def bench_vo(torch, args, dist, rank, local, world):
         err = f"{type(e).__name__}: {e}"[:300]
         r = {"frames": 0, "loop_ms": 0.0, "frames_per_s": 0.0, "stage_ms_per_frame": {},
              "mean_measurements": 0.0, "mean_correspondences": 0.0, "map_points": 0,
-             "rot_err_mean_rad": None, "scale_first_pair": None, "scale_median": None, "impl": "failed"}
+             "rot_err_mean_rad": None, "scale_first_pair": None, "scale_median": None,
+             "scale_alive_frames": 0, "impl": "failed"}
     # the same frames through the drop-in classes (the reference's call surface, call by call)
     rc = None
     if rank == 0 and world == 1:
@@ -633,11 +634,14 @@ def bench_vo(torch, args, dist, rank, local, world):
         "scaling": "weak",
         "config": {"workload": f"batched vo_complete: {world} independent synthetic sequence(s) x "
                                f"{args.vo_frames} frames x {args.vo_landmarks} landmarks, one per GPU, "
-                               "100 PICP rounds/frame; the first 20 loop frames are untimed warm-up"},
+                               "100 PICP rounds/frame; the first 20 loop frames are untimed warm-up",
+                   "note": "scale_alive_frames = frames before the estimated step length falls below half its "
+                           "initial value: the reference's frame-to-frame monocular scale decays and collapses on "
+                           "long sequences in BOTH builds (DESIGN.md 5); the per-frame work is unaffected"},
         "per_rank": per_rank, "slowest_rank": slowest,
         "rank0": {k: r[k] for k in ("impl", "frames_per_s", "stage_ms_per_frame", "mean_measurements",
                                     "mean_correspondences", "map_points", "rot_err_mean_rad",
-                                    "scale_first_pair", "scale_median")},
+                                    "scale_first_pair", "scale_median", "scale_alive_frames") if k in r},
         "e2e": {"value": frames / sec, "unit": "frames/s",
                 "h2d_bytes_per_step": int(44 * r["mean_measurements"]), "d2h_bytes_per_step": 64 + 268,
                 "note": "host frames in, host pose out every frame through vo_pipe_step (the "

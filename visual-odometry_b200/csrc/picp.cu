@@ -32,7 +32,13 @@
 
 namespace vo {
 
-constexpr int PICP_THREADS = 384;
+#ifndef PICP_THREADS_N
+#define PICP_THREADS_N 384
+#endif
+#ifndef PICP_DEPTH_N
+#define PICP_DEPTH_N 3
+#endif
+constexpr int PICP_THREADS = PICP_THREADS_N;
 constexpr int PICP_UNROLL = 4;
 constexpr int PICP_NACC = 32;  // 21 H + 6 b + chi_in + chi_out + n_in (as float bits of int) + 2 pad
 
@@ -52,7 +58,8 @@ struct PicpParams {
   int min_inliers;
   int keep_outliers;
   PicpDeviceState* st;
-  float* partials;                   // [gridDim.x][PICP_NACC]
+  float* partials;                   // [2][gridDim.x][PICP_NACC]
+  unsigned int* barrier;             // grid-barrier arrival counter, zeroed before every launch
   // frame-pipeline extensions (resident kernel only)
   const int* n_pairs_dev;            // if set: the correspondence count lives on the device
   int has_pre;                       // if set: world points are moved by `pre` while gathered
@@ -113,7 +120,11 @@ __device__ __forceinline__ f2_t f2_sel(bool c0, bool c1, f2_t a, f2_t b) {
 template <bool PINHOLE, bool KEEP>
 __device__ __forceinline__ void picp_point2(const PicpParams& p, const PicpConsts& c, f2_t wx,
                                             f2_t wy, f2_t wz, f2_t mu, f2_t mv, bool have1,
-                                            PicpAcc& a) {
+                                            PicpAcc& a, bool have0 = true) {
+#ifdef PICP_NO_MATH  // experiment: the memory pipeline alone (tools/build_variants.sh)
+  a.h[0] = f2_add(a.h[0], f2_add(f2_add(wx, wy), f2_add(wz, f2_add(mu, mv))));
+  return;
+#endif
   const float* T = c.T;
   const f2_t neg1 = f2_bc(-1.f);
   // camera_point = world_in_camera * world_point  (camera.h:27, picp_solver.cpp:38)
@@ -122,7 +133,7 @@ __device__ __forceinline__ void picp_point2(const PicpParams& p, const PicpConst
   f2_t pz = f2_fma(f2_bc(T[8]), wz, f2_fma(f2_bc(T[5]), wy, f2_fma(f2_bc(T[2]), wx, f2_bc(T[11]))));
   float pz0, pz1;
   f2_unpack(pz, pz0, pz1);
-  bool valid0 = !(pz0 > p.z_far || pz0 < p.z_near);  // camera.h:28
+  bool valid0 = have0 && !(pz0 > p.z_far || pz0 < p.z_near);  // camera.h:28
   bool valid1 = have1 && !(pz1 > p.z_far || pz1 < p.z_near);
   // phom = K * camera_point  (camera.h:30, picp_solver.cpp:43)
   f2_t hx, hy, hz;
@@ -225,6 +236,24 @@ __device__ __forceinline__ void picp_point2(const PicpParams& p, const PicpConst
   }
 }
 
+// Grid-wide barrier of a cooperative launch (all CTAs co-resident), hand-written: one arrival
+// counter on one L2 line that only ever grows — round r is complete when it reaches (r+1) x CTAs —
+// so there is no reset, no second phase and no generation flag.  arrive() publishes the CTA's
+// partial row (fence, then one relaxed atomic); wait() is one thread polling with acquire loads
+// while the rest of the CTA sleeps on the block barrier.  cooperative_groups' grid.sync() cost
+// 2.6 us per round here (measured in-kernel at 148 CTAs), this one ~1 us, and work can be placed
+// between arrive and wait.
+__device__ __forceinline__ void grid_arrive(unsigned int* counter) {
+  __threadfence();
+  atomicAdd(counter, 1u);
+}
+__device__ __forceinline__ void grid_wait(const unsigned int* counter, unsigned int target) {
+  unsigned int v;
+  do {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+  } while (v < target);
+}
+
 // ---- per-thread asynchronous staging ring (cp.async, SASS LDGSTS) ---------------------------------
 // Registers cannot hold enough loads in flight: 6.5 TB/s x ~1.5 us of loaded HBM latency is ~10 MB,
 // i.e. ~70 KB per SM, while the accumulators already take 58 registers per thread.  So the
@@ -238,7 +267,7 @@ __device__ __forceinline__ void picp_point2(const PicpParams& p, const PicpConst
 // group, and then linearises batch b.  Slots are laid out so that every access of a warp is
 // conflict-free, and so that the two points a thread pairs up in packed-FP32 lanes sit in one
 // 8-byte word: one LDS.64 yields a ready-made packed operand.
-constexpr int PICP_DEPTH = 3;
+constexpr int PICP_DEPTH = PICP_DEPTH_N;
 constexpr int PICP_SLOTS = PICP_DEPTH + 1;
 constexpr int PICP_PTS_WORDS = PICP_SLOTS * (PICP_UNROLL / 2) * 5;  // 8-byte words per thread
 constexpr int PICP_PRS_WORDS = PICP_SLOTS * PICP_UNROLL;
@@ -373,7 +402,6 @@ __global__ void __launch_bounds__(PICP_RES_THREADS, 1)
 picp_resident_kernel(const PicpParams p, const int rounds) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
-  cg::grid_group grid = cg::this_grid();
   const int csize = GRID ? (int)gridDim.x : (int)cluster.num_blocks();
   const int rank = GRID ? (int)blockIdx.x : (int)cluster.block_rank();
   extern __shared__ __align__(16) unsigned char picp_ring[];
@@ -465,8 +493,12 @@ picp_resident_kernel(const PicpParams p, const int rounds) {
       }
     }
     if (GRID) {
-      __threadfence();
-      grid.sync();
+      if (warp == 0) {
+        __syncwarp();
+        if (lane == 0) grid_arrive(p.barrier);
+      }
+      if (tid == 0) grid_wait(p.barrier, (unsigned int)(round + 1) * gridDim.x);
+      __syncthreads();
       // warp w sums rows w, w+W, ... (all loads in flight at once), warp 0 then sums the W results
       const float* part = p.partials + (int64_t)(round & 1) * csize * PICP_NACC;
       float acc = 0.f;
@@ -542,7 +574,6 @@ template <bool PINHOLE, bool KEEP>
 __global__ void __launch_bounds__(PICP_THREADS, 1)
 picp_stream_kernel(const PicpParams p, const int rounds) {
   namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
   __shared__ float s_red[PICP_THREADS / 32][PICP_NACC];
   __shared__ float s_T[12], s_H[36], s_b[6], s_keep[4];
   const int tid = threadIdx.x;
@@ -556,15 +587,20 @@ picp_stream_kernel(const PicpParams p, const int rounds) {
   const int stride = (int)gridDim.x * PICP_THREADS;
   const int i0 = (int)blockIdx.x * PICP_THREADS + tid;
   const int mine = i0 < n ? (n - i0 + stride - 1) / stride : 0;  // items of this thread
-  const int nb = mine / PICP_UNROLL;                             // full batches
+  // batches of PICP_UNROLL items; the last one is padded with repeats of the thread's first item
+  // (masked out in the arithmetic) so that EVERY item goes through the asynchronous ring — a
+  // separate tail loop of dependent global loads cost ~3 us of exposed latency per round
+  const int nb = (mine + PICP_UNROLL - 1) / PICP_UNROLL;
   const int2* pp = p.pairs + i0;
   extern __shared__ __align__(16) unsigned char picp_ring[];
   const uint32_t ring = smem_u32(picp_ring) + (uint32_t)tid * 8u;
   auto issue_pairs = [&](int b, int slot) {  // P(b)
     if (b < nb) {
 #pragma unroll
-      for (int u = 0; u < PICP_UNROLL; ++u)
-        cp_async8(ring + picp_prs_off(slot, u), pp + (int64_t)(b * PICP_UNROLL + u) * stride);
+      for (int u = 0; u < PICP_UNROLL; ++u) {
+        const int j = b * PICP_UNROLL + u;
+        cp_async8(ring + picp_prs_off(slot, u), pp + (int64_t)(j < mine ? j : 0) * stride);
+      }
     }
   };
   auto issue_gathers = [&](int b, int slot) {  // G(b); P(b) has landed
@@ -602,7 +638,16 @@ picp_stream_kernel(const PicpParams p, const int rounds) {
   fill_pairs();
   fill_gathers();
 
+#ifdef PICP_PROFILE
+  long long prof[6] = {0, 0, 0, 0, 0, 0};
+#define PP_T(v) const long long v = clock64()
+#define PP_ADD(i, v) prof[i] += clock64() - (v)
+#else
+#define PP_T(v)
+#define PP_ADD(i, v)
+#endif
   for (int round = 0; round < rounds; ++round) {
+  PP_T(t_loop);
 
   PicpConsts c;
 #pragma unroll
@@ -632,7 +677,8 @@ picp_stream_kernel(const PicpParams p, const int rounds) {
                                        lds_f2(ring + picp_pts_off(sl, pi, 1)),
                                        lds_f2(ring + picp_pts_off(sl, pi, 2)),
                                        lds_f2(ring + picp_pts_off(sl, pi, 3)),
-                                       lds_f2(ring + picp_pts_off(sl, pi, 4)), true, a);
+                                       lds_f2(ring + picp_pts_off(sl, pi, 4)),
+                                       b * PICP_UNROLL + 2 * pi + 1 < mine, a, b * PICP_UNROLL + 2 * pi < mine);
         }
       }
     }
@@ -640,65 +686,59 @@ picp_stream_kernel(const PicpParams p, const int rounds) {
     // next round's pair loads go out now; its gathers follow after the warp reduction below
     const bool more = round + 1 < rounds;
     if (more) fill_pairs();
-    // the (< PICP_UNROLL) leftover items of this thread, again two at a time
-    for (int m = nb * PICP_UNROLL; m < mine; m += 2) {
-      const bool have1 = m + 1 < mine;
-      const int2 pr0 = __ldg(pp + (int64_t)m * stride);
-      const int2 pr1 = have1 ? __ldg(pp + (int64_t)(m + 1) * stride) : pr0;
-      const float* w0 = p.world + 3 * (int64_t)pr0.y;
-      const float* w1 = p.world + 3 * (int64_t)pr1.y;
-      const float2 m0 = __ldg(reinterpret_cast<const float2*>(p.image) + pr0.x);
-      const float2 m1 = __ldg(reinterpret_cast<const float2*>(p.image) + pr1.x);
-      picp_point2<PINHOLE, KEEP>(p, c, f2_pack(__ldg(w0), __ldg(w1)),
-                                 f2_pack(__ldg(w0 + 1), __ldg(w1 + 1)),
-                                 f2_pack(__ldg(w0 + 2), __ldg(w1 + 2)), f2_pack(m0.x, m1.x),
-                                 f2_pack(m0.y, m1.y), have1, a);
-    }
   }
+  PP_ADD(0, t_loop);
+  PP_T(t_red);
 
-  // ---- block reduction: shuffle within the warp, fixed-order sum across warps ----------------
-  float v[PICP_NACC];
+  // ---- block reduction: transposed warp reduction (31 shuffles for the 30 sums), fixed-order sum
+  // across warps, one partial row per CTA ---------------------------------------------------------
+  {
+    float v[32];
 #pragma unroll
-  for (int i = 0; i < 29; ++i) {  // the two point slots
-    float lo, hi;
-    f2_unpack(i < 21 ? a.h[i] : (i < 27 ? a.b[i - 21] : (i == 27 ? a.chi_in : a.chi_out)), lo, hi);
-    v[i] = lo + hi;
-  }
-  int n_in = a.n_in;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-    for (int i = 0; i < 29; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
-    n_in += __shfl_xor_sync(0xffffffffu, n_in, o);
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < 29; ++i) s_red[warp][i] = v[i];
-    s_red[warp][29] = __int_as_float(n_in);
-  }
-  if (round + 1 < rounds) fill_gathers();  // in flight across the grid barrier and the solve
-  __syncthreads();
-  if (warp == 0 && lane < 30) {
-    float* out = p.partials + ((int64_t)(round & 1) * gridDim.x + blockIdx.x) * PICP_NACC;
-    if (lane < 29) {
-      float s = s_red[0][lane];
-#pragma unroll
-      for (int wv = 1; wv < PICP_THREADS / 32; ++wv) s += s_red[wv][lane];
-      out[lane] = s;
-    } else {
-      int s = 0;
-#pragma unroll
-      for (int wv = 0; wv < PICP_THREADS / 32; ++wv) s += __float_as_int(s_red[wv][29]);
-      out[29] = __int_as_float(s);
+    for (int i = 0; i < 29; ++i) {  // the two point slots
+      float lo, hi;
+      f2_unpack(i < 21 ? a.h[i] : (i < 27 ? a.b[i - 21] : (i == 27 ? a.chi_in : a.chi_out)), lo, hi);
+      v[i] = lo + hi;
     }
+    v[29] = (float)a.n_in;  // exact: a thread sees far fewer than 2^24 points per round
+    v[30] = v[31] = 0.f;
+    float mine_sum = warp_reduce_transposed(v);  // lane i holds sum i of the warp
+    if (lane == 29) mine_sum = __int_as_float((int)mine_sum);  // counts travel as integers
+    s_red[warp][lane] = mine_sum;
   }
+  __syncthreads();
+  if (warp == 0) {
+    if (lane < 30) {
+      float* out = p.partials + ((int64_t)(round & 1) * gridDim.x + blockIdx.x) * PICP_NACC;
+      if (lane < 29) {
+        float s = s_red[0][lane];
+#pragma unroll
+        for (int wv = 1; wv < PICP_THREADS / 32; ++wv) s += s_red[wv][lane];
+        out[lane] = s;
+      } else {
+        int s = 0;
+#pragma unroll
+        for (int wv = 0; wv < PICP_THREADS / 32; ++wv) s += __float_as_int(s_red[wv][29]);
+        out[29] = __int_as_float(s);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) grid_arrive(p.barrier);
+  }
+  PP_ADD(1, t_red);
+  PP_T(t_bar);
+  // the next round's gathers go out while the other CTAs arrive: they are in flight across the
+  // barrier, the cross-CTA sum and the solve
+  if (round + 1 < rounds) fill_gathers();
 
   // ---- every block: fixed-order sum over all blocks' partials, solve, own copy of the pose -------
   // One grid-wide barrier per round; the partial buffers alternate with the round's parity, so a
   // fast block's next round cannot overwrite what a slow one is still reading.  Every block runs
   // the same instruction stream on the same numbers, so all copies of the pose stay identical.
-  __threadfence();
-  grid.sync();
+  if (tid == 0) grid_wait(p.barrier, (unsigned int)(round + 1) * gridDim.x);
+  __syncthreads();
+  PP_ADD(2, t_bar);
+  PP_T(t_sum);
   {
     // warp w sums blocks w, w+W, ... for component `lane` (16 independent loads in flight per
     // step, combined in a fixed order); then warp 0 sums the W rows
@@ -734,16 +774,24 @@ picp_stream_kernel(const PicpParams p, const int rounds) {
       }
       s_red[0][lane] = (lane == 29) ? __int_as_float(toti) : tot;
       __syncwarp();
+      PP_ADD(3, t_sum);
+      PP_T(t_solve);
       if (lane == 0) {
         s_keep[3] = picp_solve_local(p, s_red[0], s_T, s_H, s_b) ? 1.f : 0.f;
         s_keep[0] = s_red[0][27];
         s_keep[1] = s_red[0][28];
         s_keep[2] = s_red[0][29];
       }
+      PP_ADD(4, t_solve);
     }
     __syncthreads();
   }
   }  // rounds
+#ifdef PICP_PROFILE
+  if (blockIdx.x == 0 && tid == 0)
+    printf("picp_stream profile (cycles over %d rounds, CTA 0 thread 0): loop %lld  block-reduce %lld  grid.sync %lld  partial-sum %lld  solve %lld\n",
+           rounds, prof[0], prof[1], prof[2], prof[3], prof[4]);
+#endif
   // state write-back (block 0, thread 0): the pose and the LAST linearisation
   if (blockIdx.x == 0 && tid == 0 && rounds > 0) {
     vo_picp_state& st = p.st->s;
@@ -794,7 +842,7 @@ struct vo_picp_s {
   bool force_stream = false;          // VO_PICP_FORCE_STREAM=1: never use the resident kernel
   bool force_general = false;         // VO_PICP_FORCE_GENERAL=1: never use the pinhole kernel
   int32_t min_inliers = 0;
-  DevBuf world_buf, image_buf, pairs_buf, state_buf, partials_buf, check_buf;
+  DevBuf world_buf, image_buf, pairs_buf, state_buf, partials_buf, check_buf, barrier_buf;
   const float* world = nullptr;
   const float* image = nullptr;
   const int32_t* pairs = nullptr;
@@ -830,6 +878,7 @@ static int picp_fill_params(vo_picp_s* h, int keep_outliers, PicpParams* p) {
   p->keep_outliers = keep_outliers ? 1 : 0;
   p->st = h->state_buf.as<PicpDeviceState>();
   p->partials = h->partials_buf.as<float>();
+  p->barrier = h->barrier_buf.as<unsigned int>();
   p->n_pairs_dev = nullptr;
   p->has_pre = 0;
   memset(p->pre, 0, sizeof(p->pre));
@@ -889,6 +938,7 @@ int vo_picp_destroy(vo_picp_t h) {
   h->state_buf.release();
   h->partials_buf.release();
   h->check_buf.release();
+  h->barrier_buf.release();
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return VO_OK;
@@ -1049,6 +1099,7 @@ static int picp_compute_common(vo_picp_t h, int keep_outliers, int rounds, const
   const int grid = picp_pick_grid(h);
   int rc = h->partials_buf.reserve((size_t)2 * grid * PICP_NACC * sizeof(float));
   if (rc) return rc;
+  if ((rc = h->barrier_buf.reserve(128))) return rc;
   PicpParams p;
   picp_fill_params(h, keep_outliers, &p);
   p.n_pairs_dev = n_pairs_dev;
@@ -1100,6 +1151,7 @@ static int picp_compute_common(vo_picp_t h, int keep_outliers, int rounds, const
       p.partials = h->partials_buf.as<float>();
       int rounds_arg = rounds;
       void* args[] = {(void*)&p, (void*)&rounds_arg};
+      VO_CUDA(cudaMemsetAsync(h->barrier_buf.p, 0, 4, h->stream));
       VO_CUDA(cudaLaunchCooperativeKernel((const void*)gk, dim3((unsigned)sms), dim3(PICP_RES_THREADS), args,
                                           PICP_RES_SMEM, h->stream));
       VO_LAUNCH_CHECK();
@@ -1110,6 +1162,7 @@ static int picp_compute_common(vo_picp_t h, int keep_outliers, int rounds, const
   {
     int rounds_arg = rounds;
     void* args[] = {(void*)&p, (void*)&rounds_arg};
+    VO_CUDA(cudaMemsetAsync(h->barrier_buf.p, 0, 4, h->stream));
     VO_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3((unsigned)grid), dim3(PICP_THREADS),
                                         args, PICP_SMEM_BYTES, h->stream));
     VO_LAUNCH_CHECK();

@@ -121,13 +121,19 @@ struct Frame {
   Eigen::Isometry3f world_in_camera;
 };
 
+// Measurement synthesis: ONE batch call of Camera::projectPoints over all the
+// landmarks (src/camera.cpp:16-37, keep_indices = true: rejected points come back as (-1,-1)) instead
+// of a host loop over projectPoint — in the drop-in build that is project_points_kernel on the GPU,
+// in the reference build the reference's own loop; both produce the same bits.  Visible landmarks
+// are listed in ascending id with their appearance copied verbatim, as in the bundled meas-*.dat.
 Frame observe(const World& w, Camera& cam, const Robot& r) {
   Frame f;
   f.world_in_camera = (planar_pose(r.x, r.y, r.theta) * camera_in_robot()).inverse();
   cam.setWorldInCameraPose(f.world_in_camera);
-  Eigen::Vector2f uv;
+  Vector2fVector uv;
+  cam.projectPoints(uv, w.points, true);
   for (size_t i = 0; i < w.points.size(); ++i)
-    if (cam.projectPoint(uv, w.points[i])) f.pc.push_back(PointCloud<2>(uv, w.appearances[i]));
+    if (uv[i].x() >= 0.f) f.pc.push_back(PointCloud<2>(uv[i], w.appearances[i]));
   return f;
 }
 
@@ -190,6 +196,17 @@ float rotation_angle(const Eigen::Matrix3f& R) {
   return std::asin(std::min(1.f, s));
 }
 
+
+// frames (in order) before the estimated step length first falls below half of its initial value:
+// the reference's monocular scale, carried from frame to frame by a two-view triangulation, decays
+// on long sequences in BOTH builds and then collapses to a rotation-only fixed point
+int scale_alive_frames(const std::vector<double>& ratio_in_order) {
+  if (ratio_in_order.empty()) return 0;
+  const double r0 = ratio_in_order.front();
+  for (size_t i = 0; i < ratio_in_order.size(); ++i)
+    if (ratio_in_order[i] < 0.5 * r0) return (int)i;
+  return (int)ratio_in_order.size();
+}
 
 void dump_map(const char* path, const Vector3fVector& pts) {
   FILE* f = std::fopen(path, "w");
@@ -287,6 +304,7 @@ int run_pipeline(int n_landmarks, int n_frames, unsigned seed, int rounds, const
   double rot_mean = 0;
   for (double e : rot_err) rot_mean += e;
   rot_mean /= std::max<size_t>(1, rot_err.size());
+  const int alive = scale_alive_frames(ratio);
   std::sort(ratio.begin(), ratio.end());
   const double ratio_med = ratio.empty() ? 0 : ratio[ratio.size() / 2];
   std::printf(
@@ -295,10 +313,11 @@ int run_pipeline(int n_landmarks, int n_frames, unsigned seed, int rounds, const
       "\"stage_ms_per_frame\": {\"step\": %.4f}, "
       "\"mean_measurements\": %.1f, \"mean_correspondences\": %.1f, \"map_points\": %lld, "
       "\"map_overflow\": %d, "
-      "\"rot_err_mean_rad\": %.3e, \"scale_first_pair\": %.6f, \"scale_median\": %.6f}\n",
+      "\"rot_err_mean_rad\": %.3e, \"scale_first_pair\": %.6f, \"scale_median\": %.6f, "
+      "\"scale_alive_frames\": %d}\n",
       n_landmarks, frames_done, rounds, seed, loop_ms, frames_done / (loop_ms * 1e-3), t_init,
       loop_ms / frames_done, double(sum_meas) / (n_frames - 2), double(sum_corr) / (n_frames - 2),
-      (long long)n_map, overflow, rot_mean, (double)scale, ratio_med);
+      (long long)n_map, overflow, rot_mean, (double)scale, ratio_med, alive);
   return 0;
 }
 #endif
@@ -441,6 +460,7 @@ int main(int argc, char** argv) {
   double rot_mean = 0;
   for (double e : rot_err) rot_mean += e;
   rot_mean /= std::max<size_t>(1, rot_err.size());
+  const int alive = scale_alive_frames(ratio);
   std::sort(ratio.begin(), ratio.end());
   const double ratio_med = ratio.empty() ? 0 : ratio[ratio.size() / 2];
 #ifdef VO_B200_DROPIN
@@ -454,10 +474,11 @@ int main(int argc, char** argv) {
       "\"stage_ms_per_frame\": {\"associate\": %.4f, \"join_transform\": %.4f, \"picp\": %.4f, "
       "\"triangulate\": %.4f, \"map_update\": %.4f}, "
       "\"mean_measurements\": %.1f, \"mean_correspondences\": %.1f, \"map_points\": %zu, "
-      "\"rot_err_mean_rad\": %.3e, \"scale_first_pair\": %.6f, \"scale_median\": %.6f}\n",
+      "\"rot_err_mean_rad\": %.3e, \"scale_first_pair\": %.6f, \"scale_median\": %.6f, "
+      "\"scale_alive_frames\": %d}\n",
       impl, n_landmarks, frames_done, rounds, seed, loop_ms, frames_done / (loop_ms * 1e-3), t_init,
       t_assoc / frames_done, t_join / frames_done, t_picp / frames_done, t_tri / frames_done,
       t_map / frames_done, double(sum_meas) / (n_frames - 2), double(sum_corr) / (n_frames - 2),
-      map.size(), rot_mean, (double)scale, ratio_med);
+      map.size(), rot_mean, (double)scale, ratio_med, alive);
   return 0;
 }
