@@ -10,7 +10,7 @@ Primary line (BASELINE.json config 4, the only config that shards across GPUs):
           (it is the database, uploaded once like the reference builds its kd-tree once per map).
   roofline  the tensor-core filter (csrc/nn_tc.cu): executed tensor flop (2 x 16 per pair) against
             the measured dense bf16/f16 peak, with the algorithmic 30 flop per pair and
-            the TMEM-read fraction (the kernel's real limiter) beside it.
+            the fraction of the ALU-pipe min throughput (the kernel's real limiter) beside it.
   cpu_baseline  the REFERENCE's own bruteForceBestMatch (oracle/_ref, built from its sources) on
             all host cores, on a query sample against the full map.
 Extra objects on the same line (N=1 only): "nn_ffma" (the FP32 FFMA2 filter on the same config,
@@ -45,7 +45,10 @@ TRI_BYTES_PER_CORR = 44.0   # 8 pair + 8 + 8 in, 12 + 8 out
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 RADIUS = 0.1
 NN_TC_FLOP_PER_PAIR = 32.0  # what the tensor-core filter executes: K = 16 (10 + norm terms, padded) x 2
-TMEM_READ_B_PER_CLK_SM = 410.0  # measured tcgen05.ld ceiling with 16 warps (profiles/r02a_tc_probe.md)
+# the epilogue folds every accumulator element into a minimum with 3-input FMNMX3 (2 new elements per
+# instruction) on the ALU pipe, which issues 64 lanes per clock per SM: 128 pairs/clk/SM at best
+# (ncu: the ALU pipe is the busiest unit of nn_tc_filter_kernel, profiles/r02m_ncu_nn_tc.md)
+ALU_MIN_PAIRS_PER_CLK_SM = 128.0
 
 
 def nn_workload(Q, M):
@@ -921,7 +924,7 @@ def ours_arm(args):
             tc_peak = peaks.get("bf16_tflops", 1590.0)
             achieved = NN_TC_FLOP_PER_PAIR * pairs / (kms * 1e-3) / 1e12
             sm_hz = (sampler.summary().get("sm_mhz") or 1965.0) * 1e6
-            tmem_bpc = 4.0 * pairs / (kms * 1e-3) / 148 / sm_hz
+            pairs_pc = pairs / (kms * 1e-3) / 148 / sm_hz
             roof = {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
                     "frac": achieved / tc_peak,
                     **traffic_fields("nn_tc", M == 100_000_000 and Q == 100_000 and world == 1),
@@ -931,10 +934,10 @@ def ours_arm(args):
                     "algorithmic_flop_per_pair": NN_FLOP_PER_PAIR, "algorithmic_tflops": alg_tflops,
                     "algorithmic_frac_of_fp32_peak": alg_tflops / fp32_peak, "fp32_peak": fp32_peak,
                     "fp32_peak_source": peak_src,
-                    "limiter": "tcgen05.ld of the epilogue (4 B per pair)",
-                    "tmem_read_bytes_per_clk_per_sm": tmem_bpc,
-                    "tmem_read_frac": tmem_bpc / TMEM_READ_B_PER_CLK_SM,
-                    "tmem_read_peak_source": "410 B/clk/SM, tools/tc_probe.cu (profiles/r02a_tc_probe.md)",
+                    "limiter": "ALU pipe: the epilogue's 3-input min, 0.5 instruction per pair at 64 lanes/clk/SM",
+                    "pairs_per_clk_per_sm": pairs_pc,
+                    "alu_min_frac": pairs_pc / ALU_MIN_PAIRS_PER_CLK_SM,
+                    "tmem_read_bytes_per_clk_per_sm": 4.0 * pairs_pc,
                     "rescans_per_query": nn_rescans / max(nq, 1), "kernel_ms": kms}
         else:
             roof = {"bound": "fp32", "achieved": alg_tflops, "peak": fp32_peak, "unit": "TFLOP/s",

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turn the ncu artefacts a gpurun call left in gpurun_out/ into the tracked summaries under
 profiles/.   Usage: make_profiles.py <tag in gpurun_out, e.g. r1e> <round label, e.g. r01>
-Reads   gpurun_out/<tag>_launches.csv, gpurun_out/<tag>_{nn,picp,tri}.ncu-rep
+Reads   gpurun_out/<tag>_launches.csv, gpurun_out/<tag>_{nn,nn_tc,picp,picpres,tri}.ncu-rep
 Writes  profiles/<label>_launches.csv, profiles/<label>_launches.md, profiles/<label>_<k>.md"""
 import collections, csv, io, os, shutil, subprocess, sys
 
@@ -36,7 +36,7 @@ if os.path.exists(lc):
 
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 traffic = {}
-for k in ("nn", "picp", "picpres", "tri"):
+for k in ("nn", "nn_tc", "picp", "picpres", "tri"):
     rep = os.path.join(G, f"{tag}_{k}.ncu-rep")
     if not os.path.exists(rep): continue
     raw = list(csv.reader(io.StringIO(run("ncu", "-i", rep, "--page", "raw", "--csv"))))
@@ -48,7 +48,7 @@ for k in ("nn", "picp", "picpres", "tri"):
                   "gpu_time_ns_under_ncu": float(col["gpu__time_duration.sum"][1]) *
                   {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}[col["gpu__time_duration.sum"][0]],
                   "report": f"gpurun_out/{tag}_{k}.ncu-rep"}
-for k in ("nn", "picp", "picpres", "tri"):
+for k in ("nn", "nn_tc", "picp", "picpres", "tri"):
     rep = os.path.join(G, f"{tag}_{k}.ncu-rep")
     if not os.path.exists(rep): continue
     out = [f"# {label}: `ncu --set full --clock-control none --import-source on` of the {k} kernel\n",

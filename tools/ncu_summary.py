@@ -23,6 +23,7 @@ WANT = [
     "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum",
     "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__cycles_elapsed.avg.per_second",
 ]
 rep = sys.argv[1]

@@ -31,10 +31,13 @@
 //     releases the buffer, folds the 64 values into a minimum with 3-input mins and tests it.
 // Measured on hardware (tools/tc_probe.cu, profiles/r02a_tc_probe.md): one thread issues at most one
 // tcgen05.mma per 114 cycles whatever its width, several threads issue in parallel, issue-to-
-// barrier latency is 288 cycles, the f16 MMA itself takes N/2 cycles, and 16 warps read TMEM at
-// 410 B/clk/SM.  The last figure is the kernel's ceiling (4 B per pair: 0.34 s for 1e13 pairs); the
-// kernel reaches 48 % of it (0.70 s) — each warp serialises barrier wait, load latency, fold and
-// test, and 64 data registers per thread leave no room to overlap them.
+// barrier latency is 288 cycles, the f16 MMA itself takes N/2 cycles, a dependent tcgen05.ld.x32
+// 35 cycles.  The ceiling is neither of those: every accumulator element has to enter a minimum, the
+// 3-input FMNMX3 takes two new elements per instruction and executes on the ALU pipe, 64 lanes per
+// clock per SM — 128 pairs/clk/SM, 0.27 s for 1e13 pairs (ncu: ALU pipe 76 % busy, the busiest unit,
+// profiles/r02m_ncu_nn_tc.md).  The kernel reaches 44 % of that (0.62 s): 33 of the ~60 instructions
+// of an epilogue iteration are the mins, the rest is barrier / address bookkeeping on the same pipe,
+// and 96 registers per thread (608 threads fill the file) leave no room for more warps.
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -263,6 +266,30 @@ __device__ __forceinline__ float tc_rescan_warp(const float4* __restrict__ packe
   return found;
 }
 
+// The rare path of the epilogue (inlined: a call boundary measured 1.5 % slower): the warp takes its
+// flagged queries (lane = query) one by one and re-scans the 64 rows starting at row0 for each.  q0 = index of lane 0's query; thr / eps = the 32 thresholds and
+// margins of this warp's queries in shared memory.
+__device__ __forceinline__ void tc_rescan_flagged(const NNTCParams& p, bool flagged, int64_t q0, int64_t row0,
+                                               float mm_max, float* thr, const float* eps) {
+  const int lane = threadIdx.x & 31;
+  unsigned pending = __ballot_sync(0xffffffffu, flagged);
+  while (pending) {
+    const int src = __ffs(pending) - 1;
+    pending &= pending - 1;
+    const int64_t qi = q0 + src;
+    const float found = tc_rescan_warp(p.packed, row0, p.n_rows, p.queries + qi * (int64_t)p.query_stride + p.skip,
+                                       p.bound, mm_max, p.keys + qi);
+    if (lane == 0) {
+      // later rows only matter if they can reach d2 <= found.  Four warps share a query's threshold;
+      // a lost update only leaves it higher than necessary (more re-scans).
+      const float nt_thr = found + eps[src];
+      if (nt_thr < thr[src]) thr[src] = nt_thr;
+      atomicAdd(p.stats, 1ull);
+    }
+  }
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCParams p) {
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   unsigned char* sA = tc_smem;
@@ -417,56 +444,76 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
       // ===== epilogue of pipeline `pipe` (8 warps): drains buffers pipe and pipe+2 in turn, one being
       // refilled by the tensor core while the other is read; thread = TMEM lane = query, and the two
       // warps of a lane quadrant split the 128 columns ============================================
+      // ncu (profiles/r02m_ncu_nn_tc.md): the ALU pipe — where FMNMX3 executes, 64 lanes per clock per
+      // SM — is the busiest unit (76 %), and only a third of the instructions are the mins.  Everything
+      // else in this loop is therefore kept to a minimum: barrier and TMEM addresses are computed
+      // once, the buffer/phase bookkeeping is two XORs, the threshold is read before the wait, the
+      // arrive is predicated (no branch) and the re-scan hides behind one warp vote.
       const int pipe = warp / TC_PIPE_WARPS, w8 = warp % TC_PIPE_WARPS;
       const int quad = w8 & 3, half = w8 >> 2;
       const uint32_t tlane = ((uint32_t)(quad * 32) << 16) + (uint32_t)half * 64;
-      uint32_t n_acc = acc_n;
+      // buffer `sel` of this pipeline: TMEM columns + sel * 256, barriers + sel * 16 bytes.  The
+      // addresses go through an opaque move so that ptxas keeps them in registers instead of
+      // re-deriving them (generic -> shared conversion, lane arithmetic) in every iteration.
+      uint32_t t_addr0 = tlane + (uint32_t)pipe * TC_SUB;
+      uint32_t full_addr0 = smem_u32(&tfull[pipe]), empty_addr0 = smem_u32(&tempty[pipe]);
+      uint32_t thr_addr0 = smem_u32(thr_s + quad * 32 + lane);
+      asm volatile("mov.u32 %0, %0;\nmov.u32 %1, %1;\nmov.u32 %2, %2;\nmov.u32 %3, %3;"
+                   : "+r"(t_addr0), "+r"(full_addr0), "+r"(empty_addr0), "+r"(thr_addr0));
+      const uint32_t arrive_lane = lane;
+      uint32_t sel = acc_n & 1u, par = (acc_n >> 1) & 1u;  // buffer of this pipeline, phase of its barrier
       for (int64_t unit = 0; unit < nt; ++unit) {
-        for (int a = 0; a < qt; ++a, ++n_acc) {
-          const int buf = pipe + TC_PIPES * (int)(n_acc & 1u);
+        uint32_t thr_addr = thr_addr0;
+        for (int a = 0; a < qt; ++a, thr_addr += 128 * sizeof(float)) {
           TC_PROF_T(pa);
-          const int ql = a * 128 + quad * 32 + lane;
-          const float my_thr = thr_s[ql];  // read before the wait: its latency hides behind it
-          mbar_wait(&tfull[buf], (n_acc >> 1) & 1u);
+          float my_thr;  // read before the wait: its latency hides behind it
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(my_thr) : "r"(thr_addr) : "memory");
+          {
+            uint32_t ok;
+            do {
+              asm volatile(
+                  "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                  : "=r"(ok)
+                  : "r"(full_addr0 + sel * (TC_PIPES * 8u)), "r"(par)
+                  : "memory");
+            } while (!ok);
+          }
           TC_PROF_ADD(1, pa);
           TC_PROF_T(pb);
           tc_fence_after();
-          const uint32_t taddr = tlane + (uint32_t)buf * TC_SUB;
-          uint32_t r0[32], r1[32];
-          tc_ld32(taddr, r0);
-          tc_ld32(taddr + 32, r1);
-          tc_wait_ld();
-          // the buffer may be overwritten as soon as all eight warps have read it
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[buf]);
-          TC_PROF_ADD(2, pb);
-          TC_PROF_T(pc);
+          // two 32-column loads through ONE register buffer: the dependent tcgen05.ld latency is only
+          // ~35 cycles (tools/tc_probe.cu), and 32 fewer live registers let ptxas keep every address
+          // of this loop in registers
+          const uint32_t taddr = t_addr0 + sel * (uint32_t)(TC_PIPES * TC_SUB);
           float m4[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
-          tc_fold(m4, r0);
-          tc_fold(m4, r1);
+          {
+            uint32_t r[32];
+            tc_ld32(taddr, r);
+            tc_wait_ld();
+            tc_fold(m4, r);
+            tc_ld32(taddr + 32, r);
+            tc_wait_ld();
+            // the buffer may be overwritten as soon as all eight warps have read it
+            tc_fence_before();
+            __syncwarp();
+            asm volatile(
+                "{\n.reg .pred p;\nsetp.eq.u32 p, %1, 0;\n@p mbarrier.arrive.shared::cta.b64 _, [%0];\n}" ::"r"(
+                    empty_addr0 + sel * (TC_PIPES * 8u)),
+                "r"(arrive_lane)
+                : "memory");
+            TC_PROF_ADD(2, pb);
+            tc_fold(m4, r);
+          }
+          TC_PROF_T(pc);
           const float mn = fminf(tc_min3(m4[0], m4[1], m4[2]), m4[3]);
+          par ^= sel;  // the phase flips every second accumulator
+          sel ^= 1u;
 
           // `<=`: a query whose threshold is +inf (norm too large for f16) is always re-scanned
-          unsigned pending = __ballot_sync(0xffffffffu, mn <= my_thr);
-          while (pending) {
-            const int src = __ffs(pending) - 1;
-            pending &= pending - 1;
-            const int qs = a * 128 + quad * 32 + src;
-            const int64_t qi = qbase + qs;
-            const int64_t row0 = (t0 + unit) * TC_BN + pipe * TC_SUB + half * 64;
-            const float found = tc_rescan_warp(p.packed, row0, p.n_rows,
-                                               p.queries + qi * (int64_t)p.query_stride + p.skip, p.bound,
-                                               mm_max, p.keys + qi);
-            if (lane == 0) {
-              // later rows only matter if they can reach d2 <= found.  Four warps share a query's
-              // threshold; a lost update only leaves it higher than necessary (more re-scans).
-              const float nt_thr = found + eps_s[qs];
-              if (nt_thr < thr_s[qs]) thr_s[qs] = nt_thr;
-              atomicAdd(p.stats, 1ull);
-            }
-          }
-          __syncwarp();
+          if (__any_sync(0xffffffffu, mn <= my_thr))
+            tc_rescan_flagged(p, mn <= my_thr, qbase + a * 128 + quad * 32,
+                              (t0 + unit) * TC_BN + pipe * TC_SUB + half * 64, mm_max,
+                              thr_s + a * 128 + quad * 32, eps_s + a * 128 + quad * 32);
           TC_PROF_ADD(3, pc);
         }
       }
