@@ -186,6 +186,32 @@ def test_compute_many_rounds_equals_one_round_loop(vo, synth):
     b.close()
 
 
+@pytest.mark.parametrize("n,keep,outliers", [(300, False, 0.0), (5000, False, 0.0), (5000, True, 0.2),
+                                             (60000, False, 0.05), (200001, False, 0.0)])
+def test_early_out_is_exact(vo, synth, monkeypatch, n, keep, outliers):
+    """The resident kernel stops iterating once the pose sequence repeats (period 1 or 2) and
+    returns the state the remaining rounds WOULD have produced; VO_PICP_NO_EARLY_OUT=1 runs them all.
+    Every field of the state must be bit-identical, for odd and even round counts."""
+    pr = synth.picp_problem(max(n, 400) * 2, seed=41, outlier_frac=outliers)
+    pairs = pr["pairs"][:n]
+    cam = vo.Camera(pr["rows"], pr["cols"], pr["z_near"], pr["z_far"], pr["K"], np.eye(4))
+    for rounds in (99, 100):
+        states = []
+        for no_early in ("0", "1"):
+            monkeypatch.setenv("VO_PICP_NO_EARLY_OUT", no_early)
+            s = vo.PICPSolver(0)
+            s.setKernelThreshold(2000.0)
+            s.init(cam, pr["world"], pr["image"])
+            s.set_correspondences(pairs)
+            s.compute(keep, rounds)
+            st = s.state()
+            states.append((list(st.T), list(st.H), list(st.b), st.chi_inliers, st.chi_outliers,
+                           st.num_inliers, st.rounds_done, st.last_ok))
+            s.close()
+        assert states[0] == states[1], (n, rounds)
+        assert states[0][6] == rounds
+
+
 def test_compute_graph_path_equals_launch_loop_streaming(vo, synth, monkeypatch):
     """The same check on the streaming kernel (one cooperative launch for 6 rounds vs 6 launches)."""
     monkeypatch.setenv("VO_PICP_FORCE_STREAM", "1")

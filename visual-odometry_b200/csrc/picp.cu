@@ -60,6 +60,7 @@ struct PicpParams {
   PicpDeviceState* st;
   float* partials;                   // [2][gridDim.x][PICP_NACC]
   unsigned int* barrier;             // grid-barrier arrival counter, zeroed before every launch
+  int early_out;                     // resident kernel: stop iterating once the pose sequence repeats
   // frame-pipeline extensions (resident kernel only)
   const int* n_pairs_dev;            // if set: the correspondence count lives on the device
   int has_pre;                       // if set: world points are moved by `pre` while gathered
@@ -316,6 +317,9 @@ __device__ __forceinline__ constexpr uint32_t picp_prs_off(int slot, int u) {
 //   system and updates its own copy of the pose (identical instruction stream => identical bits in
 //   every CTA, so no second barrier and no broadcast).
 // Global memory is touched at the start (gather) and at the end (state write-back) only.
+constexpr int PICP_HIST = 2;          // rounds of history kept for the exact early-out (8 was tried: at 8e3
+                                      // correspondences the pose never re-enters a cycle that short within 100
+                                      // rounds, and the longer comparison cost 6 % of a frame)
 constexpr int PICP_RES_THREADS = 512;
 constexpr int PICP_RES_CLUSTER = 8;                       // portable maximum
 constexpr int PICP_RES_SLOTS = 4096;                      // packed two-point slots per CTA
@@ -451,7 +455,17 @@ picp_resident_kernel(const PicpParams p, const int rounds) {
   if (GRID) __syncthreads();
   else cluster.sync();
 
-  __shared__ float s_H[36], s_b[6], s_keep[4];  // last linearisation, written by thread 0
+  // Results of the last PICP_HIST rounds, slot [round % PICP_HIST]: pose after the round, the round's
+  // linearisation (H with damping, b) and its statistics — written by thread 0.  Early-out:
+  // Gauss-Newton in FP32 is a deterministic map of the pose, so once the pose after a round equals
+  // (bit for bit) the pose k <= PICP_HIST rounds earlier, the iteration has entered a cycle of
+  // period k and the state after all `rounds` rounds is one of the k stored ones — known without
+  // running them (vo_complete runs 100 rounds on frames that settle, at FP32 resolution, in 10-30).
+  __shared__ float s_Ts[PICP_HIST][12], s_H[PICP_HIST][36], s_b[PICP_HIST][6], s_keep[PICP_HIST][4];
+  __shared__ int s_stop, s_final;
+  if (tid < 12) s_Ts[PICP_HIST - 1][tid] = s_T[tid];  // "round -1": the initial pose
+  if (tid == 0) s_stop = 0, s_final = (rounds - 1) % PICP_HIST;
+  __syncthreads();
   for (int round = 0; round < rounds; ++round) {
     PicpConsts c;
 #pragma unroll
@@ -533,32 +547,56 @@ picp_resident_kernel(const PicpParams p, const int rounds) {
       s_red[0][lane] = t;
       __syncwarp();
       if (lane == 0) {
-        s_keep[3] = picp_solve_local(p, s_red[0], s_T, s_H, s_b) ? 1.f : 0.f;
-        s_keep[0] = s_red[0][27];
-        s_keep[1] = s_red[0][28];
-        s_keep[2] = s_red[0][29];
+        const int cur = round % PICP_HIST;
+        s_keep[cur][3] = picp_solve_local(p, s_red[0], s_T, s_H[cur], s_b[cur]) ? 1.f : 0.f;
+        s_keep[cur][0] = s_red[0][27];
+        s_keep[cur][1] = s_red[0][28];
+        s_keep[cur][2] = s_red[0][29];
+        // smallest k with pose(after this round) == pose(after round - k); round - k == -1 is the
+        // initial pose.  Slot `cur` still holds round - PICP_HIST, so k == PICP_HIST is checked first.
+        int period = 0;
+        if (p.early_out && round + 1 < rounds) {
+          for (int k = PICP_HIST; k >= 1; --k) {
+            if (round - k < -1) continue;
+            const float* old = s_Ts[(round - k + PICP_HIST) % PICP_HIST];
+            bool same = true;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) same = same && __float_as_uint(s_T[i]) == __float_as_uint(old[i]);
+            if (same) period = k;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 12; ++i) s_Ts[cur][i] = s_T[i];
+        if (period > 0) {
+          // states repeat with this period: S(round + j) == S(round + j - period)
+          const int m = (rounds - 1 - round) % period;
+          s_stop = 1;
+          s_final = m == 0 ? cur : (round + m - period + PICP_HIST) % PICP_HIST;
+        }
       }
     }
     __syncthreads();
+    if (s_stop) break;  // the same decision in every CTA: they hold identical copies of the pose
   }
   // state write-back (CTA 0, thread 0): the pose and the LAST linearisation
   if (rank == 0 && tid == 0 && rounds > 0) {
     vo_picp_state& s = p.st->s;
+    const int fin = s_final;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int i = 0; i < 3; ++i) s.T[j * 4 + i] = s_T[j * 3 + i];
+      for (int i = 0; i < 3; ++i) s.T[j * 4 + i] = s_Ts[fin][j * 3 + i];
     s.T[3] = s.T[7] = s.T[11] = 0.f;
     s.T[15] = 1.f;
 #pragma unroll
-    for (int i = 0; i < 36; ++i) s.H[i] = s_H[i];
+    for (int i = 0; i < 36; ++i) s.H[i] = s_H[fin][i];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) s.b[i] = s_b[i];
-    s.chi_inliers = s_keep[0];
-    s.chi_outliers = s_keep[1];
-    s.num_inliers = __float_as_int(s_keep[2]);
+    for (int i = 0; i < 6; ++i) s.b[i] = s_b[fin][i];
+    s.chi_inliers = s_keep[fin][0];
+    s.chi_outliers = s_keep[fin][1];
+    s.num_inliers = __float_as_int(s_keep[fin][2]);
     s.rounds_done += rounds;
-    s.last_ok = s_keep[3] != 0.f ? 1 : 0;
+    s.last_ok = s_keep[fin][3] != 0.f ? 1 : 0;
   }
   // no CTA may exit while a peer can still push into its shared memory
   if (!GRID) cluster.sync();
@@ -841,6 +879,7 @@ struct vo_picp_s {
   bool smem_opted_in = false;
   bool force_stream = false;          // VO_PICP_FORCE_STREAM=1: never use the resident kernel
   bool force_general = false;         // VO_PICP_FORCE_GENERAL=1: never use the pinhole kernel
+  bool early_out = true;              // VO_PICP_NO_EARLY_OUT=1: always run every requested round
   int32_t min_inliers = 0;
   DevBuf world_buf, image_buf, pairs_buf, state_buf, partials_buf, check_buf, barrier_buf;
   const float* world = nullptr;
@@ -879,6 +918,7 @@ static int picp_fill_params(vo_picp_s* h, int keep_outliers, PicpParams* p) {
   p->st = h->state_buf.as<PicpDeviceState>();
   p->partials = h->partials_buf.as<float>();
   p->barrier = h->barrier_buf.as<unsigned int>();
+  p->early_out = h->early_out ? 1 : 0;
   p->n_pairs_dev = nullptr;
   p->has_pre = 0;
   memset(p->pre, 0, sizeof(p->pre));
@@ -924,6 +964,8 @@ int vo_picp_create(vo_picp_t* out, int device) {
   h->force_general = fg != nullptr && fg[0] == '1';
   const char* fs = getenv("VO_PICP_FORCE_STREAM");
   h->force_stream = fs != nullptr && fs[0] == '1';
+  const char* ne = getenv("VO_PICP_NO_EARLY_OUT");
+  h->early_out = !(ne != nullptr && ne[0] == '1');
   *out = h;
   return VO_OK;
 }
