@@ -186,6 +186,45 @@ def test_compute_many_rounds_equals_one_round_loop(vo, synth):
     b.close()
 
 
+@pytest.mark.parametrize("order", ["sorted", "reversed", "shuffled", "blocks"])
+def test_window_streaming_kernel_any_correspondence_order(vo, oracle, synth, monkeypatch, order):
+    """The two streaming kernels: picp_stream_kernel (per-thread cp.async gathers, the default) and
+    picp_window_kernel (VO_PICP_STREAM_V2=1: the window of world / image points a tile of pairs
+    references is staged with bulk copies, points outside it are gathered from global memory).
+    Every correspondence order must give the float64 truth through both, and the same H up to
+    summation order."""
+    pr = synth.picp_problem(150000, seed=43, outlier_frac=0.02)
+    pairs = pr["pairs"]
+    rng = np.random.RandomState(1)
+    if order == "reversed":
+        pairs = pairs[::-1].copy()
+    elif order == "shuffled":
+        pairs = pairs[rng.permutation(len(pairs))]
+    elif order == "blocks":  # sorted inside blocks of 1000, blocks in random order: tiles straddle two windows
+        nb = len(pairs) // 1000
+        pairs = np.concatenate([pairs[b * 1000:(b + 1) * 1000] for b in rng.permutation(nb)] + [pairs[nb * 1000:]])
+    monkeypatch.setenv("VO_PICP_FORCE_STREAM", "1")
+    res = {}
+    for v1 in ("0", "1"):
+        monkeypatch.setenv("VO_PICP_STREAM_V2", v1)
+        s, o = _mk(vo, oracle, pr, 2000.0)
+        s.set_correspondences(pairs)
+        s.compute(False, 1)
+        st1 = s.state()
+        s.compute(False, 9)
+        res[v1] = (np.array(st1.H[:]).reshape(6, 6).T, np.array(st1.b[:]), st1.num_inliers, s.pose())
+        if v1 == "1":
+            o.one_round_f64(pairs, False)
+            assert st1.num_inliers == int(o.stats64[2])
+            assert rel_blocks(res[v1][0], o.H64m(), res[v1][1], o.b64) <= TOL
+            for _ in range(9):
+                o.one_round_f64(pairs, False)
+            assert rel_pose(res[v1][3], o.pose64()) <= TOL
+        s.close()
+    assert res["0"][2] == res["1"][2]
+    assert rel_blocks(res["0"][0], res["1"][0], res["0"][1], res["1"][1]) <= TOL
+
+
 @pytest.mark.parametrize("n,keep,outliers", [(300, False, 0.0), (5000, False, 0.0), (5000, True, 0.2),
                                              (60000, False, 0.05), (200001, False, 0.0)])
 def test_early_out_is_exact(vo, synth, monkeypatch, n, keep, outliers):

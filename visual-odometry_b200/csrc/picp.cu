@@ -18,6 +18,7 @@
 // at a time in the lanes of packed FP32 pairs.  Reductions are fixed-order (no float atomics:
 // results are run-to-run deterministic); the damping, the pivoted 6x6 LDL^T solve, v2tEuler(dx)
 // and the pose update run on the device, so there is no host round-trip between rounds.
+#include <limits.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -851,6 +852,315 @@ picp_stream_kernel(const PicpParams p, const int rounds) {
   }
 }
 
+// ---- streaming kernel, second generation: TMA windows instead of per-thread gathers ----------------
+// What limits picp_stream_kernel is not HBM: with its arithmetic removed it still needs 44 us per
+// round for 279 MB (6.3 TB/s), and the arithmetic adds 8 us that do not overlap — 6 cp.async and
+// ~15 address/LDS instructions per point compete with 80 arithmetic ones for the issue slots of 12
+// warps.  Correspondence lists that reach this size are monotone or nearly so (the synthetic sweeps
+// of picp_solver_test.cpp:8-26 pair point i with point i): a tile of 1536 consecutive pairs then
+// references a WINDOW of the world / image arrays barely larger than the tile.  So a producer warp
+//   1. GUESSES the windows from the tile's first and last pair (PW_MAX points from the smaller index
+//      on; the two pairs are read with plain loads one tile earlier),
+//   2. requests the tile's pairs (12 KB) and both windows with three bulk copies (cp.async.bulk) on one
+//      mbarrier, three tiles ahead of the arithmetic,
+// and the 12 arithmetic warps read pairs and points from shared memory, spending their issue slots
+// on arithmetic.  The guess needs no proof: every thread checks that its pair's indices fall inside
+// the staged windows and gathers the point from global memory itself when they do not (a shuffled
+// list, the ragged end of the list, a window cut short by the end of an array) — correct for any
+// correspondence list, just slower.  The producer runs ahead across round boundaries: the next
+// round's first tiles land while the grid reduces and solves.
+// RESULT (B200, 9.97e6 correspondences, 10 rounds): 61.3 us per round against 57.4 for
+// picp_stream_kernel — the instruction count per point drops as intended, but what the arithmetic
+// warps lack is not issue slots: at 128 registers only 3 of them fit per scheduler and the ~25-deep
+// dependent chain of projection -> reciprocal -> Jacobian leaves the issue port idle half the time
+// either way, and a tile-wide barrier marches all twelve warps in step where the per-thread rings
+// let them drift apart.  Kept opt-in (VO_PICP_STREAM_V2=1) and tested, not the default.
+constexpr int PW_THREADS = 384;                 // arithmetic threads
+constexpr int PW_TILE = PW_THREADS * 4;         // pairs per tile
+constexpr int PW_MAX = 2048;                    // points per window
+constexpr int PW_STAGES = 4;
+constexpr uint32_t PW_PAIR_BYTES = PW_TILE * 8;
+constexpr uint32_t PW_WORLD_BYTES = PW_MAX * 12 + 32;
+constexpr uint32_t PW_IMAGE_BYTES = PW_MAX * 8 + 32;
+constexpr uint32_t PW_STAGE_BYTES = PW_PAIR_BYTES + PW_WORLD_BYTES + PW_IMAGE_BYTES;
+constexpr size_t PW_SMEM_BYTES = (size_t)PW_STAGES * PW_STAGE_BYTES;
+
+struct PwTile {      // what the producer tells the arithmetic warps about a staged tile
+  int pairs_staged;  // 0: ragged last tile, pairs are read from global memory too
+  int world_first;   // index of the first world / image point held by the windows ...
+  int image_first;
+  int world_count;   // ... and how many complete points each window holds (0: nothing staged)
+  int image_count;
+  int world_skip;    // bytes between the window's 16-byte aligned start and that first element
+  int image_skip;
+};
+
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PW_THREADS) : "memory"); }
+
+template <bool PINHOLE, bool KEEP>
+__global__ void __launch_bounds__(PW_THREADS + 32, 1)
+picp_window_kernel(const PicpParams p, const int rounds, const int64_t n_world, const int64_t n_image) {
+  extern __shared__ __align__(128) unsigned char pw_smem[];
+  __shared__ uint64_t full[PW_STAGES], empty[PW_STAGES];
+  __shared__ PwTile s_tile[PW_STAGES];
+  __shared__ float s_red[PW_THREADS / 32][PICP_NACC];
+  __shared__ float s_T[12], s_H[36], s_b[6], s_keep[4];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int64_t n = p.n_pairs;
+  const int64_t n_tiles = (n + PW_TILE - 1) / PW_TILE;
+  // tiles blockIdx.x, blockIdx.x + grid, ... of every round, as one sequence over all rounds
+  const int64_t mine = (int64_t)blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t total = mine * rounds;
+  if (tid == 0) {
+    for (int s = 0; s < PW_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], PW_THREADS / 32);
+    }
+    mbar_fence_init();
+  }
+  if (tid < 12) s_T[tid] = p.st->s.T[(tid / 3) * 4 + (tid % 3)];
+  __syncthreads();
+
+  if (warp == PW_THREADS / 32) {
+    // ===== producer (one thread) =========================================================================
+    // A tile's pairs and both windows are requested together, PW_STAGES - 1 tiles ahead of the
+    // arithmetic: the windows are guessed from the tile's first and last pair, which are read with
+    // two plain loads one iteration before they are needed.
+    if (lane == 0) {
+      auto tile_of = [&](int64_t k) { return (int64_t)blockIdx.x + (k % mine) * gridDim.x; };
+      int2 nf = make_int2(0, 0), nl = make_int2(0, 0);
+      auto peek = [&](int64_t k) {
+        const int64_t t = tile_of(k);
+        if ((t + 1) * PW_TILE <= n) {
+          nf = __ldg(p.pairs + t * PW_TILE);
+          nl = __ldg(p.pairs + t * PW_TILE + PW_TILE - 1);
+        }
+      };
+      if (total > 0) peek(0);
+      for (int64_t k = 0; k < total; ++k) {
+        const int s = (int)(k % PW_STAGES);
+        const int2 first = nf, last = nl;
+        if (k + 1 < total) peek(k + 1);
+        mbar_wait(&empty[s], (uint32_t)(((k / PW_STAGES) & 1) ^ 1));
+        const int64_t t = tile_of(k);
+        const bool whole = (t + 1) * PW_TILE <= n;
+        PwTile d;
+        d.pairs_staged = whole ? 1 : 0;
+        d.world_first = d.image_first = d.world_count = d.image_count = d.world_skip = d.image_skip = 0;
+        uint32_t bytes = whole ? PW_PAIR_BYTES : 0u;
+        int64_t w0 = 0, w1 = 0, i0 = 0, i1 = 0;
+        bool windows = false;
+        if (whole) {
+          const int64_t lo_w = max(0, min(first.y, last.y)), lo_i = max(0, min(first.x, last.x));
+          // byte ranges of the windows: from the 16-byte boundary below the first element, PW_MAX
+          // points long, cut at the last 16-byte boundary inside the array
+          w0 = (lo_w * 12) & ~15LL;
+          w1 = min((long long)(w0 + (int64_t)PW_MAX * 12), (long long)((n_world * 12) & ~15LL));
+          i0 = (lo_i * 8) & ~15LL;
+          i1 = min((long long)(i0 + (int64_t)PW_MAX * 8), (long long)((n_image * 8) & ~15LL));
+          if (w1 > w0 && i1 > i0) {
+            windows = true;
+            d.world_first = (int)lo_w, d.image_first = (int)lo_i;
+            d.world_count = (int)max(0LL, (long long)(w1 / 12 - lo_w));
+            d.image_count = (int)max(0LL, (long long)(i1 / 8 - lo_i));
+            d.world_skip = (int)(lo_w * 12 - w0), d.image_skip = (int)(lo_i * 8 - i0);
+            bytes += (uint32_t)((w1 - w0) + (i1 - i0));
+          }
+        }
+        s_tile[s] = d;
+        unsigned char* base = pw_smem + (size_t)s * PW_STAGE_BYTES;
+        if (bytes) mbar_arrive_expect_tx(&full[s], bytes);
+        else mbar_arrive(&full[s]);
+        if (whole) tma_load_1d(base, p.pairs + t * PW_TILE, PW_PAIR_BYTES, &full[s]);
+        if (windows) {
+          tma_load_1d(base + PW_PAIR_BYTES, reinterpret_cast<const unsigned char*>(p.world) + w0, (uint32_t)(w1 - w0),
+                      &full[s]);
+          tma_load_1d(base + PW_PAIR_BYTES + PW_WORLD_BYTES, reinterpret_cast<const unsigned char*>(p.image) + i0,
+                      (uint32_t)(i1 - i0), &full[s]);
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== arithmetic warps ==================================================================================
+  int64_t k = 0;  // position in this CTA's tile sequence
+  for (int round = 0; round < rounds; ++round) {
+    PicpConsts c;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) c.T[i] = s_T[i];
+    PicpAcc a;
+#pragma unroll
+    for (int i = 0; i < 21; ++i) a.h[i] = 0ull;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) a.b[i] = 0ull;
+    a.chi_in = a.chi_out = 0ull;
+    a.n_in = 0;
+
+    for (int64_t m = 0; m < mine; ++m, ++k) {
+      const int s = (int)(k % PW_STAGES);
+      const uint32_t ph = (uint32_t)((k / PW_STAGES) & 1);
+      mbar_wait(&full[s], ph);
+      const unsigned char* base = pw_smem + (size_t)s * PW_STAGE_BYTES;
+      const PwTile d = s_tile[s];
+      const int64_t t0 = ((int64_t)blockIdx.x + m * gridDim.x) * PW_TILE;
+      // thread t takes pairs t, t + 384, t + 768, t + 1152 of the tile: the first two and the last
+      // two share the lanes of a packed pair
+      float wx[4], wy[4], wz[4], mu[4], mv[4];
+      bool have[4];
+      {
+        const int2* pr = reinterpret_cast<const int2*>(base);
+        const unsigned char* wwin = base + PW_PAIR_BYTES + d.world_skip;
+        const unsigned char* iwin = base + PW_PAIR_BYTES + PW_WORLD_BYTES + d.image_skip;
+        int2 v[4];
+        unsigned dw[4], di[4];
+        bool inside = d.pairs_staged != 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t i = t0 + u * PW_THREADS + tid;
+          have[u] = i < n;
+          v[u] = d.pairs_staged ? pr[u * PW_THREADS + tid] : __ldg(p.pairs + (have[u] ? i : 0));
+          dw[u] = (unsigned)(v[u].y - d.world_first), di[u] = (unsigned)(v[u].x - d.image_first);
+          inside = inside && dw[u] < (unsigned)d.world_count && di[u] < (unsigned)d.image_count;
+        }
+        if (__all_sync(0xffffffffu, inside)) {
+          // the common case, branch-free: every point of the warp is in the staged windows
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float* w = reinterpret_cast<const float*>(wwin + (size_t)dw[u] * 12);
+            const float2 im = *reinterpret_cast<const float2*>(iwin + (size_t)di[u] * 8);
+            wx[u] = w[0], wy[u] = w[1], wz[u] = w[2], mu[u] = im.x, mv[u] = im.y;
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (dw[u] < (unsigned)d.world_count) {
+              const float* w = reinterpret_cast<const float*>(wwin + (size_t)dw[u] * 12);
+              wx[u] = w[0], wy[u] = w[1], wz[u] = w[2];
+            } else {
+              const float* w = p.world + 3 * (int64_t)v[u].y;
+              wx[u] = __ldg(w), wy[u] = __ldg(w + 1), wz[u] = __ldg(w + 2);
+            }
+            if (di[u] < (unsigned)d.image_count) {
+              const float2 im = *reinterpret_cast<const float2*>(iwin + (size_t)di[u] * 8);
+              mu[u] = im.x, mv[u] = im.y;
+            } else {
+              const float2 im = __ldg(reinterpret_cast<const float2*>(p.image) + v[u].x);
+              mu[u] = im.x, mv[u] = im.y;
+            }
+          }
+        }
+      }
+      // this warp is done with the stage as soon as its operands are in registers
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+#pragma unroll
+      for (int pi = 0; pi < 2; ++pi)
+        picp_point2<PINHOLE, KEEP>(p, c, f2_pack(wx[2 * pi], wx[2 * pi + 1]), f2_pack(wy[2 * pi], wy[2 * pi + 1]),
+                                   f2_pack(wz[2 * pi], wz[2 * pi + 1]), f2_pack(mu[2 * pi], mu[2 * pi + 1]),
+                                   f2_pack(mv[2 * pi], mv[2 * pi + 1]), have[2 * pi + 1], a, have[2 * pi]);
+    }
+
+    // ---- block reduction, grid barrier, cross-CTA sum, solve: as in picp_stream_kernel ---------------
+    {
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 29; ++i) {
+        float lo, hi;
+        f2_unpack(i < 21 ? a.h[i] : (i < 27 ? a.b[i - 21] : (i == 27 ? a.chi_in : a.chi_out)), lo, hi);
+        v[i] = lo + hi;
+      }
+      v[29] = (float)a.n_in;
+      v[30] = v[31] = 0.f;
+      float mine_sum = warp_reduce_transposed(v);
+      if (lane == 29) mine_sum = __int_as_float((int)mine_sum);
+      s_red[warp][lane] = mine_sum;
+    }
+    consumer_sync();
+    if (warp == 0) {
+      if (lane < 30) {
+        float* out = p.partials + ((int64_t)(round & 1) * gridDim.x + blockIdx.x) * PICP_NACC;
+        if (lane < 29) {
+          float sum = s_red[0][lane];
+#pragma unroll
+          for (int wv = 1; wv < PW_THREADS / 32; ++wv) sum += s_red[wv][lane];
+          out[lane] = sum;
+        } else {
+          int sum = 0;
+#pragma unroll
+          for (int wv = 0; wv < PW_THREADS / 32; ++wv) sum += __float_as_int(s_red[wv][29]);
+          out[29] = __int_as_float(sum);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) grid_arrive(p.barrier);
+    }
+    if (tid == 0) grid_wait(p.barrier, (unsigned int)(round + 1) * gridDim.x);
+    consumer_sync();
+    {
+      constexpr int W = PW_THREADS / 32;
+      constexpr int B = 16;
+      float sum = 0.f;
+      int si = 0;
+      const int nblk = (int)gridDim.x;
+      const float* part = p.partials + (int64_t)(round & 1) * gridDim.x * PICP_NACC;
+      for (int bk0 = warp; bk0 < nblk; bk0 += W * B) {
+        float x[B];
+#pragma unroll
+        for (int q = 0; q < B; ++q) {
+          const int bk = bk0 + q * W;
+          x[q] = (bk < nblk && lane < 30) ? __ldcg(part + (int64_t)bk * PICP_NACC + lane) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < B; ++q) {
+          if (lane == 29) si += __float_as_int(x[q]);
+          else sum += x[q];
+        }
+      }
+      consumer_sync();
+      s_red[warp][lane] = (lane == 29) ? __int_as_float(si) : sum;
+      consumer_sync();
+      if (warp == 0) {
+        float tot = 0.f;
+        int toti = 0;
+#pragma unroll
+        for (int wv = 0; wv < W; ++wv) {
+          if (lane == 29) toti += __float_as_int(s_red[wv][29]);
+          else tot += s_red[wv][lane];
+        }
+        s_red[0][lane] = (lane == 29) ? __int_as_float(toti) : tot;
+        __syncwarp();
+        if (lane == 0) {
+          s_keep[3] = picp_solve_local(p, s_red[0], s_T, s_H, s_b) ? 1.f : 0.f;
+          s_keep[0] = s_red[0][27];
+          s_keep[1] = s_red[0][28];
+          s_keep[2] = s_red[0][29];
+        }
+      }
+      consumer_sync();
+    }
+  }
+  if (blockIdx.x == 0 && tid == 0 && rounds > 0) {
+    vo_picp_state& st = p.st->s;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) st.T[j * 4 + i] = s_T[j * 3 + i];
+    st.T[3] = st.T[7] = st.T[11] = 0.f;
+    st.T[15] = 1.f;
+#pragma unroll
+    for (int i = 0; i < 36; ++i) st.H[i] = s_H[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) st.b[i] = s_b[i];
+    st.chi_inliers = s_keep[0];
+    st.chi_outliers = s_keep[1];
+    st.num_inliers = __float_as_int(s_keep[2]);
+    st.rounds_done += rounds;
+    st.last_ok = s_keep[3] != 0.f ? 1 : 0;
+  }
+}
+
 // lowest position of a pair whose indices fall outside the two point sets (all ones = none)
 __global__ void __launch_bounds__(256)
 picp_check_pairs_kernel(const int2* __restrict__ pairs, int64_t n, int n_image, int n_world,
@@ -880,6 +1190,8 @@ struct vo_picp_s {
   bool force_stream = false;          // VO_PICP_FORCE_STREAM=1: never use the resident kernel
   bool force_general = false;         // VO_PICP_FORCE_GENERAL=1: never use the pinhole kernel
   bool early_out = true;              // VO_PICP_NO_EARLY_OUT=1: always run every requested round
+  bool stream_v2 = false;             // VO_PICP_STREAM_V2=1: TMA-window streaming kernel instead of per-thread cp.async
+  bool window_opted_in = false;
   int32_t min_inliers = 0;
   DevBuf world_buf, image_buf, pairs_buf, state_buf, partials_buf, check_buf, barrier_buf;
   const float* world = nullptr;
@@ -966,6 +1278,8 @@ int vo_picp_create(vo_picp_t* out, int device) {
   h->force_stream = fs != nullptr && fs[0] == '1';
   const char* ne = getenv("VO_PICP_NO_EARLY_OUT");
   h->early_out = !(ne != nullptr && ne[0] == '1');
+  const char* v2 = getenv("VO_PICP_STREAM_V2");
+  h->stream_v2 = v2 != nullptr && v2[0] == '1';
   *out = h;
   return VO_OK;
 }
@@ -1199,6 +1513,36 @@ static int picp_compute_common(vo_picp_t h, int keep_outliers, int rounds, const
       VO_LAUNCH_CHECK();
       return VO_OK;
     }
+  }
+  // streaming, second generation: TMA windows — opt-in (VO_PICP_STREAM_V2=1; bulk copies need 16-byte
+  // aligned arrays).  Measured SLOWER than the per-thread cp.async kernel below (61.3 against 57.4 us
+  // per round at 9.97e6), see the comment on picp_window_kernel.
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(h->world) | reinterpret_cast<uintptr_t>(h->image) |
+                           reinterpret_cast<uintptr_t>(h->pairs)) & 15u) == 0;
+  if (aligned16 && h->stream_v2) {
+    auto wk = pinhole ? (p.keep_outliers ? picp_window_kernel<true, true> : picp_window_kernel<true, false>)
+                      : (p.keep_outliers ? picp_window_kernel<false, true> : picp_window_kernel<false, false>);
+    if (!h->window_opted_in) {
+      VO_CUDA(cudaFuncSetAttribute(picp_window_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PW_SMEM_BYTES));
+      VO_CUDA(cudaFuncSetAttribute(picp_window_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PW_SMEM_BYTES));
+      VO_CUDA(cudaFuncSetAttribute(picp_window_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PW_SMEM_BYTES));
+      VO_CUDA(cudaFuncSetAttribute(picp_window_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PW_SMEM_BYTES));
+      h->window_opted_in = true;
+    }
+    const int sms = num_sms(h->device);
+    const int64_t n_tiles = (h->n_pairs + PW_TILE - 1) / PW_TILE;
+    const int wgrid = (int)std::min<int64_t>(sms, n_tiles);
+    rc = h->partials_buf.reserve((size_t)2 * sms * PICP_NACC * sizeof(float));
+    if (rc) return rc;
+    p.partials = h->partials_buf.as<float>();
+    int rounds_arg = rounds;
+    int64_t nw = h->n_world, ni = h->n_image;
+    void* args[] = {(void*)&p, (void*)&rounds_arg, (void*)&nw, (void*)&ni};
+    VO_CUDA(cudaMemsetAsync(h->barrier_buf.p, 0, 4, h->stream));
+    VO_CUDA(cudaLaunchCooperativeKernel((const void*)wk, dim3((unsigned)wgrid), dim3(PW_THREADS + 32), args,
+                                        PW_SMEM_BYTES, h->stream));
+    VO_LAUNCH_CHECK();
+    return VO_OK;
   }
   // streaming kernel: ONE cooperative launch runs every round (grid-wide barrier per round)
   {
