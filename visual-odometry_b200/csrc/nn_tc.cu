@@ -464,6 +464,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
       uint32_t sel = acc_n & 1u, par = (acc_n >> 1) & 1u;  // buffer of this pipeline, phase of its barrier
       for (int64_t unit = 0; unit < nt; ++unit) {
         uint32_t thr_addr = thr_addr0;
+#pragma unroll 4
         for (int a = 0; a < qt; ++a, thr_addr += 128 * sizeof(float)) {
           TC_PROF_T(pa);
           float my_thr;  // read before the wait: its latency hides behind it
