@@ -94,6 +94,25 @@ def test_map_overflow_is_reported_not_fatal(vo):
     n_map = C.c_int64(0)
     assert lib.vo_pipe_get_map(h, None, None, 0, C.byref(n_map)) == 0
     assert n_map.value == 100
+    # a dropped claim must not cut later keys off their probe sequence.  The 100 stored
+    # points are still found after the overflow: merging them again (moved) changes no count and
+    # overwrites their positions in place.
+    Xf = C.POINTER(C.c_float)
+    moved = pts[:100] + np.float32(7.0)
+    assert lib.vo_pipe_merge_cloud(h, _p(moved), _p(app[:100].copy()), 100, X.ctypes.data_as(Xf)) == 0
+    got_pts, got_app = np.zeros((100, 3), np.float32), np.zeros((100, 10), np.float32)
+    assert lib.vo_pipe_get_map(h, _p(got_pts), _p(got_app), 100, C.byref(n_map)) == 0
+    assert n_map.value == 100
+    assert np.array_equal(got_app, app[:100]) and np.array_equal(got_pts, moved)
+    # ... and a new sequence on the same handle starts from an empty map
+    f = np.zeros((4, 2), np.float32)
+    a = rng.uniform(-1, 1, (4, 10)).astype(np.float32)
+    assert lib.vo_pipe_first_frame(h, _p(f), _p(a), 4) == 0
+    assert lib.vo_pipe_get_map(h, None, None, 0, C.byref(n_map)) == 0
+    assert n_map.value == 0
+    assert lib.vo_pipe_merge_cloud(h, _p(pts), _p(app), 50, X.ctypes.data_as(Xf)) == 0
+    assert lib.vo_pipe_get_map(h, None, None, 0, C.byref(n_map)) == 0
+    assert n_map.value == 50
     lib.vo_pipe_destroy(h)
 
 

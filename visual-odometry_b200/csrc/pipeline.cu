@@ -100,6 +100,9 @@ assoc_join_kernel(const int32_t* __restrict__ nn_idx, int n_q, int first_is_map,
 // slots[]: 0xFFFFFFFF empty | map index (< 2^31) | 0x80000000+i = claimed this call by new point i.
 constexpr unsigned int MAP_EMPTY = 0xFFFFFFFFu;
 constexpr unsigned int MAP_CLAIM = 0x80000000u;
+// a claim dropped because the map was full: probing walks over it (an EMPTY here would cut every key
+// that was inserted past this slot off its probe sequence) and never claims it
+constexpr unsigned int MAP_TOMB = 0x7FFFFFFFu;
 
 __device__ __forceinline__ bool app_hash(const float* a, unsigned long long* h) {
   unsigned long long x = 0x9E3779B97F4A7C15ull;
@@ -162,6 +165,10 @@ __global__ void __launch_bounds__(PIPE_THREADS) map_update_kernel(const MapParam
           }
           v = old;
         }
+        if (v == MAP_TOMB) {
+          s = (s + 1) & p.cap_mask;
+          continue;
+        }
         const float* other = (v & MAP_CLAIM) ? p.new_app + 10 * (long long)(v & ~MAP_CLAIM)
                                              : p.map_app + 10 * (long long)v;
         float b[10];
@@ -207,7 +214,7 @@ __global__ void __launch_bounds__(PIPE_THREADS) map_update_kernel(const MapParam
           p.map_pts[3 * pos + 2] = p.X[2] * x + (p.X[5] * y + p.X[8] * z) + p.X[11];
         }
       } else if (ks >= 0) {
-        p.slots[ks] = MAP_EMPTY;  // map full: drop the claim (flagged below)
+        p.slots[ks] = MAP_TOMB;  // map full: drop the claim (flagged below), keep the probe chain
       }
     }
     appended += tot;
@@ -218,7 +225,7 @@ __global__ void __launch_bounds__(PIPE_THREADS) map_update_kernel(const MapParam
     const int ks = p.key_slot[i];
     if (ks < 0 || p.last[ks] != i) continue;
     const unsigned int j = p.slots[ks];
-    if (j != MAP_EMPTY && !(j & MAP_CLAIM)) {
+    if (j != MAP_EMPTY && j != MAP_TOMB && !(j & MAP_CLAIM)) {
       const float x = p.new_pts[3 * (long long)i], y = p.new_pts[3 * (long long)i + 1],
                   z = p.new_pts[3 * (long long)i + 2];
       p.map_pts[3 * (long long)j + 0] = p.X[0] * x + (p.X[3] * y + p.X[6] * z) + p.X[9];
@@ -502,6 +509,16 @@ int vo_pipe_destroy(vo_pipe_t h) {
 int vo_pipe_first_frame(vo_pipe_t h, const float* points_host, const float* app_host, int64_t n) {
   VO_REQUIRE(h != nullptr, VO_ERR_ARG, "null handle");
   DeviceGuard g(h->device);
+  // a new sequence starts from an empty map: counters, overflow flag, hash index and history are
+  // reset (a second sequence used to merge into the first one's map)
+  cudaStreamSynchronize(h->map_stream);
+  VO_CUDA(cudaMemsetAsync(h->counts.p, 0, C_N * 8, h->stream));
+  VO_CUDA(cudaMemsetAsync(h->map_slots.p, 0xFF, (size_t)h->cap * 4, h->stream));
+  VO_CUDA(cudaMemsetAsync(h->map_last.p, 0xFF, (size_t)h->cap * 4, h->stream));
+  iso_identity(h->X_curr);
+  iso_identity(h->history);
+  h->tri_slot = 0;
+  h->n_q_last = 0;
   h->ref = 0;
   int rc = pipe_upload_frame(h, 0, points_host, app_host, n);
   if (rc) return rc;
