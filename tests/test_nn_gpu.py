@@ -288,6 +288,29 @@ def test_both_filters_agree_at_scale(vo, synth, monkeypatch):
     assert np.array_equal(out["tc"][1][hit], out["ffma"][1][hit])
 
 
+@pytest.mark.parametrize("nq", [1, 3, 8])
+def test_few_queries_single_launch_path(vo, oracle, nq):
+    """what the reference's main does (vo_complete.cpp:37-38: one bestMatchFull per measurement): up
+    to 8 queries against a frame-sized map are answered by ONE kernel launch (queries as kernel
+    parameters, answers through mapped host memory); same bits as the oracle, incl. ties and misses"""
+    rng = np.random.RandomState(31 + nq)
+    m = rng.uniform(-1, 1, (900, 11)).astype(np.float32)
+    m[500] = m[20]                                   # duplicate: the lower index wins
+    q = rng.uniform(-1, 1, (nq, 11)).astype(np.float32)
+    q[0] = m[500]
+    if nq > 1:
+        q[1, 1:] = m[77, 1:] + np.float32(0.01)      # a near match
+    nn = vo.NNIndex(0)
+    nn.set_map(m)
+    for norm in (0.1, 3.0):
+        idx, d2 = nn.best_match(q, norm, want_d2=True)
+        assert nn.last_launches() == [(1, 256, nq, 1)]
+        oi, od = oracle.nn_best_match(m, q, norm)
+        assert np.array_equal(idx, oi) and idx[0] == 20
+        assert np.array_equal(d2[oi >= 0], od[oi >= 0])
+    nn.close()
+
+
 def test_large_radius_true_argmin(vo, oracle):
     """radius large enough that EVERY row is a candidate: exercises the bound-tightening path."""
     rng = np.random.RandomState(5)

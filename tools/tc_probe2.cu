@@ -1,0 +1,443 @@
+// tc_probe2.cu — can the NN tensor filter keep its accumulators in f16?  (stand-alone, not part of
+// libvo_b200.so).  The f32-accumulator filter is bound by the ALU pipe: every accumulator element
+// has to enter a minimum and FMNMX3 takes two new elements per instruction.  With D = f16 the
+// elements can be read back packed two per register (tcgen05.ld ... .pack::16b) and folded with the
+// packed 16-bit 3-input integer minimum (VIMNMX3.S16x2: four new elements per instruction; the bit
+// pattern of a non-negative f16 orders like a signed 16-bit integer and every negative one is below
+// every non-negative one).  Three questions, answered on hardware:
+//   (1) acc16: where does tcgen05.mma put an f16 accumulator in TMEM, what does .pack::16b return,
+//       and is the f16 result the correctly rounded f32 result (one rounding at the end, not an f16
+//       accumulation)?  Data = the NN filter's own operand rows (coordinates in [-1,1], hi/lo norms).
+//   (2) minrate: instruction throughput per SM of FMNMX3, VIMNMX3.S16x2, HMNMX2, VIMNMX.S16x2 and of
+//       pairs of them interleaved (do they share a pipe?).
+//   (3) ldtm16: 16 warps reading TMEM packed and folding with VIMNMX3.S16x2 — elements per clock per
+//       SM, to compare with 102 for the unpacked f32 path (tc_probe.cu).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o build/tc_probe2 tools/tc_probe2.cu
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#define CK(x)                                                                        \
+  do {                                                                               \
+    cudaError_t e_ = (x);                                                            \
+    if (e_ != cudaSuccess) {                                                         \
+      printf("{\"error\": \"%s at %s:%d\"}\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(1);                                                                       \
+    }                                                                                \
+  } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0u;
+}
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, long long max_cycles) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity))
+    if (clock64() - t0 > max_cycles) return false;
+  return true;
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, 0, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
+#define LD32_OUT(r)                                                                                       \
+  "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),         \
+      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), \
+      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),           \
+      "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),           \
+      "=r"(r[30]), "=r"(r[31])
+#define LD32_REGS                                                                      \
+  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "            \
+  "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+// 32 columns, one per register
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 " LD32_REGS : LD32_OUT(r) : "r"(taddr) : "memory");
+}
+// 64 columns, the low halves of two adjacent columns per register
+__device__ __forceinline__ void tc_ld32_pack(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 " LD32_REGS : LD32_OUT(r) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__host__ __device__ inline uint64_t make_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  return d;
+}
+// c_format [4,6): 0 = F16, 1 = F32; A = B = F16, K-major
+__host__ __device__ inline uint32_t make_idesc(int c_fmt, int M, int N) {
+  return ((uint32_t)c_fmt << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- (1) f16 accumulator: placement in TMEM, .pack::16b, rounding -------------------------------------
+// A, B: 128 x 16 halves row-major.  Columns [0,128): D in f32.  Columns [128,256): D in f16.
+// out32[128][128] = the f32 accumulator, raw16[128][128] = the raw 32-bit cells of the f16 one,
+// packed[128][64] = what .pack::16b returns for it.
+__global__ void __launch_bounds__(128) acc16_kernel(const __half* A, const __half* B, uint32_t* out32,
+                                                    uint32_t* raw16, uint32_t* packed, int* status) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __half* sA = reinterpret_cast<__half*>(smem);
+  __half* sB = reinterpret_cast<__half*>(smem + 4096);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  auto put = [](__half* dst, const __half* src, int rows) {
+    for (int i = threadIdx.x; i < rows * 16; i += blockDim.x) {
+      const int r = i / 16, k = i % 16;
+      dst[(r / 8) * 128 + (k / 8) * 64 + (r % 8) * 8 + (k % 8)] = src[i];
+    }
+  };
+  put(sA, A, 128);
+  put(sB, B, 128);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(&tmem_base, 256);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base;
+  if (tid == 0) {
+    const uint64_t ad = make_desc(smem_u32(sA), 128, 256), bd = make_desc(smem_u32(sB), 128, 256);
+    tc_mma_f16(tb, ad, bd, make_idesc(1, 128, 128));
+    tc_mma_f16(tb + 128, ad, bd, make_idesc(0, 128, 128));
+    tc_commit(&bar);
+  }
+  if (!mbar_wait_bounded(&bar, 0, 200000000LL)) {
+    if (tid == 0) *status = -1;
+  } else {
+    tc_fence_after();
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    uint32_t r[32];
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      tc_ld32(tb + lane_base + c0, r);
+      tc_wait_ld();
+      for (int j = 0; j < 32; ++j) out32[tid * 128 + c0 + j] = r[j];
+      tc_ld32(tb + lane_base + 128 + c0, r);
+      tc_wait_ld();
+      for (int j = 0; j < 32; ++j) raw16[tid * 128 + c0 + j] = r[j];
+    }
+    for (int c0 = 0; c0 < 128; c0 += 64) {
+      tc_ld32_pack(tb + lane_base + 128 + c0, r);
+      tc_wait_ld();
+      for (int j = 0; j < 32; ++j) packed[tid * 64 + c0 / 2 + j] = r[j];
+    }
+    if (tid == 0) *status = 1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 256);
+}
+
+// ---- (2) instruction throughput of the candidate minimum instructions ------------------------------
+__device__ __forceinline__ uint32_t op_fmnmx3(uint32_t a, uint32_t b, uint32_t c) {
+  float r;
+  asm volatile("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(__uint_as_float(a)), "f"(__uint_as_float(b)), "f"(__uint_as_float(c)));
+  return __float_as_uint(r);
+}
+__device__ __forceinline__ uint32_t op_vimnmx3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm volatile("{.reg .b32 t1;\nmin.s16x2 t1, %1, %2;\nmin.s16x2 %0, t1, %3;}" : "=r"(r) : "r"(a), "r"(b), "r"(c));  // ptxas fuses the pair
+  return r;
+}
+__device__ __forceinline__ uint32_t op_vimnmx2(uint32_t a, uint32_t b, uint32_t) {
+  uint32_t r;
+  asm volatile("min.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t op_hmnmx2(uint32_t a, uint32_t b, uint32_t) {
+  uint32_t r;
+  asm volatile("min.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t op_ffma(uint32_t a, uint32_t b, uint32_t c) {
+  float r;
+  asm volatile("fma.rn.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(__uint_as_float(a)), "f"(__uint_as_float(b)), "f"(__uint_as_float(c)));
+  return __float_as_uint(r);
+}
+template <int OP>
+__device__ __forceinline__ uint32_t op_apply(uint32_t a, uint32_t b, uint32_t c) {
+  if (OP == 0) return op_fmnmx3(a, b, c);
+  if (OP == 1) return op_vimnmx3(a, b, c);
+  if (OP == 2) return op_hmnmx2(a, b, c);
+  if (OP == 3) return op_vimnmx2(a, b, c);
+  return op_ffma(a, b, c);
+}
+// 8 independent chains of OPA, interleaved with 8 chains of OPB (OPB = -1: none)
+template <int OPA, int OPB>
+__global__ void __launch_bounds__(512) minrate_kernel(int iters, const uint32_t* in, uint32_t* sink, long long* cycles) {
+  uint32_t a[8], b[8];
+  const uint32_t x = in[threadIdx.x & 31], y = in[32 + (threadIdx.x & 31)];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] = in[i] + threadIdx.x;
+    b[i] = in[8 + i] ^ threadIdx.x;
+  }
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int rep = 0; rep < 4; ++rep)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        a[i] = op_apply<OPA>(a[i], x, y);
+        if (OPB >= 0) b[i] = op_apply<OPB>(b[i], y, x);
+      }
+  }
+  const long long t1 = clock64();
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s ^= a[i] ^ b[i];
+  if (s == 0x12345678u) sink[0] = s;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+// ---- (3) packed TMEM read + packed fold ------------------------------------------------------------
+// MODE 0: .pack::16b loads (64 columns per instruction) folded with VIMNMX3.S16x2
+// MODE 1: plain loads (32 columns per instruction) folded with FMNMX3 (the present epilogue)
+template <int MODE>
+__global__ void __launch_bounds__(512) ldtm16_kernel(int iters, int cols, uint32_t* sink, long long* cycles) {
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t mn[4] = {0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu};
+  constexpr int STEP = MODE == 0 ? 64 : 32;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    for (int c0 = 0; c0 < cols; c0 += STEP) {
+      uint32_t r[32];
+      if (MODE == 0) tc_ld32_pack(tb + (c0 & 511), r);
+      else tc_ld32(tb + (c0 & 511), r);
+      tc_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; j += 8)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          mn[c] = MODE == 0 ? op_vimnmx3(mn[c], r[j + 2 * c], r[j + 2 * c + 1]) : op_fmnmx3(mn[c], r[j + 2 * c], r[j + 2 * c + 1]);
+    }
+  }
+  const long long t1 = clock64();
+  __syncthreads();
+  if ((mn[0] ^ mn[1] ^ mn[2] ^ mn[3]) == 0x12345678u) sink[0] = mn[0];
+  if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+static uint32_t rng_state = 12345u;
+static float frand() {  // uniform in [-1, 1)
+  rng_state = rng_state * 1664525u + 1013904223u;
+  return (float)((rng_state >> 8) & 0xFFFFFF) / 8388608.f - 1.f;
+}
+static void split16(float x, __half* hi, __half* lo) {
+  const __half h = __float2half_rn(x);
+  *hi = h;
+  *lo = __float2half_rn(x - __half2float(h));
+}
+static uint16_t hbits(__half h) {
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
+}
+
+int main() {
+  int dev = 0, sms = 0;
+  CK(cudaSetDevice(dev));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+
+  // (1) f16 accumulators on the filter's own operands; scale = coordinate range, near = fraction of
+  // rows that are a small perturbation of a query (results near zero, where the threshold lives)
+  {
+    __half *dA, *dB;
+    uint32_t *d32, *d16, *dP;
+    int* dS;
+    CK(cudaMalloc(&dA, 128 * 16 * 2));
+    CK(cudaMalloc(&dB, 128 * 16 * 2));
+    CK(cudaMalloc(&d32, 128 * 128 * 4));
+    CK(cudaMalloc(&d16, 128 * 128 * 4));
+    CK(cudaMalloc(&dP, 128 * 64 * 4));
+    CK(cudaMalloc(&dS, 4));
+    std::vector<__half> A(128 * 16), B(128 * 16);
+    std::vector<uint32_t> o32(128 * 128), o16(128 * 128), oP(128 * 64);
+    for (int cfg = 0; cfg < 4; ++cfg) {
+      const float scale = cfg == 1 ? 8.f : (cfg == 2 ? 0.05f : 1.f);
+      const float near_frac = cfg == 3 ? 1.0f : 0.25f;
+      long long n = 0, hi_garbage = 0, pack_bad = 0, ne_rn32 = 0, ne_exact = 0, max_ulp32 = 0, max_ulp_exact = 0;
+      long long small = 0, small_ne = 0;
+      int st_all = 1;
+      for (int tile = 0; tile < 64; ++tile) {
+        std::vector<float> q(128 * 10), m(128 * 10);
+        for (auto& v : q) v = scale * frand();
+        for (int j = 0; j < 128; ++j)
+          for (int k = 0; k < 10; ++k) {
+            const bool near_row = (float)((j * 7 + tile) % 16) / 16.f < near_frac;
+            m[j * 10 + k] = near_row ? q[((j * 5) % 128) * 10 + k] + 0.02f * scale * frand() : scale * frand();
+          }
+        for (int i = 0; i < 128; ++i) {
+          float qq = 0.f, mm = 0.f;
+          for (int k = 0; k < 10; ++k) {
+            A[i * 16 + k] = __float2half_rn(-2.f * q[i * 10 + k]);
+            B[i * 16 + k] = __float2half_rn(m[i * 10 + k]);
+            qq += q[i * 10 + k] * q[i * 10 + k];
+            mm += m[i * 10 + k] * m[i * 10 + k];
+          }
+          A[i * 16 + 10] = A[i * 16 + 11] = __float2half_rn(1.f);
+          split16(qq, &A[i * 16 + 12], &A[i * 16 + 13]);
+          split16(mm, &B[i * 16 + 10], &B[i * 16 + 11]);
+          B[i * 16 + 12] = B[i * 16 + 13] = __float2half_rn(1.f);
+          A[i * 16 + 14] = A[i * 16 + 15] = B[i * 16 + 14] = B[i * 16 + 15] = __float2half_rn(0.f);
+        }
+        CK(cudaMemcpy(dA, A.data(), A.size() * 2, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dB, B.data(), B.size() * 2, cudaMemcpyHostToDevice));
+        CK(cudaMemset(dS, 0, 4));
+        acc16_kernel<<<1, 128, 8192>>>(dA, dB, d32, d16, dP, dS);
+        CK(cudaDeviceSynchronize());
+        int st = 0;
+        CK(cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost));
+        if (st != 1) st_all = st;
+        CK(cudaMemcpy(o32.data(), d32, o32.size() * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(o16.data(), d16, o16.size() * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(oP.data(), dP, oP.size() * 4, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 128; ++i)
+          for (int j = 0; j < 128; ++j) {
+            ++n;
+            const uint32_t cell = o16[i * 128 + j];
+            if (cell >> 16) ++hi_garbage;
+            const uint16_t got = (uint16_t)(cell & 0xFFFF);
+            const uint32_t pk = oP[i * 64 + j / 2];
+            if ((uint16_t)((j & 1) ? (pk >> 16) : (pk & 0xFFFF)) != got) ++pack_bad;
+            float f32;
+            memcpy(&f32, &o32[i * 128 + j], 4);
+            double exact = 0.0;
+            for (int k = 0; k < 16; ++k) exact += (double)__half2float(A[i * 16 + k]) * (double)__half2float(B[j * 16 + k]);
+            const uint16_t want32 = hbits(__float2half_rn(f32));
+            const uint16_t want_ex = hbits(__double2half(exact));
+            // distance in f16 codes (sign-magnitude -> monotone integer)
+            auto key = [](uint16_t h) { return (h & 0x8000) ? -(int)(h & 0x7FFF) : (int)(h & 0x7FFF); };
+            const long long d32u = llabs((long long)key(got) - key(want32));
+            const long long dexu = llabs((long long)key(got) - key(want_ex));
+            if (d32u) ++ne_rn32;
+            if (dexu) ++ne_exact;
+            if (d32u > max_ulp32) max_ulp32 = d32u;
+            if (dexu > max_ulp_exact) max_ulp_exact = dexu;
+            if (fabs(exact) < 0.05 * scale * scale) {
+              ++small;
+              if (dexu) ++small_ne;
+            }
+          }
+      }
+      printf("{\"probe\": \"acc16\", \"cfg\": %d, \"scale\": %g, \"status\": %d, \"elements\": %lld, "
+             "\"high_half_nonzero\": %lld, \"pack_mismatch\": %lld, \"ne_round_of_f32_acc\": %lld, "
+             "\"max_code_dist_vs_f32_acc\": %lld, \"ne_round_of_exact\": %lld, \"max_code_dist_vs_exact\": %lld, "
+             "\"near_threshold_elements\": %lld, \"near_threshold_ne_exact\": %lld}\n",
+             cfg, scale, st_all, n, hi_garbage, pack_bad, ne_rn32, max_ulp32, ne_exact, max_ulp_exact, small, small_ne);
+    }
+  }
+
+  uint32_t *sink, *din;
+  long long* cyc;
+  CK(cudaMalloc(&sink, 64));
+  CK(cudaMalloc(&din, 256));
+  CK(cudaMalloc(&cyc, sizeof(long long) * 1024));
+  {
+    uint32_t h[64];
+    for (int i = 0; i < 64; ++i) h[i] = 0x3c003c00u + i * 0x00010001u;
+    CK(cudaMemcpy(din, h, 256, cudaMemcpyHostToDevice));
+  }
+  std::vector<long long> h(1024);
+  auto max_cycles = [&]() {
+    CK(cudaMemcpy(h.data(), cyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+    long long mx = 0;
+    for (int i = 0; i < sms; ++i) mx = h[i] > mx ? h[i] : mx;
+    return mx;
+  };
+
+  // (2) instruction throughput, 16 warps per SM
+  {
+    const int iters = 4000;
+    const char* names[] = {"FMNMX3", "VIMNMX3.S16x2", "HMNMX2", "VIMNMX.S16x2", "FFMA"};
+#define RUN_MIN(OPA, OPB)                                                                                   \
+  {                                                                                                         \
+    for (int rep = 0; rep < 2; ++rep) {                                                                     \
+      minrate_kernel<OPA, OPB><<<sms, 512>>>(iters, din, sink, cyc);                                         \
+      CK(cudaDeviceSynchronize());                                                                          \
+    }                                                                                                       \
+    const long long mx = max_cycles();                                                                      \
+    const double instr = (double)iters * 32 * 16 * (OPB >= 0 ? 2 : 1);                                      \
+    printf("{\"probe\": \"minrate\", \"a\": \"%s\", \"b\": \"%s\", \"warp_instr_per_clk_per_sm\": %.3f, "    \
+           "\"lanes_per_clk_per_sm\": %.1f}\n",                                                             \
+           names[OPA], OPB >= 0 ? names[OPB >= 0 ? OPB : 0] : "-", instr / mx, instr * 32 / mx);             \
+  }
+    RUN_MIN(0, -1)
+    RUN_MIN(1, -1)
+    RUN_MIN(2, -1)
+    RUN_MIN(3, -1)
+    RUN_MIN(4, -1)
+    RUN_MIN(0, 1)
+    RUN_MIN(1, 2)
+    RUN_MIN(0, 2)
+    RUN_MIN(1, 4)
+    RUN_MIN(2, 4)
+  }
+
+  // (3) TMEM read + fold
+  for (int mode = 0; mode < 2; ++mode)
+    for (int warps = 4; warps <= 16; warps *= 2) {
+      const int iters = 2000, cols = 256;
+      for (int rep = 0; rep < 2; ++rep) {
+        if (mode == 0) ldtm16_kernel<0><<<sms, warps * 32>>>(iters, cols, sink, cyc);
+        else ldtm16_kernel<1><<<sms, warps * 32>>>(iters, cols, sink, cyc);
+        CK(cudaDeviceSynchronize());
+      }
+      const long long mx = max_cycles();
+      const double elems = (double)warps * iters * cols * 32;
+      printf("{\"probe\": \"ldtm16\", \"mode\": \"%s\", \"warps\": %d, \"elems_per_clk_per_sm\": %.1f}\n",
+             mode == 0 ? "pack16+VIMNMX3.S16x2" : "f32+FMNMX3", warps, elems / mx);
+    }
+  return 0;
+}

@@ -361,6 +361,51 @@ nn_general_kernel(const float* __restrict__ rows, int64_t n_rows, int row_stride
   if (best_row >= 0) atomicMin(keys + qi, nn_pack_key(best, static_cast<uint32_t>(best_row)));
 }
 
+// ---- a handful of queries against a frame-sized map: ONE launch, nothing else ------------------
+// The reference's main asks one query at a time (vo_complete.cpp:37-38: bestMatchFull per
+// measurement, ~100 per frame against ~100 rows).  Through the general path every such call costs
+// an upload, a memset, two kernels, two downloads and a synchronisation.  Here the queries travel
+// as kernel parameters, one block per query scans the packed rows with the reference-order distance
+// (no filter: the map is a few KB), and the answer is written straight into mapped pinned host
+// memory — one launch and one synchronisation per call.
+constexpr int NN_TINY_MAX_Q = 8;
+constexpr int64_t NN_TINY_MAX_ROWS = 16384;
+struct NNTinyParams {
+  const float4* packed;
+  int n_rows;
+  int n_queries;
+  float bound;
+  float q[NN_TINY_MAX_Q][NN_DIM];
+  int32_t* idx_out;   // device view of mapped host memory
+  float* d2_out;
+};
+
+__global__ void __launch_bounds__(256) nn_tiny_kernel(const NNTinyParams p) {
+  __shared__ unsigned long long s_best[8];
+  const int qi = blockIdx.x, tid = threadIdx.x;
+  float q[NN_DIM];
+#pragma unroll
+  for (int k = 0; k < NN_DIM; ++k) q[k] = p.q[qi][k];
+  unsigned long long best = NN_KEY_NONE;
+  for (int r = tid; r < p.n_rows; r += 256) {
+    const float4 a = __ldg(p.packed + r * 3 + 0), b = __ldg(p.packed + r * 3 + 1), c = __ldg(p.packed + r * 3 + 2);
+    const float m[NN_DIM] = {a.x, a.y, a.z, a.w, b.x, b.y, c.x, c.y, c.z, c.w};
+    const float d2 = ref_sqdist<NN_DIM>(m, q);
+    if (d2 < p.bound) best = min(best, nn_pack_key(d2, (uint32_t)r));  // strict <, lowest row on ties
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((tid & 31) == 0) s_best[tid >> 5] = best;
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) best = min(best, s_best[w]);
+    p.idx_out[qi] = best == NN_KEY_NONE ? -1 : (int32_t)(best & 0xFFFFFFFFull);
+    p.d2_out[qi] = best == NN_KEY_NONE ? p.bound : __uint_as_float((unsigned int)(best >> 32));
+    __threadfence_system();
+  }
+}
+
 // ---- bruteForceSearch: one warp per query, ascending row order -----------------------------------
 __global__ void __launch_bounds__(128)
 nn_radius_kernel(const float* __restrict__ rows, int64_t n_rows, int row_stride, int skip, int dim,
@@ -645,6 +690,7 @@ int vo_nn_destroy(vo_nn_t h) {
   h->list_stage.release();
   h->tiles16.release();
   h->tc_stats.release();
+  if (h->tiny_host) cudaFreeHost(h->tiny_host);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return VO_OK;
@@ -751,6 +797,34 @@ int vo_nn_best_match(vo_nn_t h, const float* queries_host, int64_t n_queries, in
   VO_REQUIRE((queries_host && best_idx_host) || n_queries == 0, VO_ERR_ARG, "null pointer");
   if (n_queries == 0) return VO_OK;
   DeviceGuard g(h->device);
+  if (n_queries <= NN_TINY_MAX_Q && h->fast && h->n_rows > 0 && h->n_rows <= NN_TINY_MAX_ROWS && h->force_path == 0) {
+    if (!h->tiny_host) {
+      VO_CUDA(cudaHostAlloc(&h->tiny_host, 2 * NN_TINY_MAX_Q * sizeof(float), cudaHostAllocMapped));
+      VO_CUDA(cudaHostGetDevicePointer(&h->tiny_dev, h->tiny_host, 0));
+    }
+    NNTinyParams tp;
+    tp.packed = h->packed.as<float4>();
+    tp.n_rows = (int)h->n_rows;
+    tp.n_queries = (int)n_queries;
+    tp.bound = norm * norm;  // brute_force_search.h:31
+    for (int64_t i = 0; i < n_queries; ++i)
+      for (int k = 0; k < NN_DIM; ++k) tp.q[i][k] = queries_host[i * query_stride + h->skip + k];
+    tp.idx_out = static_cast<int32_t*>(h->tiny_dev);
+    tp.d2_out = reinterpret_cast<float*>(static_cast<int32_t*>(h->tiny_dev) + NN_TINY_MAX_Q);
+    h->last_launches.clear();
+    h->last_was_tc = false;
+    nn_tiny_kernel<<<(unsigned)n_queries, 256, 0, h->stream>>>(tp);
+    VO_LAUNCH_CHECK();
+    h->last_launches.insert(h->last_launches.end(), {1, 256, (int32_t)n_queries, 1});
+    VO_CUDA(cudaStreamSynchronize(h->stream));
+    const int32_t* ih = static_cast<const int32_t*>(h->tiny_host);
+    const float* dh = reinterpret_cast<const float*>(ih + NN_TINY_MAX_Q);
+    for (int64_t i = 0; i < n_queries; ++i) {
+      best_idx_host[i] = ih[i];
+      if (best_d2_host) best_d2_host[i] = dh[i];
+    }
+    return VO_OK;
+  }
   const size_t qbytes = (size_t)n_queries * query_stride * sizeof(float);
   int rc = h->q_stage.reserve(qbytes);
   if (rc) return rc;

@@ -170,6 +170,8 @@ struct vo_nn_s {
   bool tc_ready = false, tc_opted_in = false, last_was_tc = false;
   float mm_max_host = 0.f;  // host copy of max|m|^2 (read back on first use)
   bool have_mm_max = false;
+  void* tiny_host = nullptr;  // mapped pinned memory for the answers of the few-queries path
+  void* tiny_dev = nullptr;
   int force_path = 0;  // VO_NN_FORCE_PATH: 0 auto, 1 ffma (FP32 CUDA cores), 2 tc (tensor cores)
 };
 

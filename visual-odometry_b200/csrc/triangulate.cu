@@ -26,8 +26,6 @@ namespace vo {
 constexpr int TRI_THREADS = 256;
 constexpr int TRI_ITEMS = 4;
 constexpr int TRI_TILE = TRI_THREADS * TRI_ITEMS;
-// shared memory of triangulate_kernel: pairs[2], parked points[2], parked second indices[2] (+ sources[2])
-constexpr size_t tri_smem_bytes(bool with_src) { return (size_t)2 * TRI_TILE * (8 + 12 + 4 + (with_src ? 4 : 0)); }
 
 struct TriParams {
   float iK[9];    // K^-1                      (utils.cpp:54)
@@ -139,27 +137,20 @@ __device__ __forceinline__ void triangulate_pair_dev(const f2_t (&d1)[3], const 
 //      as fully coalesced stores.
 // Item j of lane l of warp w sits at tile position w*32*ITEMS + j*32 + l, so every load of a warp
 // is a contiguous run.
-__device__ __forceinline__ void tri_cp_async8(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-
-// WITH_SRC: also report the position of every success in `corr` (out_src; tests only — the extra
-// shared memory costs one resident block per SM).
-template <int THREADS, int ITEMS, bool WITH_SRC>
+// Tried in round 2 and dropped (profiles/r02_notes.md): fetching the NEXT tile's index pairs with
+// cp.async while the current tile is solved (tickets two ahead) — 0.101 ms against 0.092 for this
+// version at 8.9e6 correspondences; block shapes 128x4, 512x4, 128x8, 256x2 — all slower.  ncu: 193
+// executed instructions per correspondence at 57 % issue utilisation; the kernel is co-limited by
+// issue and latency, not by bytes in flight.
+template <int THREADS, int ITEMS>
 __global__ void __launch_bounds__(THREADS) triangulate_kernel(const TriParams q) {
   static_assert(ITEMS % 2 == 0, "items are processed in packed pairs");
   constexpr int TILE = THREADS * ITEMS;
   constexpr int WARPS = THREADS / 32;
-  // dynamic shared memory (more than the 48 KB a static allocation may have), see tri_smem_bytes
-  extern __shared__ __align__(16) unsigned char tri_smem[];
-  // the index pairs of the NEXT tile, fetched with cp.async while this one is solved: the gathers of
-  // a tile can then start the moment the block turns to it (one dependent memory round trip less
-  // per tile, and another 8 KB per block in flight)
-  int2(*s_pairs)[TILE] = reinterpret_cast<int2(*)[TILE]>(tri_smem);
-  float(*s_pts)[TILE * 3] = reinterpret_cast<float(*)[TILE * 3]>(tri_smem + 2 * TILE * sizeof(int2));
-  int(*s_c2)[TILE] = reinterpret_cast<int(*)[TILE]>(tri_smem + 2 * TILE * (sizeof(int2) + 3 * sizeof(float)));
-  int(*s_src)[TILE] = reinterpret_cast<int(*)[TILE]>(tri_smem + 2 * TILE * (sizeof(int2) + 4 * sizeof(float)));
-  __shared__ int s_next2;
+  __shared__ float s_pts[2][TILE * 3];
+  __shared__ int s_c2[2][TILE];
+  __shared__ int s_src[2][TILE];
+  __shared__ int s_next;
   __shared__ int s_warp_tot[WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float t[3] = {q.t[0], q.t[1], q.t[2]};
@@ -187,7 +178,7 @@ __global__ void __launch_bounds__(THREADS) triangulate_kernel(const TriParams q)
         if (r < total) q.out_corr_new[excl + r] = make_int2(s_c2[slot][r], (int)(excl + r));  // (idx_second, k) :97
       }
     }
-    if (WITH_SRC && q.out_src)
+    if (q.out_src)
       for (int r = tid; r < total; r += THREADS) q.out_src[excl + r] = s_src[slot][r];
     if (q.out_app)  // :127 — the appearance travels with the point
       for (int r = tid; r < total; r += THREADS) {
@@ -199,41 +190,20 @@ __global__ void __launch_bounds__(THREADS) triangulate_kernel(const TriParams q)
     if (tile == num_tiles - 1 && tid == 0) *q.n_success = excl + total;
   };
 
-  // item j of lane l of warp w sits at tile position w*32*ITEMS + j*32 + l
-  auto prefetch_pairs = [&](int tile, int buf) {
-    if (tile < num_tiles) {
-      const int64_t warp_base = (int64_t)tile * TILE + (int64_t)warp * (32 * ITEMS);
-#pragma unroll
-      for (int j = 0; j < ITEMS; ++j) {
-        const int64_t i = warp_base + j * 32 + lane;
-        // out-of-range slots of the last tile re-read the last correspondence and are masked out
-        tri_cp_async8(&s_pairs[buf][warp * (32 * ITEMS) + j * 32 + lane], q.corr + (i < n_corr ? i : n_corr - 1));
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-
-  // tickets are claimed TWO tiles ahead (a tile can only ever depend on tiles already claimed by
-  // running blocks, and a block works through its tickets in increasing order)
-  int pend_tile = -1, pend_total = 0, pend_slot = 0, slot = 0, pbuf = 0;
-  if (tid == 0) {
-    s_next2 = (int)atomicAdd(q.ws.ticket, 1u);
-    s_warp_tot[0] = (int)atomicAdd(q.ws.ticket, 1u);
-  }
+  int pend_tile = -1, pend_total = 0, pend_slot = 0, slot = 0;
+  if (tid == 0) s_next = (int)atomicAdd(q.ws.ticket, 1u);
   __syncthreads();
-  int tile = s_next2, next = s_warp_tot[0];
-  __syncthreads();
-  prefetch_pairs(tile, pbuf);
+  int tile = s_next;
   while (tile < num_tiles) {
     const int64_t warp_base = (int64_t)tile * TILE + (int64_t)warp * (32 * ITEMS);
-    asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's own pairs have landed
+    // out-of-range slots of the last tile re-read the last correspondence and are masked out
     int2 c[ITEMS];
     bool in[ITEMS];
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
       const int64_t i = warp_base + j * 32 + lane;
       in[j] = i < n_corr;
-      c[j] = s_pairs[pbuf][warp * (32 * ITEMS) + j * 32 + lane];
+      c[j] = __ldg(q.corr + (in[j] ? i : n_corr - 1));
       if ((unsigned)c[j].x >= (unsigned)q.n_p1 || (unsigned)c[j].y >= (unsigned)q.n_p2) {
         if (in[j] && q.bad) atomicMin(q.bad, (unsigned long long)i);
         in[j] = false;
@@ -246,8 +216,7 @@ __global__ void __launch_bounds__(THREADS) triangulate_kernel(const TriParams q)
       a[j] = __ldg(q.p1 + c[j].x);  // .first  -> image 1   (utils.cpp:87)
       b[j] = __ldg(q.p2 + c[j].y);  // .second -> image 2   (utils.cpp:88)
     }
-    prefetch_pairs(next, pbuf ^ 1);  // each thread copies exactly the slots it will read itself
-    int claimed = 0;  // the tile after the next one
+    int claimed = 0;  // the tile after this one, claimed early so the atomic's latency is hidden too
     if (tid == 0) claimed = (int)atomicAdd(q.ws.ticket, 1u);
     f2_t P[ITEMS / 2][3];
     bool ok[ITEMS];
@@ -279,7 +248,7 @@ __global__ void __launch_bounds__(THREADS) triangulate_kernel(const TriParams q)
       run += __popc(bal);
     }
     if (lane == 0) s_warp_tot[warp] = run;
-    if (tid == 0) s_next2 = claimed;
+    if (tid == 0) s_next = claimed;
     __syncthreads();
     int warp_off = 0, total = 0;
 #pragma unroll
@@ -288,7 +257,7 @@ __global__ void __launch_bounds__(THREADS) triangulate_kernel(const TriParams q)
       warp_off += (w < warp) ? x : 0;
       total += x;
     }
-    const int after_next = s_next2;
+    const int next = s_next;
     if (tid == 0) {
       scan_st(q.ws.status + tile, SCAN_POSTED | (unsigned long long)total);
       atomicAdd(q.ws.groups + tile / q.ws.group_tiles,
@@ -307,7 +276,7 @@ __global__ void __launch_bounds__(THREADS) triangulate_kernel(const TriParams q)
         s_pts[slot][3 * r + 1] = (j & 1) ? oy : py;
         s_pts[slot][3 * r + 2] = (j & 1) ? oz : pz;
         s_c2[slot][r] = c[j].y;
-        if (WITH_SRC) s_src[slot][r] = (int)(warp_base + j * 32 + lane);
+        s_src[slot][r] = (int)(warp_base + j * 32 + lane);
       }
     // retire the previous tile now that this one is published: its predecessors have had a whole
     // tile time to publish (measured: retiring it earlier, under this tile's load latency, brings
@@ -319,11 +288,8 @@ __global__ void __launch_bounds__(THREADS) triangulate_kernel(const TriParams q)
     pend_total = total;
     pend_slot = slot;
     slot ^= 1;
-    pbuf ^= 1;
     tile = next;
-    next = after_next;
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (pend_tile >= 0) {
     __syncthreads();
     retire(pend_slot, pend_tile, pend_total);
@@ -465,28 +431,17 @@ static int tri_launch(cudaStream_t stream, const float K[9], const float X[16], 
   q.n_p2 = (int)std::min<int64_t>(n_p2, INT32_MAX);
   q.bad = bad;
   // persistent blocks: as many as can be resident, each loops over dynamically claimed tiles
-  static int resident[2] = {0, 0};
-  const int v = out_src ? 1 : 0;
-  if (resident[v] == 0) {
+  static int resident = 0;
+  if (resident == 0) {
     int per_sm = 1, dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (v) {
-      cudaFuncSetAttribute(triangulate_kernel<TRI_THREADS, TRI_ITEMS, true>,
-                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_smem_bytes(true));
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, triangulate_kernel<TRI_THREADS, TRI_ITEMS, true>,
-                                                    TRI_THREADS, tri_smem_bytes(true));
-    } else {
-      cudaFuncSetAttribute(triangulate_kernel<TRI_THREADS, TRI_ITEMS, false>,
-                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_smem_bytes(false));
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, triangulate_kernel<TRI_THREADS, TRI_ITEMS, false>,
-                                                    TRI_THREADS, tri_smem_bytes(false));
-    }
-    resident[v] = (per_sm < 1 ? 1 : per_sm) * (sms < 1 ? 1 : sms);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, triangulate_kernel<TRI_THREADS, TRI_ITEMS>,
+                                                  TRI_THREADS, 0);
+    resident = (per_sm < 1 ? 1 : per_sm) * (sms < 1 ? 1 : sms);
   }
-  const unsigned grid = (unsigned)(tiles < resident[v] ? tiles : resident[v]);
-  if (v) triangulate_kernel<TRI_THREADS, TRI_ITEMS, true><<<grid, TRI_THREADS, tri_smem_bytes(true), stream>>>(q);
-  else triangulate_kernel<TRI_THREADS, TRI_ITEMS, false><<<grid, TRI_THREADS, tri_smem_bytes(false), stream>>>(q);
+  const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
+  triangulate_kernel<TRI_THREADS, TRI_ITEMS><<<grid, TRI_THREADS, 0, stream>>>(q);
   VO_LAUNCH_CHECK();
   return VO_OK;
 }
