@@ -41,6 +41,8 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include "nn.cuh"
 
@@ -62,14 +64,17 @@ constexpr int TC_SUB = 128;                 // rows per MMA (N) and per TMEM buf
 constexpr int TC_ROW_BYTES = 32;            // 16 halves
 constexpr uint32_t TC_TILE_BYTES = TC_BN * TC_ROW_BYTES;   // 8 KB
 constexpr int TC_RESCAN = 64;                // rows one epilogue warp answers for (its column half)
-constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES = 8;
+constexpr int TC_LOOKAHEAD = 6;             // map tiles requested ahead of the one being multiplied
 constexpr int TC_QT_MAX = 16;               // query tiles (of 128) resident per CTA
 constexpr uint32_t TC_A_BYTES = 128 * TC_ROW_BYTES;        // 4 KB per query tile
 constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_PIPES = TC_BN / TC_SUB;    // 2 independent MMA->epilogue pipelines (halves of a map tile)
 constexpr int TC_PIPE_WARPS = TC_EPI_WARPS / TC_PIPES;     // 8 epilogue warps per pipeline
-constexpr int TC_THREADS = (TC_EPI_WARPS + 1 + TC_PIPES) * 32;  // + TMA warp + one MMA warp per pipeline
 constexpr int TC_BUFS = 4;                  // TMEM accumulator buffers of TC_SUB columns; pipeline p owns p, p+2
+// + one MMA-issuing warp per buffer (the first also requests the map tiles).  20 warps = 5 per
+// scheduler partition of the register file: 96 registers per thread (a 21st warp would cap all at 80)
+constexpr int TC_THREADS = (TC_EPI_WARPS + TC_BUFS) * 32;
 constexpr float TC_U16 = 4.8828125e-4f;     // 2^-11, unit roundoff of f16 (round to nearest)
 constexpr float TC_PAD_NORM = 60000.f;      // |m|^2 of a padding row: never under any threshold
 constexpr float TC_MAX_NORM = 30000.f;      // |m|^2, |q|^2 above this do not fit f16 arithmetic
@@ -134,7 +139,69 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// 64 columns of an f16 accumulator: two adjacent columns (their low halves) per register
+__device__ __forceinline__ void tc_ld32_pack(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// packed signed 16-bit minima: ptxas fuses the pair into ONE VIMNMX3.S16x2 (four new values per
+// instruction on the ALU pipe, against two for FMNMX3)
+__device__ __forceinline__ uint32_t tc_min3_s16x2(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("{\n.reg .b32 t;\nmin.s16x2 t, %1, %2;\nmin.s16x2 %0, t, %3;\n}" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t tc_min_s16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("min.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t tc_max_s16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("max.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+// minimum of 64 packed accumulator columns (even columns in the low halves, odd ones in the high
+// halves), four independent chains
+__device__ __forceinline__ uint32_t tc_fold16(const uint32_t (&r)[32]) {
+  uint32_t mn[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) mn[c] = tc_min3_s16x2(r[c], r[4 + c], r[8 + c]);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) mn[c] = tc_min3_s16x2(mn[c], r[12 + c], r[16 + c]);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) mn[c] = tc_min3_s16x2(mn[c], r[20 + c], r[24 + c]);
+  mn[0] = tc_min3_s16x2(mn[0], r[28], r[29]);
+  mn[1] = tc_min3_s16x2(mn[1], r[30], r[31]);
+  return tc_min_s16x2(tc_min3_s16x2(mn[0], mn[1], mn[2]), mn[3]);
+}
+// The f16 accumulator is compared as a SIGNED 16-BIT INTEGER: the code of a non-negative f16 grows
+// with its value (+inf = 0x7C00 above every finite one) and every negative f16 (distances that came
+// out below zero: true matches) is a negative integer, below every threshold.  tc_thr16 returns c,
+// in both halves of a word, such that an accumulator is worth a re-scan iff code < c:
+//   thr = +inf (norms too large for f16: always re-scan) -> 0x7FFF, above +inf's code;
+//   thr = -inf (non-finite query: never)                 -> -32768, below everything;
+//   otherwise code(thr rounded UP to f16) + 3.  Rounding is monotone, so a value <= thr has a code
+//   <= code(ru(thr)) if the tensor core rounds its internal sum once; measured (tools/tc_probe2.cu,
+//   4e6 elements) its f16 result is within ONE code of the rounded f32 result it would have
+//   delivered — two codes of slack (1.5e-5 at 0.016) on top.
+__device__ __forceinline__ uint32_t tc_thr16(float thr) {
+  int c;
+  if (thr == INFINITY) c = 0x7FFF;
+  else if (!(thr > 0.f)) c = -32768;
+  else c = min((int)__half_as_ushort(__float2half_ru(thr)) + 3, 0x7FFF);
+  return ((uint32_t)c & 0xFFFFu) * 0x10001u;
+}
 __device__ __forceinline__ float tc_min3(float a, float b, float c) {
   float r;
   asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));  // SASS FMNMX3
@@ -164,6 +231,7 @@ __device__ __forceinline__ uint64_t tc_desc_hi() {  // everything but the start 
 // instruction descriptor: D = F32 (bits 4-5 = 1), A = B = F16 (0), both K-major, N>>3 at bit 17,
 // M>>4 at bit 24
 constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(TC_SUB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+constexpr uint32_t TC_IDESC_D16 = TC_IDESC & ~(3u << 4);  // D = F16 (bits 4-5 = 0)
 
 // byte offset of (row r, K chunk c) inside an interleaved operand tile
 __host__ __device__ __forceinline__ uint32_t tc_row_off(int r, int c) {
@@ -269,6 +337,7 @@ __device__ __forceinline__ float tc_rescan_warp(const float4* __restrict__ packe
 // The rare path of the epilogue (inlined: a call boundary measured 1.5 % slower): the warp takes its
 // flagged queries (lane = query) one by one and re-scans the 64 rows starting at row0 for each.  q0 = index of lane 0's query; thr / eps = the 32 thresholds and
 // margins of this warp's queries in shared memory.
+template <bool ACC16>
 __device__ __forceinline__ void tc_rescan_flagged(const NNTCParams& p, bool flagged, int64_t q0, int64_t row0,
                                                float mm_max, float* thr, const float* eps) {
   const int lane = threadIdx.x & 31;
@@ -283,13 +352,23 @@ __device__ __forceinline__ void tc_rescan_flagged(const NNTCParams& p, bool flag
       // later rows only matter if they can reach d2 <= found.  Four warps share a query's threshold;
       // a lost update only leaves it higher than necessary (more re-scans).
       const float nt_thr = found + eps[src];
-      if (nt_thr < thr[src]) thr[src] = nt_thr;
+      if (ACC16) {  // thresholds are kept as packed 16-bit codes (tc_thr16)
+        uint32_t* thr16 = reinterpret_cast<uint32_t*>(thr);
+        const uint32_t c = tc_thr16(nt_thr);
+        if ((short)(c & 0xFFFFu) < (short)(thr16[src] & 0xFFFFu)) thr16[src] = c;
+      } else if (nt_thr < thr[src]) {
+        thr[src] = nt_thr;
+      }
       atomicAdd(p.stats, 1ull);
     }
   }
   __syncwarp();
 }
 
+// ACC16: the accumulators are f16 (D format of the instruction descriptor), read back packed and folded
+// as 16-bit integers — see the epilogue below.  ACC16 = false is the f32-accumulator version
+// (VO_NN_TC_ACC=32), kept as the comparator.
+template <bool ACC16>
 __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCParams p) {
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   unsigned char* sA = tc_smem;
@@ -310,16 +389,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
 #pragma unroll
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], TC_PIPES);  // one commit per MMA warp
+      mbar_init(&empty[s], TC_BUFS);  // one commit per MMA warp
     }
 #pragma unroll
     for (int b = 0; b < TC_BUFS; ++b) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], TC_PIPE_WARPS);
+      mbar_init(&tempty[b], ACC16 ? TC_PIPE_WARPS / 2 : TC_PIPE_WARPS);
     }
     mbar_fence_init();
   }
-  if (warp == TC_EPI_WARPS + 1) tmem_alloc(tmem_slot, 512);  // the whole tensor memory of the SM
+  if (warp == TC_EPI_WARPS) tmem_alloc(tmem_slot, 512);  // the whole tensor memory of the SM
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -378,7 +457,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
         unsigned char* dst = sA + (i >> 7) * TC_A_BYTES;
         *reinterpret_cast<uint4*>(dst + tc_row_off(i & 127, 0)) = *reinterpret_cast<const uint4*>(&v[0]);
         *reinterpret_cast<uint4*>(dst + tc_row_off(i & 127, 1)) = *reinterpret_cast<const uint4*>(&v[8]);
-        thr_s[i] = thr;
+        if (ACC16) reinterpret_cast<uint32_t*>(thr_s)[i] = tc_thr16(thr);
+        else thr_s[i] = thr;
         eps_s[i] = eps;
       }
       // the tensor core reads shared memory through the async proxy
@@ -386,59 +466,140 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
     }
     __syncthreads();
 
-    if (warp == TC_EPI_WARPS) {
-      // ===== TMA producer ==========================================================================
+    if (warp >= TC_EPI_WARPS) {
+      // ===== MMA issuer of buffer `buf` = pipeline `pipe` (rows [pipe*128, +128) of every map tile),
+      // every second accumulator of that pipeline.  ONE thread runs the whole loop.  A thread needs
+      // ~100 cycles to issue a tcgen05.mma and ~60 for the commit whatever the shape (in-kernel
+      // counters, make TC_PROFILE=1), several threads issue in parallel: with one issuer per pipeline
+      // the issuing threads were the limit of the whole kernel (430 cycles per accumulator), hence one
+      // per buffer.
+      const int buf = warp - TC_EPI_WARPS;
+      const int pipe = buf % TC_PIPES;
+      const uint32_t bsel = (uint32_t)(buf / TC_PIPES);
       if (lane == 0) {
-        for (int64_t i = 0; i < nt; ++i) {
+        const uint32_t a_desc0 = (uint32_t)((smem_u32(sA) >> 4) & 0x3FFF);
+        // accumulator f of this segment (f = tile * qt + a) is number acc_n + f of the pipeline and lands
+        // in buffer (acc_n + f) & 1; k counts the uses of this buffer
+        int a = (int)((acc_n ^ bsel) & 1u);
+        uint32_t k = (acc_n + (uint32_t)a) >> 1;
+        // buffer 0's thread is also the TMA producer: 256-row map tiles, TC_LOOKAHEAD ahead of the
+        // one being multiplied, into a ring of TC_STAGES (a stage is free once all four issuers have
+        // committed the MMAs that read it)
+        auto request = [&](int64_t i) {
           const uint32_t n = unit_n + (uint32_t)i;
           const int s = (int)(n % TC_STAGES);
           mbar_wait(&empty[s], ((n / TC_STAGES) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&full[s], TC_TILE_BYTES);
-          tma_load_1d(sB + s * TC_TILE_BYTES, p.tiles16 + (t0 + i) * (int64_t)TC_TILE_BYTES, TC_TILE_BYTES,
-                      &full[s]);
-        }
-      }
-      __syncwarp();
-    } else if (warp > TC_EPI_WARPS) {
-      // ===== MMA issuer of pipeline `pipe`: rows [pipe*128, +128) of every map tile ==================
-      // The loop is warp-uniform (all lanes track the same counters); one lane issues.  A single
-      // thread needs ~100 cycles of instruction latency per MMA + commit + barrier wait, which is
-      // why each pipeline has its own issuing warp (profiles/r02d_ncu_nn_tc.md).
-      const int pipe = warp - (TC_EPI_WARPS + 1);
-      const uint32_t a_desc0 = (uint32_t)((smem_u32(sA) >> 4) & 0x3FFF);
-      uint32_t n_acc = acc_n;
-      for (int64_t i = 0; i < nt; ++i) {
-        const uint32_t n = unit_n + (uint32_t)i;
-        const int s = (int)(n % TC_STAGES);
-        TC_PROF_T(pa);
-        mbar_wait(&full[s], (n / TC_STAGES) & 1u);
-        TC_PROF_ADD(4, pa);
-        tc_fence_after();
-        const uint64_t bdesc = tc_desc(smem_u32(sB + s * TC_TILE_BYTES) + pipe * (TC_SUB * TC_ROW_BYTES));
-        for (int a = 0; a < qt; ++a) {
-          const int buf = pipe + TC_PIPES * (int)(n_acc & 1u);
-          TC_PROF_T(pb);
-          mbar_wait(&tempty[buf], ((n_acc >> 1) & 1u) ^ 1u);
-          TC_PROF_ADD(5, pb);
-          TC_PROF_T(pc);
+          tma_load_1d(sB + s * TC_TILE_BYTES, p.tiles16 + (t0 + i) * (int64_t)TC_TILE_BYTES, TC_TILE_BYTES, &full[s]);
+        };
+        if (buf == 0)
+          for (int64_t i = 0; i < min(nt, (int64_t)TC_LOOKAHEAD); ++i) request(i);
+        for (int64_t i = 0; i < nt; ++i) {
+          if (buf == 0 && i + TC_LOOKAHEAD < nt) request(i + TC_LOOKAHEAD);
+          const uint32_t n = unit_n + (uint32_t)i;
+          const int s = (int)(n % TC_STAGES);
+          TC_PROF_T(pa);
+          mbar_wait(&full[s], (n / TC_STAGES) & 1u);
+          TC_PROF_ADD(4, pa);
           tc_fence_after();
-          TC_PROF_ADD(6, pc);
-          if (lane == 0) {
+          const uint64_t bdesc = tc_desc(smem_u32(sB + s * TC_TILE_BYTES) + pipe * (TC_SUB * TC_ROW_BYTES));
+          for (; a < qt; a += 2, ++k) {
+            TC_PROF_T(pb);
+            mbar_wait(&tempty[buf], (k & 1u) ^ 1u);
+            TC_PROF_ADD(5, pb);
+            tc_fence_after();
             TC_PROF_T(pd);
             tc_mma_f16((uint32_t)buf * TC_SUB, tc_desc_hi() | (uint64_t)(a_desc0 + a * (TC_A_BYTES >> 4)), bdesc,
-                       TC_IDESC);
+                       ACC16 ? TC_IDESC_D16 : TC_IDESC);
             TC_PROF_ADD(7, pd);
             TC_PROF_T(pe);
             tc_commit(&tfull[buf]);
             TC_PROF_ADD(3, pe);
           }
-          TC_PROF_T(pf);
-          __syncwarp();
-          TC_PROF_ADD(2, pf);
-          ++n_acc;
+          a -= qt;
+          tc_commit(&empty[s]);  // the stage is free once every MMA above has read it
         }
-        if (lane == 0) tc_commit(&empty[s]);  // the stage is free once every MMA above has read it
-        __syncwarp();
+      }
+      __syncwarp();
+    } else if (ACC16) {
+      // ===== f16-accumulator epilogue.  Of the 8 warps of pipeline `pipe`, warps 0-3 (one per lane
+      // quadrant) drain buffer `pipe`, warps 4-7 buffer `pipe + 2`: a warp takes every SECOND
+      // accumulator of its pipeline and reads all 128 columns of it — two packed loads of 64 columns
+      // through one 32-register buffer, 16 VIMNMX3.S16x2 each.  Per 4096 pairs a warp executes about
+      // as many instructions as the f32 epilogue needs for 2048.
+      const int pipe = warp / TC_PIPE_WARPS, w8 = warp % TC_PIPE_WARPS;
+      const int quad = w8 & 3;
+      const uint32_t bsel = (uint32_t)(w8 >> 2);
+      const int buf = pipe + TC_PIPES * (int)bsel;
+      uint32_t t_addr = ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * TC_SUB;
+      uint32_t full_addr = smem_u32(&tfull[buf]), empty_addr = smem_u32(&tempty[buf]);
+      uint32_t thr_addr0 = smem_u32(thr_s + quad * 32 + lane);
+      asm volatile("mov.u32 %0, %0;\nmov.u32 %1, %1;\nmov.u32 %2, %2;\nmov.u32 %3, %3;"
+                   : "+r"(t_addr), "+r"(full_addr), "+r"(empty_addr), "+r"(thr_addr0));
+      const uint32_t arrive_lane = lane;
+      // accumulator f of this segment (f = unit * qt + a) is number acc_n + f of the pipeline and lands
+      // in buffer (acc_n + f) & 1
+      const uint32_t total = (uint32_t)(nt * qt);
+      uint32_t f = (acc_n ^ bsel) & 1u;
+      uint32_t par = ((acc_n + f) >> 1) & 1u;
+      int a = (int)f;
+      int64_t unit = 0;
+      while (a >= qt) {
+        a -= qt;
+        ++unit;
+      }
+      for (; f < total; f += 2) {
+        TC_PROF_T(pa);
+        uint32_t my_thr;  // packed code, read before the wait: its latency hides behind it
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(my_thr) : "r"(thr_addr0 + (uint32_t)a * 512u) : "memory");
+        {
+          uint32_t ok;
+          do {
+            asm volatile(
+                "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                : "=r"(ok)
+                : "r"(full_addr), "r"(par)
+                : "memory");
+          } while (!ok);
+        }
+        TC_PROF_ADD(1, pa);
+        TC_PROF_T(pb);
+        tc_fence_after();
+        uint32_t mA, mB;
+        {
+          uint32_t r[32];
+          tc_ld32_pack(t_addr, r);
+          tc_wait_ld();
+          mA = tc_fold16(r);
+          tc_ld32_pack(t_addr + 64, r);
+          tc_wait_ld();
+          // the buffer may be overwritten as soon as its four warps have read it
+          tc_fence_before();
+          __syncwarp();
+          asm volatile(
+              "{\n.reg .pred p;\nsetp.eq.u32 p, %1, 0;\n@p mbarrier.arrive.shared::cta.b64 _, [%0];\n}" ::"r"(empty_addr),
+              "r"(arrive_lane)
+              : "memory");
+          TC_PROF_ADD(2, pb);
+          mB = tc_fold16(r);
+        }
+        TC_PROF_T(pc);
+        par ^= 1u;
+        // some half below its threshold code  <=>  max(m, c) != m
+        const uint32_t mAB = tc_min_s16x2(mA, mB);
+        if (__any_sync(0xffffffffu, tc_max_s16x2(mAB, my_thr) != mAB)) {
+          const int64_t row0 = (t0 + unit) * TC_BN + pipe * TC_SUB;
+          tc_rescan_flagged<true>(p, tc_max_s16x2(mA, my_thr) != mA, qbase + a * 128 + quad * 32, row0, mm_max,
+                                  thr_s + a * 128 + quad * 32, eps_s + a * 128 + quad * 32);
+          tc_rescan_flagged<true>(p, tc_max_s16x2(mB, my_thr) != mB, qbase + a * 128 + quad * 32, row0 + 64, mm_max,
+                                  thr_s + a * 128 + quad * 32, eps_s + a * 128 + quad * 32);
+        }
+        TC_PROF_ADD(3, pc);
+        a += 2;
+        while (a >= qt) {
+          a -= qt;
+          ++unit;
+        }
       }
     } else {
       // ===== epilogue of pipeline `pipe` (8 warps): drains buffers pipe and pipe+2 in turn, one being
@@ -512,7 +673,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
 
           // `<=`: a query whose threshold is +inf (norm too large for f16) is always re-scanned
           if (__any_sync(0xffffffffu, mn <= my_thr))
-            tc_rescan_flagged(p, mn <= my_thr, qbase + a * 128 + quad * 32,
+            tc_rescan_flagged<false>(p, mn <= my_thr, qbase + a * 128 + quad * 32,
                               (t0 + unit) * TC_BN + pipe * TC_SUB + half * 64, mm_max,
                               thr_s + a * 128 + quad * 32, eps_s + a * 128 + quad * 32);
           TC_PROF_ADD(3, pc);
@@ -524,13 +685,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
   }
 
 #ifdef NN_TC_PROFILE
-  if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == TC_EPI_WARPS + 1))
+  if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == TC_EPI_WARPS))
     for (int i = 1; i < 8; ++i)
       if (prof[i]) atomicAdd(p.stats + (warp == 0 ? 0 : 8) + i, (unsigned long long)prof[i]);
 #endif
   tc_fence_before();
   __syncthreads();
-  if (warp == TC_EPI_WARPS + 1) tmem_dealloc(tmem_base, 512);
+  if (warp == TC_EPI_WARPS) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace vo
@@ -577,8 +738,15 @@ int nn_tc_launch(vo_nn_s* h, const float* queries_dev, int64_t nq, int qstride, 
   p.qt = tc_pick_qt(n_qtiles);
   p.n_groups = (int)((n_qtiles + p.qt - 1) / p.qt);
   p.stats = h->tc_stats.as<unsigned long long>();
+  // f16 accumulators unless VO_NN_TC_ACC=32 asks for the f32-accumulator comparator
+  static const bool acc32 = [] {
+    const char* e = getenv("VO_NN_TC_ACC");
+    return e && !strcmp(e, "32");
+  }();
   if (!h->tc_opted_in) {
-    VO_CUDA(cudaFuncSetAttribute(nn_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VO_CUDA(cudaFuncSetAttribute(nn_tc_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)TC_SMEM_BYTES));
+    VO_CUDA(cudaFuncSetAttribute(nn_tc_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)TC_SMEM_BYTES));
     h->tc_opted_in = true;
   }
@@ -586,7 +754,8 @@ int nn_tc_launch(vo_nn_s* h, const float* queries_dev, int64_t nq, int qstride, 
   const int sms = num_sms(h->device);
   const int64_t units = (int64_t)p.n_groups * p.n_tiles16;
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(sms, units));
-  nn_tc_filter_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(p);
+  if (acc32) nn_tc_filter_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(p);
+  else nn_tc_filter_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(p);
   VO_LAUNCH_CHECK();
   // (queries per thread = 0 marks the tensor-core filter, threads, query groups, CTAs)
   h->last_launches.insert(h->last_launches.end(), {0, TC_THREADS, (int32_t)p.n_groups, (int32_t)grid});
