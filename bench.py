@@ -10,7 +10,7 @@ Primary line (BASELINE.json config 4, the only config that shards across GPUs):
           (it is the database, uploaded once like the reference builds its kd-tree once per map).
   roofline  the tensor-core filter (csrc/nn_tc.cu): executed tensor flop (2 x 16 per pair) against
             the measured dense bf16/f16 peak, with the algorithmic 30 flop per pair and
-            the fraction of the ALU-pipe min throughput (the kernel's real limiter) beside it.
+            the fraction of the measured packed TMEM-read + fold rate beside it.
   cpu_baseline  the REFERENCE's own bruteForceBestMatch (oracle/_ref, built from its sources) on
             all host cores, on a query sample against the full map.
 Extra objects on the same line (N=1 only): "nn_ffma" (the FP32 FFMA2 filter on the same config,
@@ -45,10 +45,13 @@ TRI_BYTES_PER_CORR = 44.0   # 8 pair + 8 + 8 in, 12 + 8 out
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 RADIUS = 0.1
 NN_TC_FLOP_PER_PAIR = 32.0  # what the tensor-core filter executes: K = 16 (10 + norm terms, padded) x 2
-# the epilogue folds every accumulator element into a minimum with 3-input FMNMX3 (2 new elements per
-# instruction) on the ALU pipe, which issues 64 lanes per clock per SM: 128 pairs/clk/SM at best
-# (ncu: the ALU pipe is the busiest unit of nn_tc_filter_kernel, profiles/r02m_ncu_nn_tc.md)
-ALU_MIN_PAIRS_PER_CLK_SM = 128.0
+# Ceilings of the f16-accumulator filter per SM and clock (tools/tc_probe2.cu, profiles/r02p_tc_probe2.md):
+# the MMA itself 256 pairs, the packed 16-bit 3-input min on the ALU pipe 256, 16 warps reading the
+# accumulators back packed and folding them 175 (TMEM read port).  What binds is none of them: all 512
+# TMEM columns hold four 128x128 accumulators, and one takes ~700 cycles from the issue of its MMA
+# until its last column has been read (issue -> barrier-visible alone is 288): 65536 / 700 = 94.
+TMEM_READ_PAIRS_PER_CLK_SM = 175.0
+TMEM_INFLIGHT_PAIRS = 65536.0
 
 
 def nn_workload(Q, M):
@@ -934,10 +937,13 @@ def ours_arm(args):
                     "algorithmic_flop_per_pair": NN_FLOP_PER_PAIR, "algorithmic_tflops": alg_tflops,
                     "algorithmic_frac_of_fp32_peak": alg_tflops / fp32_peak, "fp32_peak": fp32_peak,
                     "fp32_peak_source": peak_src,
-                    "limiter": "ALU pipe: the epilogue's 3-input min, 0.5 instruction per pair at 64 lanes/clk/SM",
+                    "limiter": ("TMEM capacity x latency: four 128x128 f16 accumulators fill the 512 columns; "
+                                "accumulator_round_trip_clk = cycles from the issue of an MMA until its "
+                                "buffer is drained and reissued (issue -> visible alone is 288)"),
                     "pairs_per_clk_per_sm": pairs_pc,
-                    "alu_min_frac": pairs_pc / ALU_MIN_PAIRS_PER_CLK_SM,
-                    "tmem_read_bytes_per_clk_per_sm": 4.0 * pairs_pc,
+                    "accumulator_round_trip_clk": TMEM_INFLIGHT_PAIRS / pairs_pc,
+                    "tmem_read_frac": pairs_pc / TMEM_READ_PAIRS_PER_CLK_SM,
+                    "tmem_read_bytes_per_clk_per_sm": 2.0 * pairs_pc,
                     "rescans_per_query": nn_rescans / max(nq, 1), "kernel_ms": kms}
         else:
             roof = {"bound": "fp32", "achieved": alg_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
