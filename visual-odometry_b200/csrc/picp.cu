@@ -36,9 +36,6 @@ namespace vo {
 #ifndef PICP_THREADS_N
 #define PICP_THREADS_N 384
 #endif
-#ifndef PICP_ALTERNATE
-#define PICP_ALTERNATE 1  // streaming kernel: odd rounds walk the correspondences backwards (L2 reuse)
-#endif
 #ifndef PICP_DEPTH_N
 #define PICP_DEPTH_N 3
 #endif
@@ -636,18 +633,11 @@ picp_stream_kernel(const PicpParams p, const int rounds) {
   const int2* pp = p.pairs + i0;
   extern __shared__ __align__(16) unsigned char picp_ring[];
   const uint32_t ring = smem_u32(picp_ring) + (uint32_t)tid * 8u;
-  // Rounds alternate their direction over the batches (round r walks them forwards when r is even,
-  // backwards when it is odd; `rev` is the direction of the batches being ISSUED).  What a round read
-  // last is what the next one reads first, so the tail of every pass — as much as the 126 MB L2
-  // keeps of the 279 MB a round touches — is served from L2 instead of HBM; a same-direction sweep
-  // over a working set larger than L2 evicts every line before it is needed again.  Only the order of
-  // each thread's partial sums changes with the direction (still a fixed order per round).
-  auto issue_pairs = [&](int b, int slot, bool rev) {  // P(b)
+  auto issue_pairs = [&](int b, int slot) {  // P(b)
     if (b < nb) {
-      const int pb = rev ? nb - 1 - b : b;
 #pragma unroll
       for (int u = 0; u < PICP_UNROLL; ++u) {
-        const int j = pb * PICP_UNROLL + u;
+        const int j = b * PICP_UNROLL + u;
         cp_async8(ring + picp_prs_off(slot, u), pp + (int64_t)(j < mine ? j : 0) * stride);
       }
     }
@@ -670,22 +660,22 @@ picp_stream_kernel(const PicpParams p, const int rounds) {
   };
   // The ring's fill does not depend on the pose, only the arithmetic does: the fill of round r+1
   // (three dependent memory round-trips) is issued while round r is being reduced and solved.
-  auto fill_pairs = [&](bool rev) {  // P(0..DEPTH-1)
+  auto fill_pairs = [&]() {  // P(0..DEPTH-1)
 #pragma unroll
-    for (int j = 0; j < PICP_DEPTH; ++j) issue_pairs(j, j % PICP_SLOTS, rev);
+    for (int j = 0; j < PICP_DEPTH; ++j) issue_pairs(j, j % PICP_SLOTS);
     cp_async_commit();
   };
-  auto fill_gathers = [&](bool rev) {  // G(j) + P(j+DEPTH) as the groups the main loop expects
+  auto fill_gathers = [&]() {  // G(j) + P(j+DEPTH) as the groups the main loop expects
     cp_async_wait<0>();
 #pragma unroll
     for (int j = 0; j < PICP_DEPTH; ++j) {
       issue_gathers(j, j % PICP_SLOTS);
-      issue_pairs(j + PICP_DEPTH, (j + PICP_DEPTH) % PICP_SLOTS, rev);
+      issue_pairs(j + PICP_DEPTH, (j + PICP_DEPTH) % PICP_SLOTS);
       cp_async_commit();
     }
   };
-  fill_pairs(false);
-  fill_gathers(false);
+  fill_pairs();
+  fill_gathers();
 
 #ifdef PICP_PROFILE
   long long prof[6] = {0, 0, 0, 0, 0, 0};
@@ -711,7 +701,6 @@ picp_stream_kernel(const PicpParams p, const int rounds) {
   a.n_in = 0;
 
   {
-    const bool rev = PICP_ALTERNATE && (round & 1);
     for (int b0 = 0; b0 < nb; b0 += PICP_SLOTS) {
 #pragma unroll
       for (int sl = 0; sl < PICP_SLOTS; ++sl) {
@@ -719,9 +708,8 @@ picp_stream_kernel(const PicpParams p, const int rounds) {
         if (b < nb) {
           cp_async_wait<PICP_DEPTH - 1>();  // G(b) and P(b+DEPTH) have landed
           issue_gathers(b + PICP_DEPTH, (sl + PICP_DEPTH) % PICP_SLOTS);
-          issue_pairs(b + 2 * PICP_DEPTH, (sl + 2 * PICP_DEPTH) % PICP_SLOTS, rev);
+          issue_pairs(b + 2 * PICP_DEPTH, (sl + 2 * PICP_DEPTH) % PICP_SLOTS);
           cp_async_commit();
-          const int j0 = (rev ? nb - 1 - b : b) * PICP_UNROLL;  // first item of the batch
 #pragma unroll
           for (int pi = 0; pi < PICP_UNROLL / 2; ++pi)
             picp_point2<PINHOLE, KEEP>(p, c, lds_f2(ring + picp_pts_off(sl, pi, 0)),
@@ -729,14 +717,14 @@ picp_stream_kernel(const PicpParams p, const int rounds) {
                                        lds_f2(ring + picp_pts_off(sl, pi, 2)),
                                        lds_f2(ring + picp_pts_off(sl, pi, 3)),
                                        lds_f2(ring + picp_pts_off(sl, pi, 4)),
-                                       j0 + 2 * pi + 1 < mine, a, j0 + 2 * pi < mine);
+                                       b * PICP_UNROLL + 2 * pi + 1 < mine, a, b * PICP_UNROLL + 2 * pi < mine);
         }
       }
     }
     cp_async_wait<0>();
     // next round's pair loads go out now; its gathers follow after the warp reduction below
     const bool more = round + 1 < rounds;
-    if (more) fill_pairs(PICP_ALTERNATE && !(round & 1));
+    if (more) fill_pairs();
   }
   PP_ADD(0, t_loop);
   PP_T(t_red);
@@ -780,7 +768,7 @@ picp_stream_kernel(const PicpParams p, const int rounds) {
   PP_T(t_bar);
   // the next round's gathers go out while the other CTAs arrive: they are in flight across the
   // barrier, the cross-CTA sum and the solve
-  if (round + 1 < rounds) fill_gathers(PICP_ALTERNATE && !(round & 1));
+  if (round + 1 < rounds) fill_gathers();
 
   // ---- every block: fixed-order sum over all blocks' partials, solve, own copy of the pose -------
   // One grid-wide barrier per round; the partial buffers alternate with the round's parity, so a
