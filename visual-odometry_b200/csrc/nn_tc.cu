@@ -72,6 +72,16 @@ constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_PIPES = TC_BN / TC_SUB;    // 2 independent MMA->epilogue pipelines (halves of a map tile)
 constexpr int TC_PIPE_WARPS = TC_EPI_WARPS / TC_PIPES;     // 8 epilogue warps per pipeline
 constexpr int TC_BUFS = 4;                  // TMEM accumulator buffers of TC_SUB columns; pipeline p owns p, p+2
+#ifndef TC_HALVES_N
+#define TC_HALVES_N 1
+#endif
+// TC_HALVES = 2 fills and releases a buffer in two independent column halves (one MMA of N = 64 each,
+// own full/empty barriers) so that the refill of the first half is under way while the second is
+// still being read.  Measured SLOWER (433 against 397 ms at the headline size): an issuing thread
+// needs ~400 cycles per MMA + commit + barrier wait, two per accumulator make the four issuers the
+// limit again.  Kept as a switch.
+constexpr int TC_HALVES = TC_HALVES_N;
+constexpr int TC_HCOLS = TC_SUB / TC_HALVES;
 // + one MMA-issuing warp per buffer (the first also requests the map tiles).  20 warps = 5 per
 // scheduler partition of the register file: 96 registers per thread (a 21st warp would cap all at 80)
 constexpr int TC_THREADS = (TC_EPI_WARPS + TC_BUFS) * 32;
@@ -82,7 +92,7 @@ constexpr float TC_MAX_NORM = 30000.f;      // |m|^2, |q|^2 above this do not fi
 constexpr size_t TC_SMEM_A = (size_t)TC_QT_MAX * TC_A_BYTES;            // 64 KB
 constexpr size_t TC_SMEM_B = (size_t)TC_STAGES * TC_TILE_BYTES;         // 32 KB
 constexpr size_t TC_SMEM_THR = (size_t)TC_QT_MAX * 128 * sizeof(float); // 8 KB (x2: thr, eps)
-constexpr size_t TC_SMEM_BYTES = TC_SMEM_A + TC_SMEM_B + 2 * TC_SMEM_THR + 256;
+constexpr size_t TC_SMEM_BYTES = TC_SMEM_A + TC_SMEM_B + 2 * TC_SMEM_THR + 512;
 
 struct NNTCParams {
   const unsigned char* tiles16;  // f16 map tiles, TC_TILE_BYTES each, 8-row interleaved
@@ -124,19 +134,6 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
       "{\n.reg .pred p;\nsetp.ne.b32 p, 0, 0;\n"  // p = false: D = A*B (no accumulation)
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
-        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
-        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
-        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
       : "memory");
 }
 // 64 columns of an f16 accumulator: two adjacent columns (their low halves) per register
@@ -202,22 +199,6 @@ __device__ __forceinline__ uint32_t tc_thr16(float thr) {
   else c = min((int)__half_as_ushort(__float2half_ru(thr)) + 3, 0x7FFF);
   return ((uint32_t)c & 0xFFFFu) * 0x10001u;
 }
-__device__ __forceinline__ float tc_min3(float a, float b, float c) {
-  float r;
-  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));  // SASS FMNMX3
-  return r;
-}
-// minimum of 32 accumulator columns, folded into four independent chains (a single chain of
-// dependent 3-input mins would leave the warp waiting on its own latency)
-__device__ __forceinline__ void tc_fold(float (&mn)[4], const uint32_t (&r)[32]) {
-#pragma unroll
-  for (int j = 0; j < 32; j += 8) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-      mn[c] = tc_min3(mn[c], __uint_as_float(r[j + 2 * c]), __uint_as_float(r[j + 2 * c + 1]));
-  }
-}
-
 // Shared-memory matrix descriptor: K-major, no swizzle.  A core matrix is 8 rows x 16 bytes stored
 // as 128 contiguous bytes; the two 16-byte K chunks of one instruction are `lbo` bytes apart,
 // consecutive 8-row groups `sbo` bytes (layout verified on hardware by tools/tc_probe.cu).
@@ -228,10 +209,9 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr) {
 __device__ __forceinline__ uint64_t tc_desc_hi() {  // everything but the start address
   return ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
 }
-// instruction descriptor: D = F32 (bits 4-5 = 1), A = B = F16 (0), both K-major, N>>3 at bit 17,
-// M>>4 at bit 24
-constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(TC_SUB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-constexpr uint32_t TC_IDESC_D16 = TC_IDESC & ~(3u << 4);  // D = F16 (bits 4-5 = 0)
+// instruction descriptor: D = F16 (bits 4-5 = 0; 1 would be F32), A = B = F16 (0), both K-major,
+// N>>3 at bit 17, M>>4 at bit 24
+constexpr uint32_t TC_IDESC_D16 = ((uint32_t)(TC_HCOLS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 // byte offset of (row r, K chunk c) inside an interleaved operand tile
 __host__ __device__ __forceinline__ uint32_t tc_row_off(int r, int c) {
@@ -337,9 +317,8 @@ __device__ __forceinline__ float tc_rescan_warp(const float4* __restrict__ packe
 // The rare path of the epilogue (inlined: a call boundary measured 1.5 % slower): the warp takes its
 // flagged queries (lane = query) one by one and re-scans the 64 rows starting at row0 for each.  q0 = index of lane 0's query; thr / eps = the 32 thresholds and
 // margins of this warp's queries in shared memory.
-template <bool ACC16>
 __device__ __forceinline__ void tc_rescan_flagged(const NNTCParams& p, bool flagged, int64_t q0, int64_t row0,
-                                               float mm_max, float* thr, const float* eps) {
+                                               float mm_max, uint32_t* thr, const float* eps) {
   const int lane = threadIdx.x & 31;
   unsigned pending = __ballot_sync(0xffffffffu, flagged);
   while (pending) {
@@ -352,35 +331,27 @@ __device__ __forceinline__ void tc_rescan_flagged(const NNTCParams& p, bool flag
       // later rows only matter if they can reach d2 <= found.  Four warps share a query's threshold;
       // a lost update only leaves it higher than necessary (more re-scans).
       const float nt_thr = found + eps[src];
-      if (ACC16) {  // thresholds are kept as packed 16-bit codes (tc_thr16)
-        uint32_t* thr16 = reinterpret_cast<uint32_t*>(thr);
-        const uint32_t c = tc_thr16(nt_thr);
-        if ((short)(c & 0xFFFFu) < (short)(thr16[src] & 0xFFFFu)) thr16[src] = c;
-      } else if (nt_thr < thr[src]) {
-        thr[src] = nt_thr;
-      }
+      // thresholds are kept as packed 16-bit codes (tc_thr16)
+      const uint32_t c = tc_thr16(nt_thr);
+      if ((short)(c & 0xFFFFu) < (short)(thr[src] & 0xFFFFu)) thr[src] = c;
       atomicAdd(p.stats, 1ull);
     }
   }
   __syncwarp();
 }
 
-// ACC16: the accumulators are f16 (D format of the instruction descriptor), read back packed and folded
-// as 16-bit integers — see the epilogue below.  ACC16 = false is the f32-accumulator version
-// (VO_NN_TC_ACC=32), kept as the comparator.
-template <bool ACC16>
 __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCParams p) {
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   unsigned char* sA = tc_smem;
   unsigned char* sB = tc_smem + TC_SMEM_A;
-  float* thr_s = reinterpret_cast<float*>(tc_smem + TC_SMEM_A + TC_SMEM_B);  // [qt][128]
-  float* eps_s = thr_s + TC_QT_MAX * 128;
+  uint32_t* thr_s = reinterpret_cast<uint32_t*>(tc_smem + TC_SMEM_A + TC_SMEM_B);  // [qt][128] packed codes
+  float* eps_s = reinterpret_cast<float*>(thr_s + TC_QT_MAX * 128);
   uint64_t* bars = reinterpret_cast<uint64_t*>(eps_s + TC_QT_MAX * 128);
   uint64_t* full = bars;                       // [TC_STAGES]  TMA bytes landed
   uint64_t* empty = full + TC_STAGES;          // [TC_STAGES]  every MMA reading the stage is done
-  uint64_t* tfull = empty + TC_STAGES;         // [TC_BUFS]    accumulator written
-  uint64_t* tempty = tfull + TC_BUFS;          // [TC_BUFS]    accumulator drained (the 4 warps of a warpgroup)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + TC_BUFS);
+  uint64_t* tfull = empty + TC_STAGES;               // [TC_BUFS * TC_HALVES]  accumulator half written
+  uint64_t* tempty = tfull + TC_BUFS * TC_HALVES;    // [TC_BUFS * TC_HALVES]  drained by its four warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + TC_BUFS * TC_HALVES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qt = p.qt;
@@ -392,9 +363,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
       mbar_init(&empty[s], TC_BUFS);  // one commit per MMA warp
     }
 #pragma unroll
-    for (int b = 0; b < TC_BUFS; ++b) {
+    for (int b = 0; b < TC_BUFS * TC_HALVES; ++b) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], ACC16 ? TC_PIPE_WARPS / 2 : TC_PIPE_WARPS);
+      mbar_init(&tempty[b], 4);  // one warp per lane quadrant
     }
     mbar_fence_init();
   }
@@ -457,8 +428,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
         unsigned char* dst = sA + (i >> 7) * TC_A_BYTES;
         *reinterpret_cast<uint4*>(dst + tc_row_off(i & 127, 0)) = *reinterpret_cast<const uint4*>(&v[0]);
         *reinterpret_cast<uint4*>(dst + tc_row_off(i & 127, 1)) = *reinterpret_cast<const uint4*>(&v[8]);
-        if (ACC16) reinterpret_cast<uint32_t*>(thr_s)[i] = tc_thr16(thr);
-        else thr_s[i] = thr;
+        thr_s[i] = tc_thr16(thr);
         eps_s[i] = eps;
       }
       // the tensor core reads shared memory through the async proxy
@@ -504,24 +474,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
           tc_fence_after();
           const uint64_t bdesc = tc_desc(smem_u32(sB + s * TC_TILE_BYTES) + pipe * (TC_SUB * TC_ROW_BYTES));
           for (; a < qt; a += 2, ++k) {
-            TC_PROF_T(pb);
-            mbar_wait(&tempty[buf], (k & 1u) ^ 1u);
-            TC_PROF_ADD(5, pb);
-            tc_fence_after();
-            TC_PROF_T(pd);
-            tc_mma_f16((uint32_t)buf * TC_SUB, tc_desc_hi() | (uint64_t)(a_desc0 + a * (TC_A_BYTES >> 4)), bdesc,
-                       ACC16 ? TC_IDESC_D16 : TC_IDESC);
-            TC_PROF_ADD(7, pd);
-            TC_PROF_T(pe);
-            tc_commit(&tfull[buf]);
-            TC_PROF_ADD(3, pe);
+            const uint64_t adesc = tc_desc_hi() | (uint64_t)(a_desc0 + a * (TC_A_BYTES >> 4));
+#pragma unroll
+            for (int h = 0; h < TC_HALVES; ++h) {
+              TC_PROF_T(pb);
+              mbar_wait(&tempty[buf * TC_HALVES + h], (k & 1u) ^ 1u);
+              TC_PROF_ADD(5, pb);
+              tc_fence_after();
+              TC_PROF_T(pd);
+              tc_mma_f16((uint32_t)(buf * TC_SUB + h * TC_HCOLS), adesc, bdesc + (uint64_t)((h * TC_HCOLS * TC_ROW_BYTES) >> 4),
+                         TC_IDESC_D16);
+              TC_PROF_ADD(7, pd);
+              TC_PROF_T(pe);
+              tc_commit(&tfull[buf * TC_HALVES + h]);
+              TC_PROF_ADD(3, pe);
+            }
           }
           a -= qt;
           tc_commit(&empty[s]);  // the stage is free once every MMA above has read it
         }
       }
       __syncwarp();
-    } else if (ACC16) {
+    } else {
       // ===== f16-accumulator epilogue.  Of the 8 warps of pipeline `pipe`, warps 0-3 (one per lane
       // quadrant) drain buffer `pipe`, warps 4-7 buffer `pipe + 2`: a warp takes every SECOND
       // accumulator of its pipeline and reads all 128 columns of it — two packed loads of 64 columns
@@ -532,7 +506,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
       const uint32_t bsel = (uint32_t)(w8 >> 2);
       const int buf = pipe + TC_PIPES * (int)bsel;
       uint32_t t_addr = ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * TC_SUB;
-      uint32_t full_addr = smem_u32(&tfull[buf]), empty_addr = smem_u32(&tempty[buf]);
+      uint32_t full_addr = smem_u32(&tfull[buf * TC_HALVES]), empty_addr = smem_u32(&tempty[buf * TC_HALVES]);
       uint32_t thr_addr0 = smem_u32(thr_s + quad * 32 + lane);
       asm volatile("mov.u32 %0, %0;\nmov.u32 %1, %1;\nmov.u32 %2, %2;\nmov.u32 %3, %3;"
                    : "+r"(t_addr), "+r"(full_addr), "+r"(empty_addr), "+r"(thr_addr0));
@@ -548,20 +522,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
         a -= qt;
         ++unit;
       }
+      auto wait_full = [&](uint32_t addr) {
+        uint32_t ok;
+        do {
+          asm volatile(
+              "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+              : "=r"(ok)
+              : "r"(addr), "r"(par)
+              : "memory");
+        } while (!ok);
+      };
+      // the half may be overwritten as soon as its four warps have read it
+      auto release = [&](uint32_t addr) {
+        tc_fence_before();
+        __syncwarp();
+        asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, %1, 0;\n@p mbarrier.arrive.shared::cta.b64 _, [%0];\n}" ::"r"(addr),
+                     "r"(arrive_lane)
+                     : "memory");
+      };
       for (; f < total; f += 2) {
         TC_PROF_T(pa);
         uint32_t my_thr;  // packed code, read before the wait: its latency hides behind it
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(my_thr) : "r"(thr_addr0 + (uint32_t)a * 512u) : "memory");
-        {
-          uint32_t ok;
-          do {
-            asm volatile(
-                "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                : "=r"(ok)
-                : "r"(full_addr), "r"(par)
-                : "memory");
-          } while (!ok);
-        }
+        wait_full(full_addr);
         TC_PROF_ADD(1, pa);
         TC_PROF_T(pb);
         tc_fence_after();
@@ -570,16 +553,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
           uint32_t r[32];
           tc_ld32_pack(t_addr, r);
           tc_wait_ld();
-          mA = tc_fold16(r);
+          if (TC_HALVES == 2) {
+            release(empty_addr);
+            mA = tc_fold16(r);
+            wait_full(full_addr + 8u);
+            tc_fence_after();
+          } else {
+            mA = tc_fold16(r);
+          }
           tc_ld32_pack(t_addr + 64, r);
           tc_wait_ld();
-          // the buffer may be overwritten as soon as its four warps have read it
-          tc_fence_before();
-          __syncwarp();
-          asm volatile(
-              "{\n.reg .pred p;\nsetp.eq.u32 p, %1, 0;\n@p mbarrier.arrive.shared::cta.b64 _, [%0];\n}" ::"r"(empty_addr),
-              "r"(arrive_lane)
-              : "memory");
+          release(empty_addr + (TC_HALVES == 2 ? 8u : 0u));
           TC_PROF_ADD(2, pb);
           mB = tc_fold16(r);
         }
@@ -589,9 +573,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
         const uint32_t mAB = tc_min_s16x2(mA, mB);
         if (__any_sync(0xffffffffu, tc_max_s16x2(mAB, my_thr) != mAB)) {
           const int64_t row0 = (t0 + unit) * TC_BN + pipe * TC_SUB;
-          tc_rescan_flagged<true>(p, tc_max_s16x2(mA, my_thr) != mA, qbase + a * 128 + quad * 32, row0, mm_max,
+          tc_rescan_flagged(p, tc_max_s16x2(mA, my_thr) != mA, qbase + a * 128 + quad * 32, row0, mm_max,
                                   thr_s + a * 128 + quad * 32, eps_s + a * 128 + quad * 32);
-          tc_rescan_flagged<true>(p, tc_max_s16x2(mB, my_thr) != mB, qbase + a * 128 + quad * 32, row0 + 64, mm_max,
+          tc_rescan_flagged(p, tc_max_s16x2(mB, my_thr) != mB, qbase + a * 128 + quad * 32, row0 + 64, mm_max,
                                   thr_s + a * 128 + quad * 32, eps_s + a * 128 + quad * 32);
         }
         TC_PROF_ADD(3, pc);
@@ -599,84 +583,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
         while (a >= qt) {
           a -= qt;
           ++unit;
-        }
-      }
-    } else {
-      // ===== epilogue of pipeline `pipe` (8 warps): drains buffers pipe and pipe+2 in turn, one being
-      // refilled by the tensor core while the other is read; thread = TMEM lane = query, and the two
-      // warps of a lane quadrant split the 128 columns ============================================
-      // ncu (profiles/r02m_ncu_nn_tc.md): the ALU pipe — where FMNMX3 executes, 64 lanes per clock per
-      // SM — is the busiest unit (76 %), and only a third of the instructions are the mins.  Everything
-      // else in this loop is therefore kept to a minimum: barrier and TMEM addresses are computed
-      // once, the buffer/phase bookkeeping is two XORs, the threshold is read before the wait, the
-      // arrive is predicated (no branch) and the re-scan hides behind one warp vote.
-      const int pipe = warp / TC_PIPE_WARPS, w8 = warp % TC_PIPE_WARPS;
-      const int quad = w8 & 3, half = w8 >> 2;
-      const uint32_t tlane = ((uint32_t)(quad * 32) << 16) + (uint32_t)half * 64;
-      // buffer `sel` of this pipeline: TMEM columns + sel * 256, barriers + sel * 16 bytes.  The
-      // addresses go through an opaque move so that ptxas keeps them in registers instead of
-      // re-deriving them (generic -> shared conversion, lane arithmetic) in every iteration.
-      uint32_t t_addr0 = tlane + (uint32_t)pipe * TC_SUB;
-      uint32_t full_addr0 = smem_u32(&tfull[pipe]), empty_addr0 = smem_u32(&tempty[pipe]);
-      uint32_t thr_addr0 = smem_u32(thr_s + quad * 32 + lane);
-      asm volatile("mov.u32 %0, %0;\nmov.u32 %1, %1;\nmov.u32 %2, %2;\nmov.u32 %3, %3;"
-                   : "+r"(t_addr0), "+r"(full_addr0), "+r"(empty_addr0), "+r"(thr_addr0));
-      const uint32_t arrive_lane = lane;
-      uint32_t sel = acc_n & 1u, par = (acc_n >> 1) & 1u;  // buffer of this pipeline, phase of its barrier
-      for (int64_t unit = 0; unit < nt; ++unit) {
-        uint32_t thr_addr = thr_addr0;
-#pragma unroll 4
-        for (int a = 0; a < qt; ++a, thr_addr += 128 * sizeof(float)) {
-          TC_PROF_T(pa);
-          float my_thr;  // read before the wait: its latency hides behind it
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(my_thr) : "r"(thr_addr) : "memory");
-          {
-            uint32_t ok;
-            do {
-              asm volatile(
-                  "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                  : "=r"(ok)
-                  : "r"(full_addr0 + sel * (TC_PIPES * 8u)), "r"(par)
-                  : "memory");
-            } while (!ok);
-          }
-          TC_PROF_ADD(1, pa);
-          TC_PROF_T(pb);
-          tc_fence_after();
-          // two 32-column loads through ONE register buffer: the dependent tcgen05.ld latency is only
-          // ~35 cycles (tools/tc_probe.cu), and 32 fewer live registers let ptxas keep every address
-          // of this loop in registers
-          const uint32_t taddr = t_addr0 + sel * (uint32_t)(TC_PIPES * TC_SUB);
-          float m4[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
-          {
-            uint32_t r[32];
-            tc_ld32(taddr, r);
-            tc_wait_ld();
-            tc_fold(m4, r);
-            tc_ld32(taddr + 32, r);
-            tc_wait_ld();
-            // the buffer may be overwritten as soon as all eight warps have read it
-            tc_fence_before();
-            __syncwarp();
-            asm volatile(
-                "{\n.reg .pred p;\nsetp.eq.u32 p, %1, 0;\n@p mbarrier.arrive.shared::cta.b64 _, [%0];\n}" ::"r"(
-                    empty_addr0 + sel * (TC_PIPES * 8u)),
-                "r"(arrive_lane)
-                : "memory");
-            TC_PROF_ADD(2, pb);
-            tc_fold(m4, r);
-          }
-          TC_PROF_T(pc);
-          const float mn = fminf(tc_min3(m4[0], m4[1], m4[2]), m4[3]);
-          par ^= sel;  // the phase flips every second accumulator
-          sel ^= 1u;
-
-          // `<=`: a query whose threshold is +inf (norm too large for f16) is always re-scanned
-          if (__any_sync(0xffffffffu, mn <= my_thr))
-            tc_rescan_flagged<false>(p, mn <= my_thr, qbase + a * 128 + quad * 32,
-                              (t0 + unit) * TC_BN + pipe * TC_SUB + half * 64, mm_max,
-                              thr_s + a * 128 + quad * 32, eps_s + a * 128 + quad * 32);
-          TC_PROF_ADD(3, pc);
         }
       }
     }
@@ -738,15 +644,8 @@ int nn_tc_launch(vo_nn_s* h, const float* queries_dev, int64_t nq, int qstride, 
   p.qt = tc_pick_qt(n_qtiles);
   p.n_groups = (int)((n_qtiles + p.qt - 1) / p.qt);
   p.stats = h->tc_stats.as<unsigned long long>();
-  // f16 accumulators unless VO_NN_TC_ACC=32 asks for the f32-accumulator comparator
-  static const bool acc32 = [] {
-    const char* e = getenv("VO_NN_TC_ACC");
-    return e && !strcmp(e, "32");
-  }();
   if (!h->tc_opted_in) {
-    VO_CUDA(cudaFuncSetAttribute(nn_tc_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)TC_SMEM_BYTES));
-    VO_CUDA(cudaFuncSetAttribute(nn_tc_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VO_CUDA(cudaFuncSetAttribute(nn_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)TC_SMEM_BYTES));
     h->tc_opted_in = true;
   }
@@ -754,8 +653,7 @@ int nn_tc_launch(vo_nn_s* h, const float* queries_dev, int64_t nq, int qstride, 
   const int sms = num_sms(h->device);
   const int64_t units = (int64_t)p.n_groups * p.n_tiles16;
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(sms, units));
-  if (acc32) nn_tc_filter_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(p);
-  else nn_tc_filter_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(p);
+  nn_tc_filter_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(p);
   VO_LAUNCH_CHECK();
   // (queries per thread = 0 marks the tensor-core filter, threads, query groups, CTAs)
   h->last_launches.insert(h->last_launches.end(), {0, TC_THREADS, (int32_t)p.n_groups, (int32_t)grid});
