@@ -2,11 +2,14 @@
 //
 // Usage is unchanged: init(camera, world_points, image_points), then oneRound(correspondences,
 // keep_outliers) as often as wanted, then camera() / chiInliers() / ... .  What changed is WHERE
-// it runs: init() uploads the two point sets once, every oneRound() is one asynchronous kernel
-// launch (projection, 2x6 Jacobians, robust weights, the 6x6 H / b reduction, the LDL^T solve and
-// the pose update all stay on the device), and the host only synchronises when an accessor is
-// read.  compute(correspondences, keep_outliers, n) is the additive multi-round entry: n rounds
-// in one kernel launch.
+// it runs: init() uploads the two point sets once; oneRound() only QUEUES a Gauss-Newton iteration,
+// and the queue is flushed as ONE kernel launch (projection, 2x6 Jacobians, robust weights, the 6x6
+// H / b reduction, the LDL^T solve and the pose update of all queued rounds stay on the device) when
+// an accessor is read, the correspondences or keep_outliers change, or init() is called — the
+// reference's main calls oneRound() a hundred times and then camera() (vo_complete.cpp:164-166): one
+// launch and one synchronisation per frame instead of a hundred.  n rounds in one launch are
+// bit-identical to n launches of one round (tests/test_picp_gpu.py).  compute(correspondences,
+// keep_outliers, n) is the additive multi-round entry.
 #pragma once
 #include <vector>
 
@@ -41,13 +44,14 @@ class PICPSolver {
   const int numInliers() const;
 
   // one Gauss-Newton iteration (picp_solver.cpp:98-112); correspondences are
-  // (first: measurement index, second: world-point index).  Asynchronous.
+  // (first: measurement index, second: world-point index).  Queued (see above).
   bool oneRound(const IntPairVector& correspondences, bool keep_outliers);
   // `rounds` iterations without leaving the device
   bool compute(const IntPairVector& correspondences, bool keep_outliers, int rounds);
 
  protected:
-  void upload(const IntPairVector& correspondences);
+  bool upload(const IntPairVector& correspondences);  // true if the device copy had to change
+  void flush() const;    // launch the queued rounds
   void refresh() const;  // device state -> host mirrors
 
   vo_picp_s* _handle;
@@ -56,7 +60,9 @@ class PICPSolver {
   float _damping;
   int _min_num_inliers;
   std::vector<int> _pairs_cache;  // last uploaded correspondences (flattened)
-  mutable bool _dirty;            // rounds were queued since the last refresh
+  mutable bool _dirty;            // rounds were launched since the last refresh
+  mutable int _pending_rounds;    // oneRound() calls not launched yet
+  bool _pending_keep;             // their keep_outliers
   mutable float _chi_inliers, _chi_outliers;
   mutable int _num_inliers;
   // host mirrors of the last linearisation (damping included), refreshed with the accessors above;

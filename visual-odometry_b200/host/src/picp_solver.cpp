@@ -14,6 +14,8 @@ PICPSolver::PICPSolver()
       _damping(1.f),               // :10
       _min_num_inliers(0),         // :11
       _dirty(false),
+      _pending_rounds(0),
+      _pending_keep(false),
       _chi_inliers(0.f),
       _chi_outliers(0.f),
       _num_inliers(0) {
@@ -32,6 +34,7 @@ void PICPSolver::setKernelThreshold(float kernel_threshold) {
 
 void PICPSolver::init(const Camera& camera, const Vector3fVector& world_points,
                       const Vector2fVector& image_points) {
+  _pending_rounds = 0;  // rounds queued on the previous problem were never observed
   _camera = camera;
   vo_camera cam;
   cam.rows = camera.rows();
@@ -57,16 +60,27 @@ void PICPSolver::init(const Camera& camera, const Vector3fVector& world_points,
 // The reference receives the correspondence vector on every oneRound() call (typically the same
 // one a hundred times).  Re-uploading it each round would cost more than the round itself, so
 // the device copy is refreshed only when the contents differ from the last upload.
-void PICPSolver::upload(const IntPairVector& correspondences) {
+bool PICPSolver::upload(const IntPairVector& correspondences) {
   const size_t n = correspondences.size();
   const int* flat = n ? &correspondences[0].first : nullptr;
   if (_pairs_cache.size() == 2 * n && (n == 0 || std::memcmp(_pairs_cache.data(), flat, 8 * n) == 0))
-    return;
+    return false;
+  flush();  // queued rounds belong to the previous correspondences
   check(vo_picp_set_correspondences(_handle, flat, (int64_t)n), "vo_picp_set_correspondences");
   _pairs_cache.assign(flat, flat + 2 * n);
+  return true;
+}
+
+void PICPSolver::flush() const {
+  if (_pending_rounds == 0) return;
+  const int rounds = _pending_rounds;
+  _pending_rounds = 0;
+  check(vo_picp_compute(_handle, _pending_keep ? 1 : 0, rounds), "vo_picp_compute");
+  _dirty = true;
 }
 
 bool PICPSolver::compute(const IntPairVector& correspondences, bool keep_outliers, int rounds) {
+  flush();
   upload(correspondences);
   check(vo_picp_compute(_handle, keep_outliers ? 1 : 0, rounds), "vo_picp_compute");
   _dirty = true;
@@ -79,10 +93,17 @@ bool PICPSolver::compute(const IntPairVector& correspondences, bool keep_outlier
 }
 
 bool PICPSolver::oneRound(const IntPairVector& correspondences, bool keep_outliers) {
-  return compute(correspondences, keep_outliers, 1);
+  // with a minimum inlier count the return value depends on the round itself: nothing to defer
+  if (_min_num_inliers > 0) return compute(correspondences, keep_outliers, 1);
+  if (_pending_rounds > 0 && keep_outliers != _pending_keep) flush();
+  upload(correspondences);  // flushes first when the correspondences changed
+  _pending_keep = keep_outliers;
+  ++_pending_rounds;
+  return true;  // picp_solver.cpp:103-107 can only fail below _min_num_inliers (0, no setter)
 }
 
 void PICPSolver::refresh() const {
+  flush();
   if (!_dirty) return;
   vo_picp_state st;
   check(vo_picp_get_state(_handle, &st), "vo_picp_get_state");
