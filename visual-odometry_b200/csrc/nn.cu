@@ -32,6 +32,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "nn.cuh"
 
@@ -378,6 +379,8 @@ struct NNTinyParams {
   float q[NN_TINY_MAX_Q][NN_DIM];
   int32_t* idx_out;   // device view of mapped host memory
   float* d2_out;
+  unsigned int* flag_out;  // [query] = seq once idx_out / d2_out of that query are visible to the host
+  unsigned int seq;
 };
 
 __global__ void __launch_bounds__(256) nn_tiny_kernel(const NNTinyParams p) {
@@ -403,6 +406,7 @@ __global__ void __launch_bounds__(256) nn_tiny_kernel(const NNTinyParams p) {
     p.idx_out[qi] = best == NN_KEY_NONE ? -1 : (int32_t)(best & 0xFFFFFFFFull);
     p.d2_out[qi] = best == NN_KEY_NONE ? p.bound : __uint_as_float((unsigned int)(best >> 32));
     __threadfence_system();
+    *reinterpret_cast<volatile unsigned int*>(p.flag_out + qi) = p.seq;
   }
 }
 
@@ -799,8 +803,9 @@ int vo_nn_best_match(vo_nn_t h, const float* queries_host, int64_t n_queries, in
   DeviceGuard g(h->device);
   if (n_queries <= NN_TINY_MAX_Q && h->fast && h->n_rows > 0 && h->n_rows <= NN_TINY_MAX_ROWS && h->force_path == 0) {
     if (!h->tiny_host) {
-      VO_CUDA(cudaHostAlloc(&h->tiny_host, 2 * NN_TINY_MAX_Q * sizeof(float), cudaHostAllocMapped));
+      VO_CUDA(cudaHostAlloc(&h->tiny_host, 3 * NN_TINY_MAX_Q * sizeof(float), cudaHostAllocMapped));
       VO_CUDA(cudaHostGetDevicePointer(&h->tiny_dev, h->tiny_host, 0));
+      memset(h->tiny_host, 0, 3 * NN_TINY_MAX_Q * sizeof(float));
     }
     NNTinyParams tp;
     tp.packed = h->packed.as<float4>();
@@ -811,14 +816,33 @@ int vo_nn_best_match(vo_nn_t h, const float* queries_host, int64_t n_queries, in
       for (int k = 0; k < NN_DIM; ++k) tp.q[i][k] = queries_host[i * query_stride + h->skip + k];
     tp.idx_out = static_cast<int32_t*>(h->tiny_dev);
     tp.d2_out = reinterpret_cast<float*>(static_cast<int32_t*>(h->tiny_dev) + NN_TINY_MAX_Q);
+    tp.flag_out = reinterpret_cast<unsigned int*>(static_cast<int32_t*>(h->tiny_dev) + 2 * NN_TINY_MAX_Q);
+    tp.seq = ++h->tiny_seq ? h->tiny_seq : ++h->tiny_seq;  // never 0 (the initial flag value)
     h->last_launches.clear();
     h->last_was_tc = false;
     nn_tiny_kernel<<<(unsigned)n_queries, 256, 0, h->stream>>>(tp);
     VO_LAUNCH_CHECK();
     h->last_launches.insert(h->last_launches.end(), {1, 256, (int32_t)n_queries, 1});
-    VO_CUDA(cudaStreamSynchronize(h->stream));
+    // the answers arrive in mapped host memory: the host polls the per-query flags instead of paying
+    // for a stream synchronisation (the stream is looked at now and then so that a failed launch
+    // cannot spin forever)
     const int32_t* ih = static_cast<const int32_t*>(h->tiny_host);
     const float* dh = reinterpret_cast<const float*>(ih + NN_TINY_MAX_Q);
+    const volatile unsigned int* fh = reinterpret_cast<const volatile unsigned int*>(ih + 2 * NN_TINY_MAX_Q);
+    for (int64_t i = 0; i < n_queries; ++i) {
+      unsigned spins = 0;
+      while (fh[i] != tp.seq) {
+        if ((++spins & 0xFFFFu) == 0u) {
+          const cudaError_t e = cudaStreamQuery(h->stream);
+          if (e == cudaSuccess) {
+            VO_REQUIRE(fh[i] == tp.seq, VO_ERR_CUDA, "nn_tiny_kernel finished without an answer");
+          } else if (e != cudaErrorNotReady) {
+            VO_CUDA(e);
+          }
+        }
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
     for (int64_t i = 0; i < n_queries; ++i) {
       best_idx_host[i] = ih[i];
       if (best_d2_host) best_d2_host[i] = dh[i];

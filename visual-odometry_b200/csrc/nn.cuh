@@ -172,6 +172,7 @@ struct vo_nn_s {
   bool have_mm_max = false;
   void* tiny_host = nullptr;  // mapped pinned memory for the answers of the few-queries path
   void* tiny_dev = nullptr;
+  unsigned int tiny_seq = 0;  // sequence number of the last few-queries call (flag value the host waits for)
   int force_path = 0;  // VO_NN_FORCE_PATH: 0 auto, 1 ffma (FP32 CUDA cores), 2 tc (tensor cores)
 };
 
