@@ -77,14 +77,17 @@ constexpr int TC_BUFS = 4;                  // TMEM accumulator buffers of TC_SU
 #endif
 // TC_HALVES = 2 fills and releases a buffer in two independent column halves (one MMA of N = 64 each,
 // own full/empty barriers) so that the refill of the first half is under way while the second is
-// still being read.  Measured SLOWER (433 against 397 ms at the headline size): an issuing thread
-// needs ~400 cycles per MMA + commit + barrier wait, two per accumulator make the four issuers the
-// limit again.  Kept as a switch.
+// still being read, with one issuing warp per half (24 warps; setmaxnreg moves the issuers' registers
+// to the epilogue warps).  Measured SLOWER twice: 433 against 397 ms at the headline size with four
+// issuers (two MMAs per accumulator make the issuers the limit again), 88.5 against 79.1 ms at
+// M = 2e7 with eight.  Kept as a switch.
 constexpr int TC_HALVES = TC_HALVES_N;
 constexpr int TC_HCOLS = TC_SUB / TC_HALVES;
+
 // + one MMA-issuing warp per buffer (the first also requests the map tiles).  20 warps = 5 per
 // scheduler partition of the register file: 96 registers per thread (a 21st warp would cap all at 80)
-constexpr int TC_THREADS = (TC_EPI_WARPS + TC_BUFS) * 32;
+constexpr int TC_ISSUERS = TC_BUFS * TC_HALVES;  // one MMA-issuing warp per separately released part
+constexpr int TC_THREADS = (TC_EPI_WARPS + TC_ISSUERS) * 32;
 constexpr float TC_U16 = 4.8828125e-4f;     // 2^-11, unit roundoff of f16 (round to nearest)
 constexpr float TC_PAD_NORM = 60000.f;      // |m|^2 of a padding row: never under any threshold
 constexpr float TC_MAX_NORM = 30000.f;      // |m|^2, |q|^2 above this do not fit f16 arithmetic
@@ -340,43 +343,15 @@ __device__ __forceinline__ void tc_rescan_flagged(const NNTCParams& p, bool flag
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCParams p) {
-  extern __shared__ __align__(1024) unsigned char tc_smem[];
-  unsigned char* sA = tc_smem;
-  unsigned char* sB = tc_smem + TC_SMEM_A;
-  uint32_t* thr_s = reinterpret_cast<uint32_t*>(tc_smem + TC_SMEM_A + TC_SMEM_B);  // [qt][128] packed codes
-  float* eps_s = reinterpret_cast<float*>(thr_s + TC_QT_MAX * 128);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(eps_s + TC_QT_MAX * 128);
-  uint64_t* full = bars;                       // [TC_STAGES]  TMA bytes landed
-  uint64_t* empty = full + TC_STAGES;          // [TC_STAGES]  every MMA reading the stage is done
-  uint64_t* tfull = empty + TC_STAGES;               // [TC_BUFS * TC_HALVES]  accumulator half written
-  uint64_t* tempty = tfull + TC_BUFS * TC_HALVES;    // [TC_BUFS * TC_HALVES]  drained by its four warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + TC_BUFS * TC_HALVES);
-
+// The body of the kernel for one role: ISSUER = the MMA-issuing (and TMA-requesting) warps, otherwise
+// the epilogue warps.  Both roles walk the same segments and meet at the same block-wide barriers; the
+// split exists so that each role's code is dominated by its own setmaxnreg (TC_HALVES = 2).
+template <bool ISSUER>
+__device__ __forceinline__ void tc_role(const NNTCParams& p, unsigned char* sA, unsigned char* sB, uint32_t* thr_s,
+                                        float* eps_s, uint64_t* full, uint64_t* empty, uint64_t* tfull,
+                                        uint64_t* tempty) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qt = p.qt;
-
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], TC_BUFS);  // one commit per MMA warp
-    }
-#pragma unroll
-    for (int b = 0; b < TC_BUFS * TC_HALVES; ++b) {
-      mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], 4);  // one warp per lane quadrant
-    }
-    mbar_fence_init();
-  }
-  if (warp == TC_EPI_WARPS) tmem_alloc(tmem_slot, 512);  // the whole tensor memory of the SM
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  // 512 columns is all of it, so the allocation starts at column 0 / lane 0: addresses below are
-  // plain constants (and the issuing warp keeps them in uniform registers)
-  const uint32_t tmem_base = *tmem_slot;
-  if (tmem_base != 0u) __trap();
   const float mm_max = __ldg(p.mm_max);
 
   // this CTA's share of the (query group, map tile) units, group-major
@@ -400,7 +375,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
     // ---- segment prologue: this group's queries -> f16 A tiles + thresholds -------------------------
     __syncthreads();  // every accumulator of the previous segment has been drained
     const int64_t qbase = (int64_t)g * qt * 128;
-    if (warp < TC_EPI_WARPS) {
+    if (!ISSUER) {
       for (int i = tid; i < qt * 128; i += TC_EPI_WARPS * 32) {
         const int64_t qi = qbase + i;
         __align__(16) __half v[16];
@@ -436,14 +411,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
     }
     __syncthreads();
 
-    if (warp >= TC_EPI_WARPS) {
+    if (ISSUER) {
       // ===== MMA issuer of buffer `buf` = pipeline `pipe` (rows [pipe*128, +128) of every map tile),
       // every second accumulator of that pipeline.  ONE thread runs the whole loop.  A thread needs
       // ~100 cycles to issue a tcgen05.mma and ~60 for the commit whatever the shape (in-kernel
       // counters, make TC_PROFILE=1), several threads issue in parallel: with one issuer per pipeline
       // the issuing threads were the limit of the whole kernel (430 cycles per accumulator), hence one
       // per buffer.
-      const int buf = warp - TC_EPI_WARPS;
+      const int part = warp - TC_EPI_WARPS;  // (buffer, column half) this thread fills
+      const int buf = part / TC_HALVES, hh = part % TC_HALVES;
       const int pipe = buf % TC_PIPES;
       const uint32_t bsel = (uint32_t)(buf / TC_PIPES);
       if (lane == 0) {
@@ -462,33 +438,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
           mbar_arrive_expect_tx(&full[s], TC_TILE_BYTES);
           tma_load_1d(sB + s * TC_TILE_BYTES, p.tiles16 + (t0 + i) * (int64_t)TC_TILE_BYTES, TC_TILE_BYTES, &full[s]);
         };
-        if (buf == 0)
+        if (part == 0)
           for (int64_t i = 0; i < min(nt, (int64_t)TC_LOOKAHEAD); ++i) request(i);
         for (int64_t i = 0; i < nt; ++i) {
-          if (buf == 0 && i + TC_LOOKAHEAD < nt) request(i + TC_LOOKAHEAD);
+          if (part == 0 && i + TC_LOOKAHEAD < nt) request(i + TC_LOOKAHEAD);
           const uint32_t n = unit_n + (uint32_t)i;
           const int s = (int)(n % TC_STAGES);
           TC_PROF_T(pa);
           mbar_wait(&full[s], (n / TC_STAGES) & 1u);
           TC_PROF_ADD(4, pa);
           tc_fence_after();
-          const uint64_t bdesc = tc_desc(smem_u32(sB + s * TC_TILE_BYTES) + pipe * (TC_SUB * TC_ROW_BYTES));
+          const uint64_t bdesc =
+              tc_desc(smem_u32(sB + s * TC_TILE_BYTES) + pipe * (TC_SUB * TC_ROW_BYTES) + hh * (TC_HCOLS * TC_ROW_BYTES));
           for (; a < qt; a += 2, ++k) {
             const uint64_t adesc = tc_desc_hi() | (uint64_t)(a_desc0 + a * (TC_A_BYTES >> 4));
-#pragma unroll
-            for (int h = 0; h < TC_HALVES; ++h) {
-              TC_PROF_T(pb);
-              mbar_wait(&tempty[buf * TC_HALVES + h], (k & 1u) ^ 1u);
-              TC_PROF_ADD(5, pb);
-              tc_fence_after();
-              TC_PROF_T(pd);
-              tc_mma_f16((uint32_t)(buf * TC_SUB + h * TC_HCOLS), adesc, bdesc + (uint64_t)((h * TC_HCOLS * TC_ROW_BYTES) >> 4),
-                         TC_IDESC_D16);
-              TC_PROF_ADD(7, pd);
-              TC_PROF_T(pe);
-              tc_commit(&tfull[buf * TC_HALVES + h]);
-              TC_PROF_ADD(3, pe);
-            }
+            TC_PROF_T(pb);
+            mbar_wait(&tempty[part], (k & 1u) ^ 1u);
+            TC_PROF_ADD(5, pb);
+            tc_fence_after();
+            TC_PROF_T(pd);
+            tc_mma_f16((uint32_t)(buf * TC_SUB + hh * TC_HCOLS), adesc, bdesc, TC_IDESC_D16);
+            TC_PROF_ADD(7, pd);
+            TC_PROF_T(pe);
+            tc_commit(&tfull[part]);
+            TC_PROF_ADD(3, pe);
           }
           a -= qt;
           tc_commit(&empty[s]);  // the stage is free once every MMA above has read it
@@ -595,6 +568,57 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCP
     for (int i = 1; i < 8; ++i)
       if (prof[i]) atomicAdd(p.stats + (warp == 0 ? 0 : 8) + i, (unsigned long long)prof[i]);
 #endif
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_filter_kernel(const NNTCParams p) {
+  extern __shared__ __align__(1024) unsigned char tc_smem[];
+  unsigned char* sA = tc_smem;
+  unsigned char* sB = tc_smem + TC_SMEM_A;
+  uint32_t* thr_s = reinterpret_cast<uint32_t*>(tc_smem + TC_SMEM_A + TC_SMEM_B);  // [qt][128] packed codes
+  float* eps_s = reinterpret_cast<float*>(thr_s + TC_QT_MAX * 128);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(eps_s + TC_QT_MAX * 128);
+  uint64_t* full = bars;                       // [TC_STAGES]  TMA bytes landed
+  uint64_t* empty = full + TC_STAGES;          // [TC_STAGES]  every MMA reading the stage is done
+  uint64_t* tfull = empty + TC_STAGES;               // [TC_BUFS * TC_HALVES]  accumulator half written
+  uint64_t* tempty = tfull + TC_BUFS * TC_HALVES;    // [TC_BUFS * TC_HALVES]  drained by its four warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + TC_BUFS * TC_HALVES);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], TC_ISSUERS);  // one commit per MMA warp
+    }
+#pragma unroll
+    for (int b = 0; b < TC_BUFS * TC_HALVES; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 4);  // one warp per lane quadrant
+    }
+    mbar_fence_init();
+  }
+  if (warp == TC_EPI_WARPS) tmem_alloc(tmem_slot, 512);  // the whole tensor memory of the SM
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  // 512 columns is all of it, so the allocation starts at column 0 / lane 0: addresses below are
+  // plain constants (and the issuing warp keeps them in uniform registers)
+  const uint32_t tmem_base = *tmem_slot;
+  if (tmem_base != 0u) __trap();
+  if (warp >= TC_EPI_WARPS) {
+#if TC_HALVES_N == 2
+    // 24 warps: the launch gives every thread 80 registers; the issuing warpgroups hand theirs back
+    // and the epilogue warpgroups take them
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+#endif
+    tc_role<true>(p, sA, sB, thr_s, eps_s, full, empty, tfull, tempty);
+  } else {
+#if TC_HALVES_N == 2
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+#endif
+    tc_role<false>(p, sA, sB, thr_s, eps_s, full, empty, tfull, tempty);
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == TC_EPI_WARPS) tmem_dealloc(tmem_base, 512);
