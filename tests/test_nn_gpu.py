@@ -226,6 +226,32 @@ def test_tensor_core_filter_matches_at_the_edge_of_the_radius(vo, oracle):
     assert np.array_equal(d2[oi >= 0], od[oi >= 0])
 
 
+@pytest.mark.parametrize("scale,norm", [(8.0, 1.5), (0.05, 0.02), (1.0, 0.35)])
+def test_tensor_core_filter_f16_accumulators_other_magnitudes(vo, oracle, scale, norm):
+    """the accumulators of the tensor filter are f16 and compared as 16-bit codes: coordinates far from
+    the unit cube move both the size of an f16 ulp at the threshold and the tensor core's internal
+    accumulation error (tools/tc_probe2.cu).  Every query has a row at 0, 0.5, 0.999.. or 1.001..
+    radii; indices and d2 must still equal the oracle's."""
+    rng = np.random.RandomState(29)
+    M, Q = 40000, 4096
+    m = (scale * rng.uniform(-1, 1, (M, 11))).astype(np.float32)
+    q = (scale * rng.uniform(-1, 1, (Q, 11))).astype(np.float32)
+    rows = rng.choice(M, Q, replace=False)
+    d = rng.normal(size=(Q, 10))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    frac = np.choose(np.arange(Q) % 4, [0.0, 0.5, 1.0 - 3e-6, 1.0 + 3e-6])
+    q[:, 1:] = (m[rows, 1:].astype(np.float64) + d * (norm * frac)[:, None]).astype(np.float32)
+    nn = vo.NNIndex(0)
+    nn.set_map(m)
+    idx, d2 = nn.best_match(q, norm, want_d2=True)
+    assert _is_tc(nn.last_launches())
+    nn.close()
+    oi, od = oracle.nn_best_match(m, q, norm)
+    assert (oi >= 0).sum() >= Q // 2
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(d2[oi >= 0], od[oi >= 0])
+
+
 def test_tensor_core_filter_ties_large_radius_and_odd_queries(vo, oracle, monkeypatch):
     rng = np.random.RandomState(23)
     M = 33000

@@ -309,8 +309,9 @@ int main() {
       const float near_frac = cfg == 3 ? 1.0f : 0.25f;
       long long n = 0, hi_garbage = 0, pack_bad = 0, ne_rn32 = 0, ne_exact = 0, max_ulp32 = 0, max_ulp_exact = 0;
       long long small = 0, small_ne = 0;
+      double max_rel32 = 0.0, max_rel16 = 0.0;  // |D - exact| / sum_k |a_k b_k|  (f16: beyond half an f16 ulp of the result)
       int st_all = 1;
-      for (int tile = 0; tile < 64; ++tile) {
+      for (int tile = 0; tile < 256; ++tile) {
         std::vector<float> q(128 * 10), m(128 * 10);
         for (auto& v : q) v = scale * frand();
         for (int j = 0; j < 128; ++j)
@@ -353,8 +354,21 @@ int main() {
             if ((uint16_t)((j & 1) ? (pk >> 16) : (pk & 0xFFFF)) != got) ++pack_bad;
             float f32;
             memcpy(&f32, &o32[i * 128 + j], 4);
-            double exact = 0.0;
-            for (int k = 0; k < 16; ++k) exact += (double)__half2float(A[i * 16 + k]) * (double)__half2float(B[j * 16 + k]);
+            double exact = 0.0, sum_abs = 0.0;
+            for (int k = 0; k < 16; ++k) {
+              const double t = (double)__half2float(A[i * 16 + k]) * (double)__half2float(B[j * 16 + k]);
+              exact += t;
+              sum_abs += fabs(t);
+            }
+            if (sum_abs > 0.0) {
+              const double r32 = fabs((double)f32 - exact) / sum_abs;
+              if (r32 > max_rel32) max_rel32 = r32;
+              __half gh;
+              memcpy(&gh, &got, 2);
+              const double half_ulp16 = fabs(exact) * 4.8828125e-4 + 3e-8;  // 2^-11 relative, denormal floor
+              const double e16 = fabs((double)__half2float(gh) - exact) - half_ulp16;
+              if (e16 / sum_abs > max_rel16) max_rel16 = e16 / sum_abs;
+            }
             const uint16_t want32 = hbits(__float2half_rn(f32));
             const uint16_t want_ex = hbits(__double2half(exact));
             // distance in f16 codes (sign-magnitude -> monotone integer)
@@ -374,8 +388,10 @@ int main() {
       printf("{\"probe\": \"acc16\", \"cfg\": %d, \"scale\": %g, \"status\": %d, \"elements\": %lld, "
              "\"high_half_nonzero\": %lld, \"pack_mismatch\": %lld, \"ne_round_of_f32_acc\": %lld, "
              "\"max_code_dist_vs_f32_acc\": %lld, \"ne_round_of_exact\": %lld, \"max_code_dist_vs_exact\": %lld, "
-             "\"near_threshold_elements\": %lld, \"near_threshold_ne_exact\": %lld}\n",
-             cfg, scale, st_all, n, hi_garbage, pack_bad, ne_rn32, max_ulp32, ne_exact, max_ulp_exact, small, small_ne);
+             "\"near_threshold_elements\": %lld, \"near_threshold_ne_exact\": %lld, "
+             "\"f32_acc_max_err_over_sum_abs_terms\": %.3g, \"f16_acc_max_err_beyond_half_ulp_over_sum_abs_terms\": %.3g}\n",
+             cfg, scale, st_all, n, hi_garbage, pack_bad, ne_rn32, max_ulp32, ne_exact, max_ulp_exact, small, small_ne,
+             max_rel32, max_rel16);
     }
   }
 

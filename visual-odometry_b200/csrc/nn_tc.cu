@@ -643,11 +643,23 @@ int nn_tc_pack(vo_nn_s* h) {
   return VO_OK;
 }
 
-// query tiles per group: as many as fit (fewer passes over the map), trimmed so that the last group
-// is not mostly padding (a sharded batch of 12 500 queries = 98 tiles runs as 7 groups of 14)
+// query tiles per group.  The work of a launch is (groups x tiles per group) accumulators per map
+// tile, so what matters is the padding of the last group: a sharded batch of 25 000 queries = 196
+// tiles runs as 14 groups of 14 (13 groups of 16 would compute 208), 12 500 queries = 98 tiles as 7
+// groups of 14.  More groups only mean more passes over the f16 map (HBM is at 6 %).  Ties go to the
+// larger group.
 static int tc_pick_qt(int64_t n_qtiles) {
-  const int64_t groups = (n_qtiles + TC_QT_MAX - 1) / TC_QT_MAX;
-  return (int)((n_qtiles + groups - 1) / groups);
+  int best_qt = TC_QT_MAX;
+  int64_t best_cost = INT64_MAX;
+  for (int qt = TC_QT_MAX; qt >= TC_QT_MAX / 2; --qt) {
+    const int64_t groups = (n_qtiles + qt - 1) / qt;
+    const int64_t cost = groups * qt;
+    if (cost < best_cost) {
+      best_cost = cost;
+      best_qt = qt;
+    }
+  }
+  return (int)std::min<int64_t>(best_qt, std::max<int64_t>(n_qtiles, 1));
 }
 
 int nn_tc_launch(vo_nn_s* h, const float* queries_dev, int64_t nq, int qstride, float bound) {
