@@ -8,36 +8,39 @@
 //
 //     A (queries, K-major f16)   a_i = [ -2q_0 .. -2q_9 | 1 | 1 | |q|^2_hi | |q|^2_lo | 0 0 ]
 //     B (map rows, K-major f16)  b_j = [  m_0 ..  m_9   | |m|^2_hi | |m|^2_lo | 1 | 1 | 0 0 ]
-//     D = A B^T  (FP32, in TMEM)  d_ij = |m_j|^2 - 2 q_i.m_j + |q_i|^2  ~  |q_i - m_j|^2
+//     D = A B^T  (F16, in TMEM)   d_ij = |m_j|^2 - 2 q_i.m_j + |q_i|^2  ~  |q_i - m_j|^2
 //
 // (K = 16 is one kind::f16 instruction; the norms travel as hi+lo f16 pairs so that only the
 // rounding of the COORDINATES to f16, u = 2^-11, matters.)  The accumulator never leaves the chip
-// as data: 16 epilogue warps read it back with tcgen05.ld (thread = TMEM lane = query), fold their
-// 128 columns into one minimum with 3-input mins and compare it with the query's threshold
+// as data.  It is kept in F16: an epilogue thread (= TMEM lane = query) reads it back two columns
+// per register (tcgen05.ld ... .pack::16b), folds its 128 columns with the packed 16-bit 3-input
+// integer minimum (VIMNMX3.S16x2 — the code of a non-negative f16 orders like a signed integer and
+// every negative f16 is below every threshold) and compares the result with the CODE of the query's
+// threshold
 //     thr_i = best_i + eps_i ,   eps_i = 4.01 u |q_i| max|m| + (accumulation / norm slack) ,
-// which is an upper bound of d_ij for every row the reference could accept (derivation: DESIGN.md
-// §4.1b).  A warp with a flagged query re-scans those 128 rows from the FP32 rows in global memory
-// exactly as nn.cu does (full FMA test, then the reference-order distance, 64-bit atomicMin key).
-// In ten dimensions the margin costs nothing: for uniform appearances the filter passes ~3e-10 of
-// the pairs, and clustered descriptors only add re-scans, never a cliff.
+// which is an upper bound of d_ij for every row the reference could accept (derivation and the
+// measurements it rests on: DESIGN.md §4.1b, tools/tc_probe2.cu).  A warp with a flagged query
+// re-scans those 64 rows from the FP32 rows in global memory exactly as nn.cu does (full FMA test,
+// then the reference-order distance, 64-bit atomicMin key).  In ten dimensions the margin costs
+// nothing: for uniform appearances the filter passes ~3e-10 of the pairs, and clustered
+// descriptors only add re-scans, never a cliff.
 //
-// Pipeline per CTA (one per SM, persistent, 19 warps):
-//   * a TMA warp streams 256-row f16 map tiles (8 KB, 1-D bulk copies) into a 4-stage ring;
-//   * the tile is split into two 128-row halves, each the start of an independent pipeline: its own
-//     MMA-issuing warp (one N=128 tcgen05.mma per resident query tile, each committed to an mbarrier),
-//     its own two 128-column TMEM buffers (all 512 columns are in use) and its own eight epilogue
-//     warps (lane quadrant x column half: thread = TMEM lane = query, 64 columns per thread);
-//   * an epilogue warp waits for the accumulator, reads its 64 columns with two tcgen05.ld.x32,
-//     releases the buffer, folds the 64 values into a minimum with 3-input mins and tests it.
-// Measured on hardware (tools/tc_probe.cu, profiles/r02a_tc_probe.md): one thread issues at most one
-// tcgen05.mma per 114 cycles whatever its width, several threads issue in parallel, issue-to-
-// barrier latency is 288 cycles, the f16 MMA itself takes N/2 cycles, a dependent tcgen05.ld.x32
-// 35 cycles.  The ceiling is neither of those: every accumulator element has to enter a minimum, the
-// 3-input FMNMX3 takes two new elements per instruction and executes on the ALU pipe, 64 lanes per
-// clock per SM — 128 pairs/clk/SM, 0.27 s for 1e13 pairs (ncu: ALU pipe 76 % busy, the busiest unit,
-// profiles/r02m_ncu_nn_tc.md).  The kernel reaches 44 % of that (0.62 s): 33 of the ~60 instructions
-// of an epilogue iteration are the mins, the rest is barrier / address bookkeeping on the same pipe,
-// and 96 registers per thread (608 threads fill the file) leave no room for more warps.
+// Pipeline per CTA (one per SM, persistent, 20 warps):
+//   * 256-row f16 map tiles (8 KB, 1-D bulk copies) stream through an 8-stage ring, requested 6
+//     tiles ahead by the first issuing thread;
+//   * all 512 TMEM columns hold four 128x128 accumulators; accumulator b = (half `b & 1` of the map
+//     tile, every second resident query tile) has its own MMA-issuing thread (one N=128 tcgen05.mma
+//     per use, committed to an mbarrier) and its own four epilogue warps, one per TMEM lane quadrant;
+//   * an epilogue warp waits for its accumulator, reads the 128 columns with two packed loads through
+//     one 32-register buffer, releases the accumulator, folds (2 x 16 VIMNMX3.S16x2) and tests.
+// Measured on hardware (tools/tc_probe.cu, tools/tc_probe2.cu, in-kernel counters with
+// -DNN_TC_PROFILE): the f16 MMA takes N/2 cycles; a thread needs ~100 cycles to issue one and ~60 for
+// the commit whatever the shape, several threads issue in parallel; issue -> barrier-visible latency
+// 288 cycles; packed TMEM read + fold with 16 warps 175 elements per clock per SM.  What binds is
+// TMEM capacity x latency: an f16 accumulator still occupies a 32-bit cell, so 65536 cells are all
+// that is ever in flight, and one accumulator is busy for ~760 cycles from the issue of its MMA until
+// its last column has been read: 86 pairs per clock per SM, 0.397 s for 1e13 pairs (ncu: tensor pipe
+// 36 %, ALU 56 %, issue slots 49 %, profiles/r02p_ncu_nn_tc.md).
 #include <cuda_fp16.h>
 
 #include <algorithm>
