@@ -476,7 +476,7 @@ __device__ __forceinline__ void tc_role(const NNTCParams& p, unsigned char* sA, 
       // quadrant) drain buffer `pipe`, warps 4-7 buffer `pipe + 2`: a warp takes every SECOND
       // accumulator of its pipeline and reads all 128 columns of it — two packed loads of 64 columns
       // through one 32-register buffer, 16 VIMNMX3.S16x2 each.  Per 4096 pairs a warp executes about
-      // as many instructions as the f32 epilogue needs for 2048.
+      // as many instructions as the f32-accumulator epilogue of the first version needed for 2048.
       const int pipe = warp / TC_PIPE_WARPS, w8 = warp % TC_PIPE_WARPS;
       const int quad = w8 & 3;
       const uint32_t bsel = (uint32_t)(w8 >> 2);
