@@ -81,6 +81,23 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def gpu_local_cores(index):
+    """cores NVML reports as local to GPU `index`, restricted to this process' allowed set; None if
+    unknown"""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpus = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpus + 63) // 64)
+        cores = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cores &= set(os.sched_getaffinity(0))
+        return cores or None
+    except Exception:  # noqa: BLE001 — informational: an unpinned run is still a valid run
+        return None
+
+
 def measured_traffic(kernel, grid_prefix=None):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the latest
     committed `ncu --set full` capture (profiles/*_traffic.json, written by tools/make_profiles.py
@@ -603,10 +620,16 @@ def bench_vo(torch, args, dist, rank, local, world):
         return {"unavailable": "host/bin/vo_sequence not built (needs the reference checkout at build time)"}
     env = dict(os.environ, VO_B200_DEVICE=str(local))
     env.pop("VO_SEQ_MODE", None)  # default mode: the device-resident frame pipeline (vo_pipe_*)
+    # the frame loop synchronises once per frame, so where its host thread runs matters: keep each
+    # rank's process on the cores NVML reports as local to its GPU (round 1 saw one rank in four
+    # 20 % slower, unpinned)
+    near = gpu_local_cores(local)
+    pin = (lambda: os.sched_setaffinity(0, near)) if near else None
     r, err = None, None
     try:
         out = subprocess.run([exe, str(args.vo_landmarks), str(args.vo_frames), str(1000 + rank), "100"],
-                             env=env, capture_output=True, text=True, check=True, timeout=900).stdout
+                             env=env, capture_output=True, text=True, check=True, timeout=900,
+                             preexec_fn=pin).stdout
         r = json.loads(out.strip().splitlines()[-1])
     except Exception as e:  # noqa: BLE001 — every rank must still reach the collectives below
         err = f"{type(e).__name__}: {e}"[:300]
@@ -645,6 +668,7 @@ def bench_vo(torch, args, dist, rank, local, world):
                            "initial value: the reference's frame-to-frame monocular scale decays and collapses on "
                            "long sequences in BOTH builds (DESIGN.md 5); the per-frame work is unaffected"},
         "per_rank": per_rank, "slowest_rank": slowest,
+        "host_cores_pinned_rank0": len(near) if near else None,
         "rank0": {k: r[k] for k in ("impl", "frames_per_s", "stage_ms_per_frame", "mean_measurements",
                                     "mean_correspondences", "map_points", "rot_err_mean_rad",
                                     "scale_first_pair", "scale_median", "scale_alive_frames") if k in r},
