@@ -21,8 +21,17 @@ namespace vo {
 
 namespace {
 
-constexpr size_t STAGE_CHUNK = (size_t)8 << 20;  // bytes per pinned chunk
+// bytes per pinned chunk (VO_STAGE_CHUNK_MB overrides, 1..64; read once)
+static const size_t STAGE_CHUNK = []() {
+  size_t mb = 8;
+  if (const char* e = getenv("VO_STAGE_CHUNK_MB")) {
+    const long v = atol(e);
+    if (v >= 1 && v <= 64) mb = (size_t)v;
+  }
+  return mb << 20;
+}();
 constexpr int STAGE_SLOTS = 4;                   // chunks in the ring
+constexpr int STAGE_MAX_WORKERS = 7;             // + the calling thread
 constexpr size_t STAGE_MIN = (size_t)1 << 20;    // below: one plain cudaMemcpyAsync
 
 // parallel memcpy: the caller and `n` persistent workers each copy one slice
@@ -100,7 +109,7 @@ CopyPool* copy_pool() {
     else {
       const unsigned hw = std::thread::hardware_concurrency();
       n = (int)(hw / 2);
-      if (n > 7) n = 7;
+      if (n > STAGE_MAX_WORKERS) n = STAGE_MAX_WORKERS;
     }
     if (n < 0) n = 0;
     return new CopyPool(n);  // never destroyed: no static-destruction order to get wrong
