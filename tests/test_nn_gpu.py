@@ -252,6 +252,24 @@ def test_tensor_core_filter_f16_accumulators_other_magnitudes(vo, oracle, scale,
     assert np.array_equal(d2[oi >= 0], od[oi >= 0])
 
 
+@pytest.mark.parametrize("Q", [1, 100, 129, 300, 1100])
+def test_tensor_core_filter_forced_on_small_batches(vo, oracle, synth, monkeypatch, Q):
+    """VO_NN_FORCE_PATH=tc: batches of 1..9 query tiles (one, two, three ... resident tiles per group,
+    i.e. accumulator buffers that are used by every map tile, every second one, or unevenly)"""
+    monkeypatch.setenv("VO_NN_FORCE_PATH", "tc")
+    M = 33000
+    m = synth.nn_map_rows_np(0, M)
+    q, target = synth.nn_queries_np(Q, M)
+    nn = vo.NNIndex(0)
+    nn.set_map(m)
+    idx, d2 = nn.best_match(q, 0.1, want_d2=True)
+    assert _is_tc(nn.last_launches()), nn.last_launches()
+    nn.close()
+    oi, od = oracle.nn_best_match(m, q, 0.1)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(d2[oi >= 0], od[oi >= 0])
+
+
 def test_tensor_core_filter_ties_large_radius_and_odd_queries(vo, oracle, monkeypatch):
     rng = np.random.RandomState(23)
     M = 33000
