@@ -540,7 +540,6 @@ static int nn_launch_filter(vo_nn_s* h, const float* queries_dev, int64_t nq, in
 // set_map in three steps so that a host map can arrive in chunks: begin (sizes, buffers), one
 // repack per row range, end (f16 tiles for the tensor-core filter)
 static int nn_set_map_begin(vo_nn_s* h, const float* rows_dev, int64_t n_rows, int row_stride, int skip) {
-  h->have_mm_max = false;
   h->tc_ready = false;
   h->n_rows = n_rows;
   h->row_stride = row_stride;
@@ -580,8 +579,21 @@ static int nn_set_map_end(vo_nn_s* h) {
   h->rows_dev = h->packed.as<float>();
   h->map_stride = NN_ROW_BYTES / (int)sizeof(float);
   h->map_skip = 0;
-  // f16 operand tiles for the tensor-core filter (large maps only; +32 B per row)
-  if (h->force_path != 1 && (h->n_rows >= NN_TC_MIN_ROWS || h->force_path == 2)) {
+  // the new max|m|^2 travels to the host without anybody waiting for it (see vo_nn_s::mm_max_host)
+  // (maps too small for the tensor-core filter never ask)
+  if (h->n_rows >= NN_TC_MIN_ROWS && h->force_path != 1) {
+    if (!h->mm_pinned) {
+      VO_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->mm_pinned), sizeof(float), cudaHostAllocDefault));
+      VO_CUDA(cudaEventCreateWithFlags(&h->mm_event, cudaEventDisableTiming));
+    }
+    if (h->mm_pending) VO_CUDA(cudaEventSynchronize(h->mm_event));  // the slot is about to be rewritten
+    VO_CUDA(cudaMemcpyAsync(h->mm_pinned, h->scalars.p, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    VO_CUDA(cudaEventRecord(h->mm_event, h->stream));
+    h->mm_pending = true;
+  }
+  // f16 operand tiles for the tensor-core filter (+32 B per row): now for a large map, otherwise when
+  // a batch large enough to profit from them arrives (nn_best_match_common)
+  if (h->force_path != 1 && (h->n_rows >= NN_TC_EAGER_ROWS || h->force_path == 2)) {
     int rc = nn_tc_pack(h);
     if (rc) return rc;
     h->tc_ready = true;
@@ -602,7 +614,17 @@ static int nn_set_map_common(vo_nn_s* h, const float* rows_dev, int64_t n_rows, 
 // to be of the order of the radius, otherwise it passes everything and the FFMA filter (margin
 // ~2^-18) is the better tool.  max|m|^2 lives on the device; it is read back once per map.
 static int nn_tc_usable(vo_nn_s* h, float bound, bool* ok) {
-  if (!h->have_mm_max) {
+  if (h->mm_pending) {
+    const cudaError_t e = h->have_mm_max ? cudaEventQuery(h->mm_event) : cudaEventSynchronize(h->mm_event);
+    if (e == cudaSuccess) {
+      h->mm_max_host = *h->mm_pinned;
+      h->have_mm_max = true;
+      h->mm_pending = false;
+    } else if (e != cudaErrorNotReady) {
+      VO_CUDA(e);
+    }
+  }
+  if (!h->have_mm_max) {  // a map that did not come through set_map_end (replicated over NCCL)
     VO_CUDA(cudaMemcpyAsync(&h->mm_max_host, h->scalars.p, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     VO_CUDA(cudaStreamSynchronize(h->stream));
     h->have_mm_max = true;
@@ -623,10 +645,14 @@ static int nn_best_match_common(vo_nn_s* h, const float* queries_dev, int64_t nq
   h->last_was_tc = false;
   if (h->n_rows > 0) {
     if (h->fast) {
-      bool tc = h->tc_ready && (h->force_path == 2 || nq >= NN_TC_MIN_QUERIES);
+      bool tc = h->force_path == 2 || (h->force_path == 0 && nn_tc_worthwhile(h->n_rows, nq));
       if (tc && h->force_path != 2) {
         rc = nn_tc_usable(h, bound, &tc);
         if (rc) return rc;
+      }
+      if (tc && !h->tc_ready) {
+        if ((rc = nn_tc_pack(h))) return rc;
+        h->tc_ready = true;
       }
       rc = tc ? nn_tc_launch(h, queries_dev, nq, qstride, bound)
               : nn_launch_filter(h, queries_dev, nq, qstride, bound);
@@ -695,6 +721,8 @@ int vo_nn_destroy(vo_nn_t h) {
   h->tiles16.release();
   h->tc_stats.release();
   if (h->tiny_host) cudaFreeHost(h->tiny_host);
+  if (h->mm_pinned) cudaFreeHost(h->mm_pinned);
+  if (h->mm_event) cudaEventDestroy(h->mm_event);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return VO_OK;

@@ -168,8 +168,13 @@ struct vo_nn_s {
   vo::DevBuf tiles16, tc_stats;
   int64_t n_tiles16 = 0;
   bool tc_ready = false, tc_opted_in = false, last_was_tc = false;
-  float mm_max_host = 0.f;  // host copy of max|m|^2 (read back on first use)
-  bool have_mm_max = false;
+  // host copy of max|m|^2.  It only steers the CHOICE of the filter (both are exact for any data), so
+  // it may be one map old: every set_map sends the new value to pinned memory without waiting, and
+  // the first query that finds it arrived adopts it; only a handle that has never seen a value waits.
+  float mm_max_host = 0.f;
+  bool have_mm_max = false, mm_pending = false;
+  float* mm_pinned = nullptr;
+  cudaEvent_t mm_event = nullptr;
   void* tiny_host = nullptr;  // mapped pinned memory for the answers of the few-queries path
   void* tiny_dev = nullptr;
   unsigned int tiny_seq = 0;  // sequence number of the last few-queries call (flag value the host waits for)
@@ -179,6 +184,15 @@ struct vo_nn_s {
 // nn_tc.cu
 int nn_tc_pack(vo_nn_s* h);
 int nn_tc_launch(vo_nn_s* h, const float* queries_dev, int64_t nq, int qstride, float bound);
-constexpr int64_t NN_TC_MIN_ROWS = 32768;   // below: the map is a few tiles per SM, FFMA path
-constexpr int64_t NN_TC_MIN_QUERIES = 2048; // below: one or two query tiles cannot fill the chip
+// When the tensor-core filter answers (tools/nn_crossover.py, set_map + best_match, us FP32 / us
+// tensor: 8192 x 4096 29 / 32, 12000 x 4096 36 / 32, 8192 x 9000 40 / 38, 16384 x 9000 63 / 43,
+// 32768 x 30000 272 / 100, 2048 x 30000 52 / 46): from about 4e7 (query, row) pairs.  The f16 tiles
+// are built at set_map for maps of NN_TC_EAGER_ROWS rows, otherwise by the first batch that wants them.
+constexpr int64_t NN_TC_MIN_ROWS = 2048;
+constexpr int64_t NN_TC_MIN_QUERIES = 512;
+constexpr int64_t NN_TC_MIN_PAIRS = 40000000;
+constexpr int64_t NN_TC_EAGER_ROWS = 32768;
+inline bool nn_tc_worthwhile(int64_t rows, int64_t nq) {
+  return rows >= NN_TC_MIN_ROWS && nq >= NN_TC_MIN_QUERIES && rows >= (NN_TC_MIN_PAIRS + nq - 1) / nq;
+}
 

@@ -650,13 +650,16 @@ int nn_tc_pack(vo_nn_s* h) {
 // tile, so what matters is the padding of the last group: a sharded batch of 25 000 queries = 196
 // tiles runs as 14 groups of 14 (13 groups of 16 would compute 208), 12 500 queries = 98 tiles as 7
 // groups of 14.  More groups only mean more passes over the f16 map (HBM is at 6 %).  Ties go to the
-// larger group.
-static int tc_pick_qt(int64_t n_qtiles) {
+// larger group.  (For huge maps groups * tiles overflows nothing: both are < 2^31.)
+static int tc_pick_qt(int64_t n_qtiles, int64_t n_tiles16, int ctas) {
   int best_qt = TC_QT_MAX;
   int64_t best_cost = INT64_MAX;
   for (int qt = TC_QT_MAX; qt >= TC_QT_MAX / 2; --qt) {
     const int64_t groups = (n_qtiles + qt - 1) / qt;
-    const int64_t cost = groups * qt;
+    // accumulators of the busiest CTA: the (group, map tile) units are dealt out in equal contiguous
+    // shares.  For a large map this is groups * qt * tiles / ctas; for a frame-sized one (40 map
+    // tiles, 5 groups) the rounding of the shares decides.
+    const int64_t cost = ((groups * n_tiles16 + ctas - 1) / ctas) * qt;
     if (cost < best_cost) {
       best_cost = cost;
       best_qt = qt;
@@ -680,7 +683,8 @@ int nn_tc_launch(vo_nn_s* h, const float* queries_dev, int64_t nq, int qstride, 
   p.mm_max = h->scalars.as<float>();
   p.keys = h->keys.as<unsigned long long>();
   const int64_t n_qtiles = (nq + 127) / 128;
-  p.qt = tc_pick_qt(n_qtiles);
+  const int sms = num_sms(h->device);
+  p.qt = tc_pick_qt(n_qtiles, p.n_tiles16, sms);
   p.n_groups = (int)((n_qtiles + p.qt - 1) / p.qt);
   p.stats = h->tc_stats.as<unsigned long long>();
   if (!h->tc_opted_in) {
@@ -689,7 +693,6 @@ int nn_tc_launch(vo_nn_s* h, const float* queries_dev, int64_t nq, int qstride, 
     h->tc_opted_in = true;
   }
   VO_CUDA(cudaMemsetAsync(h->tc_stats.p, 0, 128, h->stream));
-  const int sms = num_sms(h->device);
   const int64_t units = (int64_t)p.n_groups * p.n_tiles16;
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(sms, units));
   nn_tc_filter_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(p);
