@@ -4,11 +4,13 @@
    matches; float equality (-0.0 == +0.0, NaN equals nothing).
  * the whole loop against the CPU reference is in tests/test_dropin_gpu.py."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def reference_update(map_pts, map_app, pts, app):
@@ -199,3 +201,57 @@ def test_python_frame_pipeline_on_a_synthetic_pair_sequence(vo, synth):
     pts, apps = pipe.map()
     assert len(pts) == n and np.array_equal(apps, app)
     pipe.close()
+
+
+def test_cluster_join_equals_single_cta_join(vo):
+    """frames of >= 2048 measurements take assoc_join_cluster_kernel (8 CTAs, counts exchanged through
+    distributed shared memory): same matches, same correspondences, same poses, bit for bit, as the
+    one-CTA kernel (VO_PIPE_JOIN_SINGLE=1, read once per process: run in a child).  The scene has
+    unmatched measurements on both sides and landmarks that appear and disappear, so hits and joins
+    are proper subsets in every slice."""
+    import json, subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import importlib, json, sys
+        import numpy as np
+        sys.path.insert(0, %r)
+        vo = importlib.import_module("visual-odometry_b200")
+        rng = np.random.RandomState(5)
+        K = np.array([[180, 0, 320], [0, 180, 240], [0, 0, 1]], np.float64)
+        n = 5000
+        world = np.stack([rng.uniform(-2, 2, n), rng.uniform(-1.5, 1.5, n), rng.uniform(2.0, 4.5, n)], 1)
+        app = rng.uniform(-1, 1, (n, 10)).astype(np.float32)
+        def view(k):
+            keep = rng.uniform(size=n) > 0.2                      # a fifth of the landmarks missing per frame
+            pc = world[keep] - np.array([0, 0, 0.1 * k])
+            uv = ((pc @ K.T)[:, :2] / pc[:, 2:3]).astype(np.float32)
+            a = app[keep].copy()
+            extra = 300                                           # clutter that matches nothing
+            uv = np.concatenate([uv, rng.uniform(0, 400, (extra, 2)).astype(np.float32)])
+            a = np.concatenate([a, rng.uniform(-1, 1, (extra, 10)).astype(np.float32)])
+            return uv, a
+        cam = vo.Camera(480, 640, 0, 50, K, np.eye(4))
+        pipe = vo.FramePipeline(cam, max_points_per_frame=8192, max_map_points=20000)
+        pipe.first_frame(*view(0))
+        m = pipe.second_frame(*view(1))
+        X = np.eye(4); X[2, 3] = -0.1
+        pipe.bootstrap(X)
+        out = {"matches": np.asarray(m).tolist(), "poses": [], "info": []}
+        for k in range(2, 7):
+            pose, info = pipe.step(*view(k), rounds=20)
+            out["poses"].append(np.asarray(pose, np.float32).view(np.uint32).tolist())
+            out["info"].append([int(info["n_matches"]), int(info["n_correspondences"])])
+        pts, apps = pipe.map()
+        out["map"] = [len(pts), int(np.asarray(pts, np.float32).view(np.uint32).sum() %% (1 << 31))]
+        pipe.close()
+        print(json.dumps(out))
+    """ % ROOT)
+    res = {}
+    for mode in ("cluster", "single"):
+        env = dict(os.environ)
+        env.pop("VO_PIPE_JOIN_SINGLE", None)
+        if mode == "single":
+            env["VO_PIPE_JOIN_SINGLE"] = "1"
+        o = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout
+        res[mode] = json.loads(o.strip().splitlines()[-1])
+    assert res["cluster"]["info"][0][0] > 3000 and res["cluster"]["info"][0][1] > 2000
+    assert res["cluster"] == res["single"]

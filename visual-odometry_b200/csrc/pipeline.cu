@@ -14,13 +14,17 @@
 //   read on device)  ->  map_update_kernel (device hash index over the map's appearances).
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <cooperative_groups.h>
 
 #include "common.cuh"
 
 namespace vo {
 
 constexpr int PIPE_THREADS = 1024;
+constexpr int PIPE_JOIN_CLUSTER = 8;    // CTAs of the association + join kernel (one cluster)
 constexpr int PIPE_MAX_POINTS = 32768;  // per frame: the join table lives in shared memory
 
 // ---- block-wide exclusive rank of a flag (one call = one chunk of PIPE_THREADS items) ----------
@@ -87,6 +91,93 @@ assoc_join_kernel(const int32_t* __restrict__ nn_idx, int n_q, int first_is_map,
   if (tid == 0) {
     counts[0] = n_ci;
     counts[1] = n_pp;
+  }
+}
+
+// The same on a thread-block cluster: CTA r takes the r-th contiguous slice of the queries, counts its
+// hits and joins, hands the two counts to every peer through distributed shared memory (one cluster
+// barrier), and writes its slice at the offsets of the slices before it — the output order is the
+// single-CTA kernel's.  Every CTA builds the whole join table itself (|corr_world| is a few thousand).
+// 29 us -> measured in profiles/r02_notes.md for a 1e4-measurement frame.
+__global__ void __cluster_dims__(PIPE_JOIN_CLUSTER, 1, 1) __launch_bounds__(PIPE_THREADS)
+assoc_join_cluster_kernel(const int32_t* __restrict__ nn_idx, int n_q, int first_is_map, int n_ref,
+                          const int2* __restrict__ corr_world, const int* __restrict__ n_corr_world_dev,
+                          int2* __restrict__ corr_imgs, int2* __restrict__ pairs_picp,
+                          long long* __restrict__ counts) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  extern __shared__ int s_first[];  // [n_ref]: first position in corr_world of each ref index
+  __shared__ int s_warp[32];
+  __shared__ int s_cnt[PIPE_JOIN_CLUSTER][2];  // [source CTA][hits, joins], written by the peers
+  const int tid = threadIdx.x;
+  const int n_cw = n_corr_world_dev ? *n_corr_world_dev : 0;
+  for (int r = tid; r < n_ref; r += PIPE_THREADS) s_first[r] = INT_MAX;
+  __syncthreads();
+  for (int j = tid; j < n_cw; j += PIPE_THREADS) {
+    const int r = corr_world[j].x;
+    if (r >= 0 && r < n_ref) atomicMin(&s_first[r], j);
+  }
+  __syncthreads();
+  const int chunk = (n_q + PIPE_JOIN_CLUSTER - 1) / PIPE_JOIN_CLUSTER;
+  const int q0 = min(n_q, rank * chunk), q1 = min(n_q, q0 + chunk);
+  // pass 1: this slice's counts
+  int c_hit = 0, c_join = 0;
+  for (int q = q0 + tid; q < q1; q += PIPE_THREADS) {
+    const int m = nn_idx[q];
+    const bool hit = m >= 0;
+    const int ref = first_is_map ? m : q;
+    c_hit += hit ? 1 : 0;
+    c_join += (hit && ref < n_ref && s_first[ref] != INT_MAX) ? 1 : 0;
+  }
+  int packed = (c_join << 16) | c_hit;  // a thread sees at most 32 queries of <= 32768
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int other = __shfl_xor_sync(0xffffffffu, packed, o);
+    packed = (((packed >> 16) + (other >> 16)) << 16) | ((packed & 0xFFFF) + (other & 0xFFFF));
+  }
+  if ((tid & 31) == 0) s_warp[tid >> 5] = packed;
+  __syncthreads();
+  if (tid == 0) {
+    int hits = 0, joins = 0;
+    for (int w = 0; w < PIPE_THREADS / 32; ++w) {
+      hits += s_warp[w] & 0xFFFF;
+      joins += s_warp[w] >> 16;
+    }
+    for (int r = 0; r < PIPE_JOIN_CLUSTER; ++r) {
+      int* dst = cluster.map_shared_rank(&s_cnt[rank][0], r);
+      dst[0] = hits;
+      dst[1] = joins;
+    }
+  }
+  cluster.sync();  // all counts are visible everywhere; also orders the reuse of s_warp below
+  int n_ci = 0, n_pp = 0, all_ci = 0, all_pp = 0;
+  for (int r = 0; r < PIPE_JOIN_CLUSTER; ++r) {
+    n_ci += r < rank ? s_cnt[r][0] : 0;
+    n_pp += r < rank ? s_cnt[r][1] : 0;
+    all_ci += s_cnt[r][0];
+    all_pp += s_cnt[r][1];
+  }
+  // pass 2: the ordered writes of this slice
+  for (int base = q0; base < q1; base += PIPE_THREADS) {
+    const int q = base + tid;
+    const int m = q < q1 ? nn_idx[q] : -1;
+    const bool hit = m >= 0;
+    const int ref = first_is_map ? m : q, cur = first_is_map ? q : m;
+    int j = INT_MAX;
+    if (hit && ref < n_ref) j = s_first[ref];
+    const bool joined = hit && j != INT_MAX;
+    int t1, t2;
+    const int r1 = block_rank(hit, s_warp, &t1);
+    const int r2 = block_rank(joined, s_warp, &t2);
+    if (hit) corr_imgs[n_ci + r1] = make_int2(ref, cur);
+    if (joined) pairs_picp[n_pp + r2] = make_int2(cur, corr_world[j].y);
+    n_ci += t1;
+    n_pp += t2;
+  }
+  if (rank == 0 && tid == 0) {
+    counts[0] = all_ci;
+    counts[1] = all_pp;
   }
 }
 
@@ -332,11 +423,19 @@ static int pipe_associate(vo_pipe_s* h, bool with_join) {
                                h->nn_idx.as<int32_t>(), nullptr);
   if (rc) return rc;
   const size_t smem = (size_t)(n_ref > 0 ? n_ref : 1) * sizeof(int);
-  assoc_join_kernel<<<1, PIPE_THREADS, smem, h->stream>>>(
-      h->nn_idx.as<int32_t>(), (int)n_q, first_is_map ? 1 : 0, (int)n_ref,
-      h->corr_world[h->tri_slot].as<int2>(),
-      with_join ? reinterpret_cast<const int*>(h->counts.as<long long>() + C_TRI0 + h->tri_slot) : nullptr,
-      h->corr_imgs.as<int2>(), h->pairs_picp.as<int2>(), h->counts.as<long long>());
+  const int* n_cw_dev =
+      with_join ? reinterpret_cast<const int*>(h->counts.as<long long>() + C_TRI0 + h->tri_slot) : nullptr;
+  static const bool single = getenv("VO_PIPE_JOIN_SINGLE") != nullptr;  // tests: the one-CTA kernel
+  if (n_q >= 2 * PIPE_THREADS && !single)  // a slice per CTA of a cluster; small frames stay on one CTA
+    assoc_join_cluster_kernel<<<PIPE_JOIN_CLUSTER, PIPE_THREADS, smem, h->stream>>>(
+        h->nn_idx.as<int32_t>(), (int)n_q, first_is_map ? 1 : 0, (int)n_ref,
+        h->corr_world[h->tri_slot].as<int2>(), n_cw_dev, h->corr_imgs.as<int2>(), h->pairs_picp.as<int2>(),
+        h->counts.as<long long>());
+  else
+    assoc_join_kernel<<<1, PIPE_THREADS, smem, h->stream>>>(
+        h->nn_idx.as<int32_t>(), (int)n_q, first_is_map ? 1 : 0, (int)n_ref,
+        h->corr_world[h->tri_slot].as<int2>(), n_cw_dev, h->corr_imgs.as<int2>(), h->pairs_picp.as<int2>(),
+        h->counts.as<long long>());
   VO_LAUNCH_CHECK();
   return VO_OK;
 }
@@ -461,6 +560,8 @@ int vo_pipe_create(vo_pipe_t* out, int device, const vo_camera* cam, int64_t max
   PIPE_TRY(cudaMemsetAsync(h->map_slots.p, 0xFF, (size_t)cap * 4, h->stream));
   PIPE_TRY(cudaMemsetAsync(h->map_last.p, 0xFF, (size_t)cap * 4, h->stream));
   PIPE_TRY(cudaFuncSetAttribute(assoc_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               PIPE_MAX_POINTS * (int)sizeof(int)));
+  PIPE_TRY(cudaFuncSetAttribute(assoc_join_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                PIPE_MAX_POINTS * (int)sizeof(int)));
   iso_identity(h->X_curr);
   iso_identity(h->history);
