@@ -138,53 +138,65 @@ int main(int argc, char** argv) {
   }
 #endif
 
-  Camera cam(480, 640, 0, 10, k);
-  Vector2fVector reference_image_points, current_measurements;
-  auto t0 = Clock::now();
-  cam.projectPoints(reference_image_points, world_points_gt, true);  // :65
-  cam.setWorldInCameraPose(X_gt1);
-  cam.projectPoints(current_measurements, world_points_gt, true);    // :67
-  const double ms_project = ms_since(t0);
-
-  IntPairVector correspondences;
-  fake_correspondences(correspondences, reference_image_points, current_measurements);
-
-  t0 = Clock::now();
-  const Eigen::Isometry3f X_est =
-      estimate_transform(cam.cameraMatrix(), correspondences, reference_image_points, current_measurements);
-  const double ms_epipolar = ms_since(t0);
-
+  // The hot path runs twice and the SECOND pass is reported (both builds): the first one pays what a
+  // process pays once — lazy loading of every kernel on its first launch, first-touch of the buffers —
+  // which says nothing about the path and varied 7x from run to run.
+  IntPairVector correspondences, correspondences_new;
   Vector3fVector world_points_est;
-  IntPairVector correspondences_new;
-  t0 = Clock::now();
-  triangulate_points(k, X_est, correspondences, reference_image_points, current_measurements, world_points_est,
-                     correspondences_new);  // :78-79
-  const double ms_triangulate = ms_since(t0);
-
-  cam.setWorldInCameraPose(X_gt2);
-  t0 = Clock::now();
-  cam.projectPoints(current_measurements, world_points_gt, true);  // :87
-  const double ms_project2 = ms_since(t0);
-
-  SolverAccess solver;
-  solver.setKernelThreshold(10000);
-  t0 = Clock::now();
-  Vector3fVector points_in_cameraframe1;
-  points_in_cameraframe1.reserve(world_points_est.size());
-  for (const auto& p : world_points_est) points_in_cameraframe1.push_back(X_est * p);  // :93-94
-  const double ms_transform = ms_since(t0);
-
-  cam.setWorldInCameraPose(Eigen::Isometry3f::Identity());
+  Eigen::Isometry3f X_est = Eigen::Isometry3f::Identity(), X_picp = Eigen::Isometry3f::Identity();
   float H1[36], b1[6];
-  t0 = Clock::now();
-  solver.init(cam, points_in_cameraframe1, current_measurements);  // :97
-  solver.oneRound(correspondences_new, false);
-  solver.snapshot(H1, b1);
-  for (int i = 1; i < rounds; i++) solver.oneRound(correspondences_new, false);  // :98-99
-  const Eigen::Isometry3f X_picp = solver.camera().worldInCameraPose();          // :101 (synchronises)
-  const double ms_picp = ms_since(t0);
-  const int n_inliers = solver.numInliers();
-  const float chi_in = solver.chiInliers();
+  int n_inliers = 0;
+  float chi_in = 0.f;
+  double ms_project = 0, ms_epipolar = 0, ms_triangulate = 0, ms_project2 = 0, ms_transform = 0, ms_picp = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    Camera cam(480, 640, 0, 10, k);
+    Vector2fVector reference_image_points, current_measurements;
+    auto t0 = Clock::now();
+    cam.projectPoints(reference_image_points, world_points_gt, true);  // :65
+    cam.setWorldInCameraPose(X_gt1);
+    cam.projectPoints(current_measurements, world_points_gt, true);    // :67
+    ms_project = ms_since(t0);
+
+    correspondences.clear();
+    fake_correspondences(correspondences, reference_image_points, current_measurements);
+
+    t0 = Clock::now();
+    X_est =
+        estimate_transform(cam.cameraMatrix(), correspondences, reference_image_points, current_measurements);
+    ms_epipolar = ms_since(t0);
+
+    world_points_est.clear();
+    correspondences_new.clear();
+    t0 = Clock::now();
+    triangulate_points(k, X_est, correspondences, reference_image_points, current_measurements, world_points_est,
+                       correspondences_new);  // :78-79
+    ms_triangulate = ms_since(t0);
+
+    cam.setWorldInCameraPose(X_gt2);
+    t0 = Clock::now();
+    cam.projectPoints(current_measurements, world_points_gt, true);  // :87
+    ms_project2 = ms_since(t0);
+
+    SolverAccess solver;
+    solver.setKernelThreshold(10000);
+    t0 = Clock::now();
+    Vector3fVector points_in_cameraframe1;
+    points_in_cameraframe1.reserve(world_points_est.size());
+    for (const auto& p : world_points_est) points_in_cameraframe1.push_back(X_est * p);  // :93-94
+    ms_transform = ms_since(t0);
+
+    cam.setWorldInCameraPose(Eigen::Isometry3f::Identity());
+    t0 = Clock::now();
+    solver.init(cam, points_in_cameraframe1, current_measurements);  // :97
+    solver.oneRound(correspondences_new, false);
+    solver.snapshot(H1, b1);
+    for (int i = 1; i < rounds; i++) solver.oneRound(correspondences_new, false);  // :98-99
+    X_picp = solver.camera().worldInCameraPose();          // :101 (synchronises)
+    ms_picp = ms_since(t0);
+    n_inliers = solver.numInliers();
+    chi_in = solver.chiInliers();
+
+  }
 
   if (FILE* f = std::fopen(dump.c_str(), "wb")) {
     put_i64(f, n);
