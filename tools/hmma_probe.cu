@@ -61,7 +61,65 @@ __global__ void __launch_bounds__(1024) hmma_kernel(int iters, const uint32_t* i
   if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// ---- accuracy of the f16-accumulator mma.sync on the NN filter's operands --------------------------
+// One warp, one m16n8k16: A = 16 query rows, B = 8 map rows (K-major), C = 0.  Fragment layout (PTX ISA):
+// a0:(g, 2t..2t+1) a1:(g+8, 2t..) a2:(g, 2t+8..) a3:(g+8, 2t+8..); b0:(k=2t.., n=g) b1:(k=2t+8.., n=g);
+// d0:(g, 2t..2t+1) d1:(g+8, 2t..2t+1), g = lane/4, t = lane%4.
+#include <cuda_fp16.h>
+__global__ void hmma_acc_kernel(const __half* A /*16x16 row-major*/, const __half* B /*8x16 row-major (n, k)*/,
+                                __half* D /*16x8*/) {
+  const int lane = threadIdx.x, g = lane >> 2, t = lane & 3;
+  auto ld2 = [](const __half* p) { return *reinterpret_cast<const uint32_t*>(p); };
+  uint32_t a[4] = {ld2(A + g * 16 + 2 * t), ld2(A + (g + 8) * 16 + 2 * t), ld2(A + g * 16 + 2 * t + 8),
+                   ld2(A + (g + 8) * 16 + 2 * t + 8)};
+  uint32_t b[2] = {ld2(B + g * 16 + 2 * t), ld2(B + g * 16 + 2 * t + 8)};
+  uint32_t z[2] = {0u, 0u}, d[2];
+  hmma16(d, a, b, z);
+  *reinterpret_cast<uint32_t*>(D + g * 8 + 2 * t) = d[0];
+  *reinterpret_cast<uint32_t*>(D + (g + 8) * 8 + 2 * t) = d[1];
+}
+static unsigned rs = 777u;
+static float frand() { rs = rs * 1664525u + 1013904223u; return (float)((rs >> 8) & 0xFFFFFF) / 8388608.f - 1.f; }
+static void split16(float x, __half* hi, __half* lo) { const __half h = __float2half_rn(x); *hi = h; *lo = __float2half_rn(x - __half2float(h)); }
+static void acc_check() {
+  __half *dA, *dB, *dD;
+  CK(cudaMalloc(&dA, 512)); CK(cudaMalloc(&dB, 256)); CK(cudaMalloc(&dD, 256));
+  double worst = 0.0, worst_near = 0.0;
+  long long n = 0;
+  for (int tile = 0; tile < 2000; ++tile) {
+    __half A[256], B[128], D[128];
+    float q[16][10], m[8][10];
+    for (auto& r : q) for (float& v : r) v = frand();
+    for (int j = 0; j < 8; ++j) for (int k = 0; k < 10; ++k) m[j][k] = (j & 1) ? q[j][k] + 0.02f * frand() : frand();
+    for (int i = 0; i < 16; ++i) {
+      float qq = 0; for (int k = 0; k < 10; ++k) { A[i * 16 + k] = __float2half_rn(-2.f * q[i][k]); qq += q[i][k] * q[i][k]; }
+      A[i * 16 + 10] = A[i * 16 + 11] = __float2half_rn(1.f); split16(qq, &A[i * 16 + 12], &A[i * 16 + 13]);
+      A[i * 16 + 14] = A[i * 16 + 15] = __float2half_rn(0.f);
+    }
+    for (int j = 0; j < 8; ++j) {
+      float mm = 0; for (int k = 0; k < 10; ++k) { B[j * 16 + k] = __float2half_rn(m[j][k]); mm += m[j][k] * m[j][k]; }
+      split16(mm, &B[j * 16 + 10], &B[j * 16 + 11]); B[j * 16 + 12] = B[j * 16 + 13] = __float2half_rn(1.f);
+      B[j * 16 + 14] = B[j * 16 + 15] = __float2half_rn(0.f);
+    }
+    CK(cudaMemcpy(dA, A, 512, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, B, 256, cudaMemcpyHostToDevice));
+    hmma_acc_kernel<<<1, 32>>>(dA, dB, dD);
+    CK(cudaMemcpy(D, dD, 256, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 16; ++i) for (int j = 0; j < 8; ++j) {
+      double exact = 0, sum_abs = 0;
+      for (int k = 0; k < 16; ++k) { const double t = (double)__half2float(A[i * 16 + k]) * (double)__half2float(B[j * 16 + k]); exact += t; sum_abs += fabs(t); }
+      const double e = fabs((double)__half2float(D[i * 8 + j]) - exact) - (fabs(exact) * 4.8828125e-4 + 3e-8);
+      const double r = e / sum_abs;
+      if (r > worst) worst = r;
+      if (fabs(exact) < 0.05 && r > worst_near) worst_near = r;
+      ++n;
+    }
+  }
+  printf("{\"probe\": \"mma.sync f16-accumulator accuracy\", \"elements\": %lld, "
+         "\"max_err_beyond_half_ulp_over_sum_abs_terms\": %.3g, \"same_for_results_near_zero\": %.3g}\n", n, worst, worst_near);
+}
+
 int main() {
+  acc_check();
   int sms = 0;
   CK(cudaSetDevice(0));
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));

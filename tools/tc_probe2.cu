@@ -269,6 +269,71 @@ __global__ void __launch_bounds__(512) ldtm16_kernel(int iters, int cols, uint32
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ---- (4) do tcgen05.mma and the legacy mma.sync share the tensor datapath? --------------------------
+// Thread 0 issues n_mma f16 MMAs (128 x 256 x 16, f16 accumulators) back to back; warps 4.. run
+// mma.sync.m16n8k16 (f16 accumulators) loops.  MODE 1: tcgen05 only, 2: mma.sync only, 3: both.
+__device__ __forceinline__ void hmma16(uint32_t (&d)[2], const uint32_t (&a)[4], const uint32_t (&b)[2], const uint32_t (&c)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f16.f16.f16.f16 {%0,%1}, {%2,%3,%4,%5}, {%6,%7}, {%8,%9};"
+               : "=r"(d[0]), "=r"(d[1]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(c[0]), "r"(c[1]));
+}
+template <int MODE>
+__global__ void __launch_bounds__(640) contend_kernel(int n_mma, int hmma_iters, const uint32_t* in, uint32_t* sink,
+                                                      long long* cyc_tc, long long* cyc_hmma) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 16384 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base;
+  if (tid == 0 && (MODE & 1)) {
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 4096);
+    const uint32_t idesc = make_idesc(0, 128, 256);
+    const long long t0 = clock64();
+    for (int i = 0; i < n_mma; ++i)
+      tc_mma_f16(tb + (uint32_t)(i & 1) * 256, make_desc(a0, 128, 256), make_desc(b0, 128, 256), idesc);
+    tc_commit(&bar);
+    mbar_wait_bounded(&bar, 0, 2000000000LL);
+    cyc_tc[blockIdx.x] = clock64() - t0;
+  }
+  if (warp >= 4 && (MODE & 2)) {
+    uint32_t a[8][4], b[2], z[2] = {0u, 0u}, mn[8];
+    for (int i = 0; i < 8; ++i) {
+      for (int k = 0; k < 4; ++k) a[i][k] = in[(tid + i * 4 + k) & 63];
+      mn[i] = 0;
+    }
+    b[0] = in[tid & 63];
+    b[1] = in[(tid + 7) & 63];
+    const long long t0 = clock64();
+    for (int it = 0; it < hmma_iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint32_t d[2];
+        hmma16(d, a[i], b, z);
+        mn[i] ^= d[0] ^ d[1];
+      }
+      b[0] += 0x00010001u;
+    }
+    const long long t1 = clock64();
+    uint32_t sacc = 0;
+    for (int i = 0; i < 8; ++i) sacc ^= mn[i];
+    if (sacc == 0x12345678u) sink[0] = sacc;
+    if ((tid & 31) == 0) atomicMax((unsigned long long*)&cyc_hmma[blockIdx.x], (unsigned long long)(t1 - t0));
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
 static uint32_t rng_state = 12345u;
 static float frand() {  // uniform in [-1, 1)
   rng_state = rng_state * 1664525u + 1013904223u;
@@ -455,5 +520,32 @@ int main() {
       printf("{\"probe\": \"ldtm16\", \"mode\": \"%s\", \"warps\": %d, \"elems_per_clk_per_sm\": %.1f}\n",
              mode == 0 ? "pack16+VIMNMX3.S16x2" : "f32+FMNMX3", warps, elems / mx);
     }
+
+  // (4) contention between the two tensor paths
+  {
+    long long *cyc_tc, *cyc_h;
+    CK(cudaMalloc(&cyc_tc, 8 * 1024));
+    CK(cudaMalloc(&cyc_h, 8 * 1024));
+    const int n_mma = 4000, hit = 2000, hwarps = 16;
+    for (int mode = 1; mode <= 3; ++mode) {
+      for (int rep = 0; rep < 2; ++rep) {
+        CK(cudaMemset(cyc_tc, 0, 8 * 1024));
+        CK(cudaMemset(cyc_h, 0, 8 * 1024));
+        if (mode == 1) contend_kernel<1><<<sms, (4 + hwarps) * 32, 16384>>>(n_mma, hit, din, sink, cyc_tc, cyc_h);
+        else if (mode == 2) contend_kernel<2><<<sms, (4 + hwarps) * 32, 16384>>>(n_mma, hit, din, sink, cyc_tc, cyc_h);
+        else contend_kernel<3><<<sms, (4 + hwarps) * 32, 16384>>>(n_mma, hit, din, sink, cyc_tc, cyc_h);
+        CK(cudaDeviceSynchronize());
+      }
+      std::vector<long long> a(sms), b(sms);
+      CK(cudaMemcpy(a.data(), cyc_tc, 8 * sms, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(b.data(), cyc_h, 8 * sms, cudaMemcpyDeviceToHost));
+      long long ma = 0, mb = 0;
+      for (int i = 0; i < sms; ++i) { ma = a[i] > ma ? a[i] : ma; mb = b[i] > mb ? b[i] : mb; }
+      printf("{\"probe\": \"contend\", \"mode\": \"%s\", \"tcgen05_mac_per_clk_per_sm\": %.0f, "
+             "\"mma_sync_mac_per_clk_per_sm\": %.0f}\n",
+             mode == 1 ? "tcgen05 only" : (mode == 2 ? "mma.sync only" : "both"),
+             ma ? (double)n_mma * 128 * 256 * 16 / ma : 0.0, mb ? (double)hit * 8 * hwarps * 2048 / mb : 0.0);
+    }
+  }
   return 0;
 }
