@@ -40,7 +40,10 @@ namespace vo {
 #define PICP_DEPTH_N 3
 #endif
 constexpr int PICP_THREADS = PICP_THREADS_N;
-constexpr int PICP_UNROLL = 4;
+#ifndef PICP_UNROLL_N
+#define PICP_UNROLL_N 4
+#endif
+constexpr int PICP_UNROLL = PICP_UNROLL_N;
 constexpr int PICP_NACC = 32;  // 21 H + 6 b + chi_in + chi_out + n_in (as float bits of int) + 2 pad
 
 struct PicpDeviceState {
